@@ -1,0 +1,673 @@
+// C ABI of magpy_rv_b200 (see include/magpy_rv_b200.h): problem handle, path selection, host loop of
+// the blocked factorisation, dense helpers, FP64 tensor-pipe microbenchmark.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/magpy_rv_b200.h"
+#include "blocked.cuh"
+#include "common.cuh"
+#include "dense_ops.cuh"
+#include "mean_model.cuh"
+#include "small_logl.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) return fail(-2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define SMALL_N_MAX 168
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMalloc(&p, need);
+    if (e != cudaSuccess) return fail(-3, "cudaMalloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
+    bytes = need;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct mrv_problem {
+  int device = 0;
+  ProblemDesc desc;
+  bool has_kepler = false;
+  int n_pad = 0, nt = 0;
+  double *d_t = nullptr, *d_y = nullptr, *d_yerr = nullptr, *d_flags = nullptr;
+  cudaStream_t stream = nullptr;  // used by the host-pointer entry points
+  // options
+  int path_opt = MRV_PATH_AUTO;
+  int64_t wave_opt = 0;
+  int panel_opt = 0;
+  // workspace
+  DevBuf hp, modpar, model, logl, status;                      // host-API staging
+  DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor;
+  int64_t wave_cur = 0;
+  int64_t launches = 0;
+  int last_path = 0;
+  bool attrs_set = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+extern "C" const char* mrv_last_error(void) { return g_err.c_str(); }
+extern "C" int mrv_abi_version(void) { return MRV_ABI_VERSION; }
+extern "C" int mrv_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static int require_device(int device) {
+  int n = mrv_device_count();
+  if (n <= 0) return fail(-4, "no CUDA device available (magpy_rv_b200 has no CPU fallback)");
+  if (device < 0 || device >= n) return fail(-4, "device %d out of range (have %d)", device, n);
+  CU(cudaSetDevice(device));
+  return 0;
+}
+
+static int kernel_nh(int id) {
+  static const int nh[7] = {2, 2, 3, 4, 5, 2, 3};
+  return (id >= 0 && id < 7) ? nh[id] : -1;
+}
+
+static int fill_desc(ProblemDesc& D, int64_t N, int kernel_id, int variant, int nh, const mrv_model_op* ops, int n_ops,
+                     int nm, const mrv_prior* priors, int n_priors) {
+  if (N <= 0 || N > (1 << 20)) return fail(-1, "N=%lld out of range", (long long)N);
+  if (kernel_nh(kernel_id) < 0) return fail(-1, "unknown kernel id %d", kernel_id);
+  if (nh != kernel_nh(kernel_id)) return fail(-1, "kernel %d needs %d hyper-parameters, got %d", kernel_id, kernel_nh(kernel_id), nh);
+  if (n_ops < 0 || n_ops > MRV_MAX_OPS) return fail(-1, "n_ops=%d out of range (max %d)", n_ops, MRV_MAX_OPS);
+  if (nm < 0 || nm > MRV_MAX_MODPAR) return fail(-1, "nm=%d out of range (max %d)", nm, MRV_MAX_MODPAR);
+  if (n_priors < 0 || n_priors > MRV_MAX_PRIORS) return fail(-1, "n_priors=%d out of range (max %d)", n_priors, MRV_MAX_PRIORS);
+  memset(&D, 0, sizeof D);
+  D.N = (int)N;
+  D.kernel_id = kernel_id;
+  D.variant = variant;
+  D.nh = nh;
+  D.nm = nm;
+  D.n_ops = n_ops;
+  D.n_priors = n_priors;
+  static const int npar[4] = {1, 4, 1, 5};
+  for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].type < 0 || ops[i].type > 3) return fail(-1, "unknown model op type %d", ops[i].type);
+    if (ops[i].param_offset < 0 || ops[i].param_offset + npar[ops[i].type] > nm)
+      return fail(-1, "model op %d reads parameters [%d,%d) outside nm=%d", i, ops[i].param_offset,
+                  ops[i].param_offset + npar[ops[i].type], nm);
+    D.ops[i].type = ops[i].type;
+    D.ops[i].param_offset = ops[i].param_offset;
+    D.ops[i].flag_val = ops[i].flag_val;
+  }
+  for (int i = 0; i < n_priors; ++i) {
+    if (priors[i].type < 0 || priors[i].type > 3) return fail(-1, "unknown prior type %d", priors[i].type);
+    const int lim = priors[i].source == 0 ? nh : nm;
+    if (priors[i].source < 0 || priors[i].source > 1 || priors[i].index < 0 || priors[i].index >= lim)
+      return fail(-1, "prior %d refers to parameter %d of source %d (limit %d)", i, priors[i].index, priors[i].source, lim);
+    D.priors[i].type = priors[i].type;
+    D.priors[i].source = priors[i].source;
+    D.priors[i].index = priors[i].index;
+    D.priors[i].p0 = priors[i].p0;
+    D.priors[i].p1 = priors[i].p1;
+    D.priors[i].p2 = priors[i].p2;
+  }
+  return 0;
+}
+
+static int upload(double** dst, const double* src, size_t n) {
+  CU(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(double)));
+  CU(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int mrv_problem_create(mrv_problem** out, int device, const double* t, const double* y, const double* yerr,
+                                  const double* flags, int64_t N, int kernel_id, int kernel_variant, int nh,
+                                  const mrv_model_op* ops, int n_ops, int nm, const mrv_prior* priors, int n_priors) {
+  if (!out || !t || !y || !yerr) return fail(-1, "null argument");
+  *out = nullptr;
+  if (int rc = require_device(device)) return rc;
+  mrv_problem* p = new (std::nothrow) mrv_problem();
+  if (!p) return fail(-3, "out of host memory");
+  p->device = device;
+  if (int rc = fill_desc(p->desc, N, kernel_id, kernel_variant, nh, ops, n_ops, nm, priors, n_priors)) {
+    delete p;
+    return rc;
+  }
+  for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].type == MRV_MODEL_KEPLER) p->has_kepler = true;
+    if (ops[i].type == MRV_MODEL_OFFSET && !flags) {
+      delete p;
+      return fail(-1, "an OFFSET model op needs a flags array");
+    }
+  }
+  p->nt = (int)((N + TILE - 1) / TILE);
+  p->n_pad = p->nt * TILE;
+  int rc = 0;
+  if ((rc = upload(&p->d_t, t, N)) || (rc = upload(&p->d_y, y, N)) || (rc = upload(&p->d_yerr, yerr, N)) ||
+      (flags && (rc = upload(&p->d_flags, flags, N)))) {
+    mrv_problem_destroy(p);
+    return rc;
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    mrv_problem_destroy(p);
+    return fail(-2, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+  }
+  *out = p;
+  return 0;
+}
+
+extern "C" void mrv_problem_destroy(mrv_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaFree(p->d_t);
+  cudaFree(p->d_y);
+  cudaFree(p->d_yerr);
+  cudaFree(p->d_flags);
+  DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
+                    &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor};
+  for (DevBuf* b : bufs) b->release();
+  if (p->stream) cudaStreamDestroy(p->stream);
+  delete p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel attribute setup (opt-in shared memory sizes), once per process per device is enough but it
+// is cheap, so once per handle.
+// ------------------------------------------------------------------------------------------------
+static int set_attrs(mrv_problem* p) {
+  if (p->attrs_set) return 0;
+  CU(cudaFuncSetAttribute(fused_small_logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
+  p->attrs_set = true;
+  return 0;
+}
+
+static int choose_path(const mrv_problem* p) {
+  if (p->path_opt == MRV_PATH_FUSED_SMEM) return MRV_PATH_FUSED_SMEM;
+  if (p->path_opt == MRV_PATH_BLOCKED) return MRV_PATH_BLOCKED;
+  return p->desc.N <= SMALL_N_MAX ? MRV_PATH_FUSED_SMEM : MRV_PATH_BLOCKED;
+}
+
+// Blocked path for one wave of `B` walkers starting at walker w0.
+static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st) {
+  const ProblemDesc& D = p->desc;
+  const int nt = p->nt, N = D.N;
+  const size_t walker_stride = tile_index(nt - 1, nt - 1) * TILE_ELEMS + TILE_ELEMS;
+  double* A = p->factor.as<double>();
+  double* resid = p->resid.as<double>() + (size_t)w0 * p->n_pad;
+  double* zbuf = p->zbuf.as<double>();
+  double* logdet = p->logdet.as<double>() + w0;
+  double* quad = p->quad.as<double>() + w0;
+  int* fstatus = p->fstatus.as<int>() + w0;
+  const double* hp_wave = d_hp + (size_t)w0 * D.nh;
+  const int PW = std::max(1, p->panel_opt > 0 ? p->panel_opt : 1);
+
+  GemmArgs g;
+  memset(&g, 0, sizeof g);
+  g.N = N;
+  g.nt = nt;
+  g.kernel_id = D.kernel_id;
+  g.variant = D.variant;
+  g.nh = D.nh;
+  g.Abase = A;
+  g.walker_stride = walker_stride;
+  g.t = p->d_t;
+  g.yerr = p->d_yerr;
+  g.hp_wave = hp_wave;
+  g.resid = resid;
+  g.ldr = p->n_pad;
+  g.zbuf = zbuf;
+
+  auto tiles_in_cols = [&](int c0, int c1) {
+    long long n = 0;
+    for (int j = c0; j < c1; ++j) n += nt - j;
+    return (unsigned)n;
+  };
+
+  gen_column_kernel<<<dim3(nt, (unsigned)B), 256, 0, st>>>(N, nt, 0, D.kernel_id, D.variant, D.nh, p->d_t, p->d_yerr,
+                                                            hp_wave, A, walker_stride);
+  p->launches++;
+  for (int p0 = 0; p0 < nt; p0 += PW) {
+    const int p1 = std::min(p0 + PW, nt);
+    for (int k = p0; k < p1; ++k) {
+      if (k > p0) {  // bring column k up to date with the part of this panel already factored
+        g.mode = GEMM_UPDATE;
+        g.col_begin = k;
+        g.col_end = k + 1;
+        g.p_begin = p0;
+        g.p_end = k;
+        g.gen = (p0 == 0);
+        gemm_tile_kernel<<<dim3(tiles_in_cols(k, k + 1), (unsigned)B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+        p->launches++;
+      }
+      potrf_tile_kernel<<<(unsigned)B, 256, POTRF_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad, zbuf,
+                                                                    logdet, quad, fstatus);
+      p->launches++;
+      if (k + 1 < nt) {
+        g.mode = GEMM_TRSM;
+        g.k = k;
+        gemm_tile_kernel<<<dim3(nt - k - 1, (unsigned)B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+        p->launches++;
+      }
+    }
+    if (p1 < nt) {
+      g.mode = GEMM_UPDATE;
+      g.col_begin = p1;
+      g.col_end = nt;
+      g.p_begin = p0;
+      g.p_end = p1;
+      g.gen = (p0 == 0);
+      gemm_tile_kernel<<<dim3(tiles_in_cols(p1, nt), (unsigned)B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+      p->launches++;
+    }
+  }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// Core: everything on device, asynchronous on `st`.
+static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, const double* d_model_given, int64_t W,
+                    int to_ecc, double* d_logl, int* d_status, cudaStream_t st) {
+  if (W <= 0) return 0;
+  if (W > 65535 * 64) return fail(-1, "W=%lld too large", (long long)W);
+  CU(cudaSetDevice(p->device));
+  if (int rc = set_attrs(p)) return rc;
+  const ProblemDesc& D = p->desc;
+  const int path = choose_path(p);
+  p->last_path = path;
+  if (path == MRV_PATH_FUSED_SMEM) {
+    if (D.N > SMALL_N_MAX) return fail(-1, "fused shared-memory path needs N <= %d (N=%d)", SMALL_N_MAX, D.N);
+    const size_t smem = small_smem_bytes(D.N);
+    fused_small_logl_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp,
+                                                                          d_modpar, d_model_given, to_ecc, d_logl,
+                                                                          d_status);
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+  }
+
+  // ---- blocked path ----
+  const int nt = p->nt;
+  const size_t walker_bytes = (tile_index(nt - 1, nt - 1) + 1) * TILE_ELEMS * sizeof(double);
+  int64_t B = p->wave_opt;
+  if (B <= 0) {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    free_b += p->factor.bytes;  // what we already hold can be reused
+    size_t budget = std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)40 << 30);
+    B = (int64_t)std::max<size_t>(1, budget / walker_bytes);
+  }
+  B = std::min<int64_t>(B, W);
+  B = std::min<int64_t>(B, 65535);
+  p->wave_cur = B;
+  int rc = 0;
+  if ((rc = p->resid.ensure((size_t)W * p->n_pad * sizeof(double)))) return rc;
+  if (p->has_kepler && (rc = p->escratch.ensure((size_t)W * p->n_pad * sizeof(double)))) return rc;
+  if ((rc = p->phys.ensure(std::max<size_t>(1, (size_t)W * D.nm) * sizeof(double)))) return rc;
+  if ((rc = p->nonfinite.ensure((size_t)W * sizeof(int)))) return rc;
+  if ((rc = p->logdet.ensure((size_t)W * sizeof(double)))) return rc;
+  if ((rc = p->quad.ensure((size_t)W * sizeof(double)))) return rc;
+  if ((rc = p->fstatus.ensure((size_t)W * sizeof(int)))) return rc;
+  if ((rc = p->zbuf.ensure((size_t)B * TILE * sizeof(double)))) return rc;
+  if ((rc = p->factor.ensure((size_t)B * walker_bytes))) return rc;
+
+  CU(cudaMemsetAsync(p->logdet.p, 0, (size_t)W * sizeof(double), st));
+  CU(cudaMemsetAsync(p->quad.p, 0, (size_t)W * sizeof(double), st));
+  CU(cudaMemsetAsync(p->fstatus.p, 0, (size_t)W * sizeof(int), st));
+  mean_residual_kernel<<<(unsigned)W, 256, 0, st>>>(D, p->d_t, p->d_y, p->d_flags, d_modpar, d_model_given, to_ecc,
+                                                    p->resid.as<double>(), p->n_pad, p->escratch.as<double>(),
+                                                    p->phys.as<double>(), p->nonfinite.as<int>());
+  p->launches++;
+  CU(cudaGetLastError());
+  for (int64_t w0 = 0; w0 < W; w0 += B) {
+    if ((rc = run_wave(p, d_hp, w0, std::min<int64_t>(B, W - w0), st))) return rc;
+  }
+  finalize_logl_kernel<<<(unsigned)((W + 127) / 128), 128, 0, st>>>(D, (int)W, d_hp, p->phys.as<double>(),
+                                                                    p->logdet.as<double>(), p->quad.as<double>(),
+                                                                    p->nonfinite.as<int>(), p->fstatus.as<int>(), d_logl,
+                                                                    d_status);
+  p->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mrv_logl_batch_device(mrv_problem* p, const double* d_hp, const double* d_modpar, int64_t W, int to_ecc,
+                                     double* d_logL_out, int32_t* d_status_out, void* stream) {
+  if (!p || !d_hp || !d_modpar || !d_logL_out || !d_status_out) return fail(-1, "null argument");
+  return run_logl(p, d_hp, d_modpar, nullptr, W, to_ecc, d_logL_out, d_status_out, (cudaStream_t)stream);
+}
+
+static int host_logl(mrv_problem* p, const double* hp, const double* modpar, const double* model_y, int64_t W, int to_ecc,
+                     double* logL_out, int32_t* status_out) {
+  if (!p || !hp || !modpar || !logL_out || !status_out) return fail(-1, "null argument");
+  if (W <= 0) return 0;
+  CU(cudaSetDevice(p->device));
+  const ProblemDesc& D = p->desc;
+  int rc = 0;
+  if ((rc = p->hp.ensure((size_t)W * D.nh * sizeof(double)))) return rc;
+  if ((rc = p->modpar.ensure(std::max<size_t>(1, (size_t)W * D.nm) * sizeof(double)))) return rc;
+  if ((rc = p->logl.ensure((size_t)W * sizeof(double)))) return rc;
+  if ((rc = p->status.ensure((size_t)W * sizeof(int)))) return rc;
+  cudaStream_t st = p->stream;
+  CU(cudaMemcpyAsync(p->hp.p, hp, (size_t)W * D.nh * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (D.nm > 0) CU(cudaMemcpyAsync(p->modpar.p, modpar, (size_t)W * D.nm * sizeof(double), cudaMemcpyHostToDevice, st));
+  const double* d_model = nullptr;
+  if (model_y) {
+    if ((rc = p->model.ensure((size_t)W * D.N * sizeof(double)))) return rc;
+    CU(cudaMemcpyAsync(p->model.p, model_y, (size_t)W * D.N * sizeof(double), cudaMemcpyHostToDevice, st));
+    d_model = p->model.as<double>();
+  }
+  if ((rc = run_logl(p, p->hp.as<double>(), p->modpar.as<double>(), d_model, W, to_ecc, p->logl.as<double>(),
+                     p->status.as<int>(), st)))
+    return rc;
+  CU(cudaMemcpyAsync(logL_out, p->logl.p, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(status_out, p->status.p, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int mrv_logl_batch(mrv_problem* p, const double* hp, const double* modpar, int64_t W, int to_ecc,
+                              double* logL_out, int32_t* status_out) {
+  return host_logl(p, hp, modpar, nullptr, W, to_ecc, logL_out, status_out);
+}
+
+extern "C" int mrv_logl_given_model(mrv_problem* p, const double* hp, const double* modpar, const double* model_y,
+                                    int64_t W, double* logL_out, int32_t* status_out) {
+  if (!model_y) return fail(-1, "null model_y");
+  return host_logl(p, hp, modpar, model_y, W, 0, logL_out, status_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int mrv_model_eval(int device, const double* t, const double* flags, int64_t N, const mrv_model_op* ops,
+                              int n_ops, int nm, const double* modpar, int64_t W, int to_ecc, double* model_out,
+                              double* modpar_phys_out) {
+  if (!t || !modpar || !model_out) return fail(-1, "null argument");
+  if (int rc = require_device(device)) return rc;
+  ProblemDesc D;
+  if (int rc = fill_desc(D, N, 0, 0, 2, ops, n_ops, nm, nullptr, 0)) return rc;
+  bool kep = false;
+  for (int i = 0; i < n_ops; ++i) {
+    if (ops[i].type == MRV_MODEL_OFFSET && !flags) return fail(-1, "an OFFSET model op needs a flags array");
+    kep |= ops[i].type == MRV_MODEL_KEPLER;
+  }
+  if (W <= 0) return 0;
+  double *d_t = nullptr, *d_f = nullptr, *d_mp = nullptr, *d_out = nullptr, *d_E = nullptr, *d_phys = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaFree(d_t);
+    cudaFree(d_f);
+    cudaFree(d_mp);
+    cudaFree(d_out);
+    cudaFree(d_E);
+    cudaFree(d_phys);
+  };
+  if ((rc = upload(&d_t, t, N)) || (flags && (rc = upload(&d_f, flags, N))) ||
+      (rc = upload(&d_mp, modpar, (size_t)W * nm))) {
+    cleanup();
+    return rc;
+  }
+  cudaError_t e = cudaMalloc((void**)&d_out, (size_t)W * N * sizeof(double));
+  if (e == cudaSuccess && kep) e = cudaMalloc((void**)&d_E, (size_t)W * N * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_phys, std::max<size_t>(1, (size_t)W * nm) * sizeof(double));
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(-3, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  mean_residual_kernel<<<(unsigned)W, 256>>>(D, d_t, nullptr, d_f, d_mp, nullptr, to_ecc, d_out, (int)N, d_E, d_phys,
+                                             nullptr);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(model_out, d_out, (size_t)W * N * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && modpar_phys_out && nm > 0)
+    e = cudaMemcpy(modpar_phys_out, d_phys, (size_t)W * nm * sizeof(double), cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(-2, "mrv_model_eval: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+static int dense_cov(int device, int kernel_id, int variant, const double* hp, int nh, const double* x1, const double* x2,
+                     const double* dist_e, const double* dist_se, int64_t n1, int64_t n2, int diag_mode,
+                     const double* diag_add, double* K_out) {
+  if (!hp || !K_out) return fail(-1, "null argument");
+  if (kernel_nh(kernel_id) < 0 || nh != kernel_nh(kernel_id)) return fail(-1, "kernel %d needs %d hyper-parameters, got %d", kernel_id, kernel_nh(kernel_id), nh);
+  if ((diag_mode & 2) && !diag_add) return fail(-1, "diag_mode bit 1 needs diag_add");
+  if (int rc = require_device(device)) return rc;
+  if (n1 <= 0 || n2 <= 0) return 0;
+  const bool from_dist = dist_e != nullptr;
+  const size_t total = (size_t)n1 * n2;
+  double *d_a = nullptr, *d_b = nullptr, *d_d = nullptr, *d_K = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaFree(d_a);
+    cudaFree(d_b);
+    cudaFree(d_d);
+    cudaFree(d_K);
+  };
+  if (from_dist) {
+    if ((rc = upload(&d_a, dist_e, total)) || (rc = upload(&d_b, dist_se, total))) {
+      cleanup();
+      return rc;
+    }
+  } else {
+    if ((rc = upload(&d_a, x1, n1)) || (rc = upload(&d_b, x2, n2))) {
+      cleanup();
+      return rc;
+    }
+  }
+  if ((diag_mode & 2) && (rc = upload(&d_d, diag_add, n2))) {
+    cleanup();
+    return rc;
+  }
+  cudaError_t e = cudaMalloc((void**)&d_K, total * sizeof(double));
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(-3, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  const CovParams cp = make_cov_params(kernel_id, variant, hp);
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  covmatrix_kernel<<<blocks, 256>>>(cp, from_dist ? 1 : 0, d_a, n1, d_b, n2, d_a, d_b, diag_mode, d_d, d_K);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(K_out, d_K, total * sizeof(double), cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(-2, "covmatrix: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int mrv_covmatrix(int device, int kernel_id, int kernel_variant, const double* hp, int nh, const double* x1,
+                             int64_t n1, const double* x2, int64_t n2, int diag_mode, const double* diag_add,
+                             double* K_out) {
+  if (!x1 || !x2) return fail(-1, "null argument");
+  return dense_cov(device, kernel_id, kernel_variant, hp, nh, x1, x2, nullptr, nullptr, n1, n2, diag_mode, diag_add, K_out);
+}
+
+extern "C" int mrv_covmatrix_from_dist(int device, int kernel_id, int kernel_variant, const double* hp, int nh,
+                                       const double* dist_e, const double* dist_se, int64_t n1, int64_t n2, int diag_mode,
+                                       const double* diag_add, double* K_out) {
+  if (!dist_e || !dist_se) return fail(-1, "null argument");
+  return dense_cov(device, kernel_id, kernel_variant, hp, nh, nullptr, nullptr, dist_e, dist_se, n1, n2, diag_mode,
+                   diag_add, K_out);
+}
+
+extern "C" int mrv_distances(int device, const double* t1, int64_t n1, const double* t2, int64_t n2, double* dist_e_out,
+                             double* dist_se_out) {
+  if (!t1 || !t2 || !dist_e_out || !dist_se_out) return fail(-1, "null argument");
+  if (int rc = require_device(device)) return rc;
+  if (n1 <= 0 || n2 <= 0) return 0;
+  const size_t total = (size_t)n1 * n2;
+  double *d_a = nullptr, *d_b = nullptr, *d_e = nullptr, *d_s = nullptr;
+  int rc = 0;
+  auto cleanup = [&]() {
+    cudaFree(d_a);
+    cudaFree(d_b);
+    cudaFree(d_e);
+    cudaFree(d_s);
+  };
+  if ((rc = upload(&d_a, t1, n1)) || (rc = upload(&d_b, t2, n2))) {
+    cleanup();
+    return rc;
+  }
+  cudaError_t e = cudaMalloc((void**)&d_e, total * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_s, total * sizeof(double));
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(-3, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  distances_kernel<<<blocks, 256>>>(d_a, n1, d_b, n2, d_e, d_s);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(dist_e_out, d_e, total * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(dist_se_out, d_s, total * sizeof(double), cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(-2, "distances: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
+  if (!p || !key) return fail(-1, "null argument");
+  if (!strcmp(key, "path")) {
+    if (value < 0 || value > 2) return fail(-1, "path must be 0 (auto), 1 (fused smem) or 2 (blocked)");
+    p->path_opt = (int)value;
+  } else if (!strcmp(key, "wave_walkers")) {
+    p->wave_opt = value;
+  } else if (!strcmp(key, "panel_tiles")) {
+    p->panel_opt = (int)value;
+  } else {
+    return fail(-1, "unknown option '%s'", key);
+  }
+  return 0;
+}
+
+extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
+  if (!p || !key) return -1;
+  if (!strcmp(key, "path")) return p->last_path ? p->last_path : choose_path(p);
+  if (!strcmp(key, "launches")) return p->launches;
+  if (!strcmp(key, "wave_walkers")) return p->wave_cur;
+  if (!strcmp(key, "n_pad")) return p->n_pad;
+  if (!strcmp(key, "small_n_max")) return SMALL_N_MAX;
+  if (!strcmp(key, "workspace_bytes")) {
+    int64_t s = 0;
+    DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
+                      &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor};
+    for (DevBuf* b : bufs) s += (int64_t)b->bytes;
+    return s;
+  }
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 MMA issue-rate microbenchmark: every warp keeps 8 independent m16n8k16 accumulator chains.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double* sink) {
+  double acc[8][4];
+  double a[8], b[4];
+#pragma unroll
+  for (int v = 0; v < 8; ++v) a[v] = 1.0 + 1e-9 * (threadIdx.x + v);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) b[v] = 1.0 - 1e-9 * (threadIdx.x + v);
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[c][v] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dmma_16816(acc[c], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) s += acc[c][v];
+  if (s == 123.456) sink[0] = s;
+}
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(int iters, double* sink) {
+  double acc[16];
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-9;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = (double)c;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = fma(acc[c], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int c = 0; c < 16; ++c) s += acc[c];
+  if (s == 123.456) sink[0] = s;
+}
+
+static double time_peak(int variant, int iters) {
+  double* sink = nullptr;
+  if (cudaMalloc((void**)&sink, 8) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = 148 * 2;
+  double best = -1.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    if (variant == 0) dmma_peak_kernel<<<blocks, 256>>>(iters, sink);
+    else dfma_peak_kernel<<<blocks, 256>>>(iters, sink);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) {
+      best = -1.0;
+      break;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double flops;
+    if (variant == 0) flops = 2.0 * 16 * 8 * 16 * 8.0 * iters * (256 / 32) * blocks;
+    else flops = 2.0 * 16.0 * iters * 256 * blocks;
+    const double rate = flops / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, rate);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return best;
+}
+
+extern "C" double mrv_fp64_mma_peak(int device, int iters) {
+  if (require_device(device)) return -1.0;
+  if (iters <= 0) iters = 20000;
+  return time_peak(0, iters);
+}
+
+extern "C" double mrv_fp64_fma_peak(int device, int iters) {
+  if (require_device(device)) return -1.0;
+  if (iters <= 0) iters = 20000;
+  return time_peak(1, iters);
+}

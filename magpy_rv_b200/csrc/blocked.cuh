@@ -1,0 +1,402 @@
+// Blocked right-looking Cholesky for large N, batched over a wave of walkers.
+//
+// Storage (per walker): lower-triangular TILES of 128 x 128 doubles, tile (i, j), i >= j, at index
+// i(i+1)/2 + j; N is padded to nt*128 with an identity block (unit diagonal, zero residual) so the
+// padding contributes nothing to log det or the quadratic form.  Inside a tile the elements are in
+// "operand order": element (r, c) lives at ((c>>2)*16 + (r>>3))*32 + (r&7)*4 + (c&3).  With that
+// one layout
+//   * a k16 slice (16 consecutive c) of a tile is 16 KiB contiguous -> one bulk copy into smem,
+//   * a warp's m16n8k16 DMMA A/B fragment loads are 32 consecutive doubles (conflict-free LDS.64),
+//   * the accumulator fragment (row g / g+8, cols 2*tig, 2*tig+1) maps to aligned 16-byte
+//     global accesses, so an updated C tile is directly usable as an operand later.
+//
+// Per tile-column k (host loop in abi.cu):
+//   potrf_tile_kernel   one CTA per walker: Gauss-Jordan sweep of tile (k,k) in smem gives the
+//                       pivots, inv(L_kk) (written back over the tile) and z_k = L_kk^-1 r_k;
+//                       accumulates log det and z^T z; records the LAPACK-style status.
+//   gemm_tile_kernel<TRSM>    X = C(i,k) * inv(L_kk)^T on the FP64 tensor pipe (DMMA), written
+//                       back as L(i,k); fused GEMV r_i -= L(i,k) z_k.
+//   gemm_tile_kernel<UPDATE>  C(i,j) -= sum_p L(i,p) L(j,p)^T over a panel of tile columns; on
+//                       first touch C(i,j) is GENERATED from t / yerr instead of loaded (the
+//                       covariance matrix is never materialised by a separate pass).
+#pragma once
+#include "mean_model.cuh"
+
+#define TILE 128
+#define TILE_ELEMS (TILE * TILE)
+#define KSLICE 16
+#define SLICE_ELEMS (TILE * KSLICE)       // 2048 doubles = 16 KiB
+#define SLICES_PER_TILE (TILE / KSLICE)   // 8
+#define GEMM_THREADS 256
+#define GEMM_STAGES 3
+
+__host__ __device__ __forceinline__ size_t tile_index(int i, int j) { return (size_t)i * (i + 1) / 2 + j; }
+__host__ __device__ __forceinline__ int tile_off(int r, int c) {
+  return (((c >> 2) * 16 + (r >> 3)) << 5) + ((r & 7) << 2) + (c & 3);
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-core MMA (DMMA): D(16x8) += A(16x16) * B(16x8), fragments as in the PTX ISA
+//   a[v]: row = g + 8*(v&1), col = tig + 4*(v>>1);  b[v]: k = tig + 4*v, n = g;
+//   c[v]: row = g + 8*(v>>1), col = 2*tig + (v&1);   g = lane>>2, tig = lane&3.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_16816(double (&d)[4], const double (&a)[8], const double (&b)[4]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, "
+      "{%12,%13,%14,%15}, {%0,%1,%2,%3};\n"
+      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+      : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]),
+        "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// ------------------------------------------------------------------------------------------------
+// Covariance value of global element (gi, gj) of the padded matrix.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gen_element(const CovParams& cp, int N, int gi, int gj, double ti, double tj,
+                                              const double* __restrict__ yerr) {
+  if (gi < N && gj < N) return (gi == gj) ? cov_diag(cp, yerr[gi]) : cov_eval(cp, ti, tj);
+  return (gi == gj) ? 1.0 : 0.0;
+}
+
+// Write the covariance tiles of tile-column `col` for every walker of the wave (needed before
+// potrf/trsm touch a column that no UPDATE has generated yet, i.e. column 0).
+__global__ void __launch_bounds__(256)
+gen_column_kernel(int N, int nt, int col, int kernel_id, int variant, int nh, const double* __restrict__ t,
+                  const double* __restrict__ yerr, const double* __restrict__ hp_wave, double* __restrict__ Abase,
+                  size_t walker_stride) {
+  __shared__ double ti_s[TILE], tj_s[TILE];
+  const int i = col + blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  if (tid < TILE) {
+    const int gi = i * TILE + tid, gj = col * TILE + tid;
+    ti_s[tid] = gi < N ? t[gi] : 0.0;
+    tj_s[tid] = gj < N ? t[gj] : 0.0;
+  }
+  __syncthreads();
+  const CovParams cp = make_cov_params(kernel_id, variant, hp_wave + (size_t)b * nh);
+  double* tile = Abase + (size_t)b * walker_stride + tile_index(i, col) * TILE_ELEMS;
+  for (int e = tid; e < TILE_ELEMS; e += 256) {
+    const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7, k3 = e & 3;
+    const int R = m8 * 8 + g, C = kg * 4 + k3;
+    tile[e] = gen_element(cp, N, i * TILE + R, col * TILE + C, ti_s[R], tj_s[C], yerr);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Diagonal tile: pivots, inverse factor, partial forward solve.  One CTA (256 threads) per walker.
+// smem: (TILE+1) x TILE column-major, ld = 129 (row 128 carries the residual block r_k).
+//
+// Gauss-Jordan sweep (square-root free): for j = 0..127, with w = 1/S[j][j] and beta_c = S[c][j]*w:
+//     rows rho < j   (inverse part)   S[rho][c] -= S[rho][j] * beta_c      c > j
+//     row  rho = j                    S[j][c]    = -beta_c                 c > j
+//     rows rho >= c  (factor part, incl. the residual row)  S[rho][c] -= S[rho][j] * beta_c
+// Afterwards, with d_c = S[c][c]:  L[i][c] = S[i][c]/sqrt(d_c) (i > c),
+//     inv(L)[c][q] = S[q][c]/sqrt(d_c) (q < c), inv(L)[c][c] = 1/sqrt(d_c), z_c = S[128][c]/sqrt(d_c).
+// ------------------------------------------------------------------------------------------------
+#define POTRF_LD (TILE + 1)
+#define POTRF_SMEM_BYTES ((size_t)POTRF_LD * TILE * sizeof(double) + (64 + TILE) * sizeof(double))
+
+__global__ void __launch_bounds__(256)
+potrf_tile_kernel(int k, int N, double* __restrict__ Abase, size_t walker_stride, double* __restrict__ resid,
+                  int ldr, double* __restrict__ zbuf, double* __restrict__ acc_logdet,
+                  double* __restrict__ acc_quad, int* __restrict__ status) {
+  extern __shared__ double smem[];
+  double* S = smem;
+  double* red = smem + (size_t)POTRF_LD * TILE;
+  int* ired = (int*)(red + 32);
+  double* isd_s = red + 64;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nwarps = 8;
+  double* tile = Abase + (size_t)b * walker_stride + tile_index(k, k) * TILE_ELEMS;
+  double* rk = resid + (size_t)b * ldr + (size_t)k * TILE;
+
+  // load the tile (operand order -> column-major smem); coalesced global reads
+  for (int e = tid; e < TILE_ELEMS; e += 256) {
+    const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7, k3 = e & 3;
+    const int R = m8 * 8 + g, C = kg * 4 + k3;
+    S[R + C * POTRF_LD] = tile[e];
+  }
+  if (tid < TILE) S[TILE + tid * POTRF_LD] = rk[tid];
+
+  for (int j = 0; j < TILE; ++j) {
+    __syncthreads();
+    const double* cj = S + j * POTRF_LD;
+    const double winv = 1.0 / cj[j];
+    for (int c = j + 1 + warp; c < TILE; c += nwarps) {
+      double* col = S + c * POTRF_LD;
+      const double beta = cj[c] * winv;
+      // rows [0, j) then [c, 128]: one fused index space so all lanes stay busy
+      const int n_inv = j, n_tot = j + (TILE + 1 - c);
+      for (int v = lane; v < n_tot; v += 32) {
+        const int rho = (v < n_inv) ? v : (c + v - n_inv);
+        col[rho] = fma(-cj[rho], beta, col[rho]);
+      }
+      if (lane == 0) col[j] = -beta;
+    }
+  }
+  __syncthreads();
+
+  // pivots -> scale factors, status, log det, z
+  double ld_part = 0.0, q_part = 0.0;
+  int first_bad = 0x7fffffff, nan_seen = 0;
+  double isd = 0.0;
+  if (tid < TILE) {
+    const double d = S[tid + tid * POTRF_LD];
+    if (!(d > 0.0)) {
+      first_bad = k * TILE + tid + 1;
+      nan_seen = isnan(d) ? 1 : 0;
+    }
+    isd = 1.0 / sqrt(d);
+    ld_part = log(d);
+    const double z = S[TILE + tid * POTRF_LD] * isd;
+    q_part = z * z;
+    zbuf[(size_t)b * TILE + tid] = z;
+  }
+  const double logdet = block_sum(ld_part, red);
+  const double quad = block_sum(q_part, red);
+  const int fb = -block_max_int(-first_bad, ired);
+  const int anynan = block_max_int(nan_seen, ired);
+  if (tid == 0) {
+    acc_logdet[b] += logdet;
+    acc_quad[b] += quad;
+    if (status[b] == 0 && fb != 0x7fffffff) status[b] = anynan ? -1 : fb;
+  }
+  if (tid < TILE) isd_s[tid] = isd;
+  __syncthreads();
+  // write inv(L_kk) over the tile in operand order: element (R = n, C = kk) = inv(L)[n][kk]
+  // inv(L)[n][kk] = S[kk][n] / sqrt(d_n) for kk < n; 1/sqrt(d_n) on the diagonal; 0 above it.
+  for (int e = tid; e < TILE_ELEMS; e += 256) {
+    const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7, k3 = e & 3;
+    const int R = m8 * 8 + g, C = kg * 4 + k3;
+    double v = 0.0;
+    if (C <= R) {
+      const double s = isd_s[R];
+      v = (C == R) ? s : S[C + R * POTRF_LD] * s;
+    }
+    tile[e] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// DMMA tile GEMM: acc(128x128) = sum over operand tile pairs of A_p * B_p^T, K = 128 per pair.
+// 8 warps as 2 (m) x 4 (n): warp tile 64 x 32 = 4 m16-fragments x 4 n8-fragments.
+// 3-stage cp.async pipeline over k16 slices (16 KiB of A + 16 KiB of B per stage).
+// ------------------------------------------------------------------------------------------------
+#define GEMM_STAGE_DOUBLES (2 * SLICE_ELEMS)
+#define GEMM_SMEM_BYTES ((size_t)GEMM_STAGES * GEMM_STAGE_DOUBLES * sizeof(double) + (2 * TILE + 4 * TILE + TILE) * sizeof(double))
+
+enum { GEMM_TRSM = 0, GEMM_UPDATE = 1 };
+
+struct GemmArgs {
+  int N, nt;
+  int mode;          // GEMM_TRSM / GEMM_UPDATE
+  int k;             // TRSM: the tile column being solved
+  int col_begin;     // UPDATE: first / one-past-last target tile column
+  int col_end;
+  int p_begin;       // UPDATE: panel of operand tile columns [p_begin, p_end)
+  int p_end;
+  int gen;           // UPDATE: 1 = target tiles are generated from t (first touch) instead of loaded
+  int kernel_id, variant, nh;
+  double* Abase;
+  size_t walker_stride;
+  const double* t;
+  const double* yerr;
+  const double* hp_wave;
+  double* resid;     // [wave, ldr]
+  int ldr;
+  const double* zbuf;  // [wave, 128]
+};
+
+__device__ __forceinline__ void load_slice(double* stage, const double* __restrict__ Asrc,
+                                           const double* __restrict__ Bsrc, int tid) {
+  // 2048 doubles each; 256 threads x 4 x 16 B per operand
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int off = (j * 256 + tid) * 2;
+    cp_async16(stage + off, Asrc + off);
+    cp_async16(stage + SLICE_ELEMS + off, Bsrc + off);
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) {
+  extern __shared__ double smem[];
+  double* stages = smem;
+  double* tis = smem + GEMM_STAGES * GEMM_STAGE_DOUBLES;  // 128: t of the tile rows
+  double* tjs = tis + TILE;                               // 128: t of the tile cols
+  double* part = tjs + TILE;                              // 4 x 128 GEMV partials
+  double* zs = part + 4 * TILE;                           // 128: z_k
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warp grid
+  const int gq = lane >> 2, tig = lane & 3;
+  const int b = blockIdx.y;
+  double* Aw = g.Abase + (size_t)b * g.walker_stride;
+
+  // decode the target tile (ti, tj) and the operand tile list
+  int ti, tj, np;
+  if (g.mode == GEMM_TRSM) {
+    ti = g.k + 1 + blockIdx.x;
+    tj = g.k;
+    np = 1;
+  } else {
+    int rem = blockIdx.x;
+    tj = g.col_begin;
+    while (rem >= g.nt - tj) {
+      rem -= g.nt - tj;
+      ++tj;
+    }
+    ti = tj + rem;
+    np = g.p_end - g.p_begin;
+  }
+  const int nslices = np * SLICES_PER_TILE;
+
+  auto a_src = [&](int q) -> const double* {
+    const int p = q >> 3, s = q & 7;
+    const size_t tix = (g.mode == GEMM_TRSM) ? tile_index(ti, g.k) : tile_index(ti, g.p_begin + p);
+    return Aw + tix * TILE_ELEMS + s * SLICE_ELEMS;
+  };
+  auto b_src = [&](int q) -> const double* {
+    const int p = q >> 3, s = q & 7;
+    const size_t tix = (g.mode == GEMM_TRSM) ? tile_index(g.k, g.k) : tile_index(tj, g.p_begin + p);
+    return Aw + tix * TILE_ELEMS + s * SLICE_ELEMS;
+  };
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+    if (s < nslices) load_slice(stages + s * GEMM_STAGE_DOUBLES, a_src(s), b_src(s), tid);
+    cp_async_commit();
+  }
+  if (g.mode == GEMM_UPDATE && g.gen) {
+    if (tid < TILE) {
+      const int gi = ti * TILE + tid;
+      tis[tid] = gi < g.N ? g.t[gi] : 0.0;
+    } else {
+      const int gj = tj * TILE + (tid - TILE);
+      tjs[tid - TILE] = gj < g.N ? g.t[gj] : 0.0;
+    }
+  }
+  if (g.mode == GEMM_TRSM && tid < TILE) zs[tid] = g.zbuf[(size_t)b * TILE + tid];
+
+  double acc[4][4][4];
+#pragma unroll
+  for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[mi][ni][v] = 0.0;
+
+  for (int q = 0; q < nslices; ++q) {
+    cp_async_wait<GEMM_STAGES - 2>();
+    __syncthreads();
+    {
+      const int qn = q + GEMM_STAGES - 1;
+      if (qn < nslices) load_slice(stages + (qn % GEMM_STAGES) * GEMM_STAGE_DOUBLES, a_src(qn), b_src(qn), tid);
+      cp_async_commit();
+    }
+    const double* As = stages + (q % GEMM_STAGES) * GEMM_STAGE_DOUBLES;
+    const double* Bs = As + SLICE_ELEMS;
+    double bf[4][4];
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bf[ni][v] = Bs[((v * 16 + (wn * 4 + ni)) << 5) + lane];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+      double af[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) af[v] = As[(((v >> 1) * 16 + (wm * 8 + mi * 2 + (v & 1))) << 5) + lane];
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) dmma_16816(acc[mi][ni], af, bf[ni]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+
+  // epilogue ------------------------------------------------------------------------------------
+  double* Ct = Aw + tile_index(ti, tj) * TILE_ELEMS;
+  // element (R, C): R = wm*64 + mi*16 + gq + 8*v1, C = wn*32 + ni*8 + 2*tig + v0
+  if (g.mode == GEMM_UPDATE) {
+    CovParams cp;
+    if (g.gen) cp = make_cov_params(g.kernel_id, g.variant, g.hp_wave + (size_t)b * g.nh);
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int v1 = 0; v1 < 2; ++v1) {
+          const int R = wm * 64 + mi * 16 + gq + 8 * v1;
+          const int C = wn * 32 + ni * 8 + 2 * tig;
+          double2* p = reinterpret_cast<double2*>(Ct + tile_off(R, C));
+          double2 old;
+          if (g.gen) {
+            old.x = gen_element(cp, g.N, ti * TILE + R, tj * TILE + C, tis[R], tjs[C], g.yerr);
+            old.y = gen_element(cp, g.N, ti * TILE + R, tj * TILE + C + 1, tis[R], tjs[C + 1], g.yerr);
+          } else {
+            old = *p;
+          }
+          old.x -= acc[mi][ni][2 * v1 + 0];
+          old.y -= acc[mi][ni][2 * v1 + 1];
+          *p = old;
+        }
+  } else {
+    // TRSM: X = acc is L(i,k); store it and fold r_i -= X z_k
+    double rowsum[4][2];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int v1 = 0; v1 < 2; ++v1) {
+        double s = 0.0;
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          const int R = wm * 64 + mi * 16 + gq + 8 * v1;
+          const int C = wn * 32 + ni * 8 + 2 * tig;
+          double2 x;
+          x.x = acc[mi][ni][2 * v1 + 0];
+          x.y = acc[mi][ni][2 * v1 + 1];
+          *reinterpret_cast<double2*>(Ct + tile_off(R, C)) = x;
+          s = fma(x.x, zs[C], s);
+          s = fma(x.y, zs[C + 1], s);
+        }
+        // reduce over the 4 lanes of a quad (columns), fixed order
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        rowsum[mi][v1] = s;
+      }
+    if (tig == 0) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int v1 = 0; v1 < 2; ++v1) part[wn * TILE + wm * 64 + mi * 16 + gq + 8 * v1] = rowsum[mi][v1];
+    }
+    __syncthreads();
+    if (tid < TILE) {
+      const double s = ((part[tid] + part[TILE + tid]) + part[2 * TILE + tid]) + part[3 * TILE + tid];
+      double* ri = g.resid + (size_t)b * g.ldr + (size_t)ti * TILE;
+      ri[tid] -= s;
+    }
+  }
+}
+
+// logL = -N/2 ln 2pi - logdet/2 - quad/2 (+ priors), status merge.  One thread per walker.
+__global__ void finalize_logl_kernel(ProblemDesc D, int W, const double* __restrict__ hp,
+                                     const double* __restrict__ phys, const double* __restrict__ acc_logdet,
+                                     const double* __restrict__ acc_quad, const int* __restrict__ nonfinite,
+                                     const int* __restrict__ fact_status, double* __restrict__ logl_out,
+                                     int* __restrict__ status_out) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  double v = -((double)D.N / 2.0) * log(2.0 * MRV_PI) - 0.5 * acc_logdet[w] - 0.5 * acc_quad[w];
+  v = add_priors(D, hp + (size_t)w * D.nh, phys + (size_t)w * D.nm, v);
+  int st = fact_status[w];
+  if (nonfinite[w]) st = -1;
+  logl_out[w] = v;
+  status_out[w] = st;
+}

@@ -1,0 +1,194 @@
+// Shared device helpers: covariance functions, priors, block reductions.
+// All arithmetic is IEEE binary64; no fast-math anywhere (compile WITHOUT --use_fast_math).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#define MRV_PI 3.141592653589793
+#define MRV_MAX_HP 8
+#define MRV_MAX_OPS 16
+#define MRV_MAX_MODPAR 48
+#define MRV_MAX_PRIORS 48
+
+struct ModelOp {
+  int type;
+  int param_offset;
+  double flag_val;
+};
+struct PriorSpec {
+  int type, source, index, pad;
+  double p0, p1, p2;
+};
+
+// Everything a kernel needs to know about the problem besides the per-walker parameters.
+struct ProblemDesc {
+  int N;             // data points
+  int kernel_id;     // MRV_KERNEL_*
+  int variant;       // 0 reference-as-coded, 1 textbook Matern5
+  int nh, nm;        // hyper-parameters / model parameters per walker
+  int n_ops, n_priors;
+  ModelOp ops[MRV_MAX_OPS];
+  PriorSpec priors[MRV_MAX_PRIORS];
+};
+
+// ------------------------------------------------------------------------------------------------
+// Covariance functions (reference src/magpy_rv/kernels.py:229, 356, 489, 629-630, 774-775, 909,
+// 1042).  CovParams holds per-walker constants so the N^2/2 evaluations are a handful of fp64 ops
+// plus the transcendental calls.  Constants fold the reference's divisions into reciprocals
+// (<= 1 ulp change per entry, far inside the 1e-9 LogL tolerance) and the two QuasiPer exps into one.
+// ------------------------------------------------------------------------------------------------
+struct CovParams {
+  int kind;      // kernel_id (Matern5 textbook -> 7)
+  double a2;     // amp^2
+  double c1, c2, c3;
+  double jit2;   // jitter^2 (0 when the kernel has none)
+};
+
+__host__ __device__ inline CovParams make_cov_params(int kernel_id, int variant, const double* hp) {
+  CovParams p;
+  p.kind = kernel_id;
+  p.a2 = p.c1 = p.c2 = p.c3 = p.jit2 = 0.0;
+  switch (kernel_id) {
+    case 0:  // Cosine: hp = amp, per
+      p.a2 = hp[0] * hp[0];
+      p.c1 = 2.0 * MRV_PI / hp[1];
+      break;
+    case 1:  // ExpSquared: amp, timescale
+      p.a2 = hp[0] * hp[0];
+      p.c1 = -0.5 / (hp[1] * hp[1]);
+      break;
+    case 2:  // ExpSinSquared: amp, timescale, per
+      p.a2 = hp[0] * hp[0];
+      p.c1 = -2.0 / (hp[1] * hp[1]);
+      p.c2 = MRV_PI / hp[2];
+      break;
+    case 3:  // QuasiPer: per, perlength, explength, amp
+    case 4:  // JitterQuasiPer: + jit
+      p.a2 = hp[3] * hp[3];
+      p.c1 = -1.0 / (hp[2] * hp[2]);
+      p.c2 = MRV_PI / hp[0];
+      p.c3 = -1.0 / (hp[1] * hp[1]);
+      if (kernel_id == 4) p.jit2 = hp[4] * hp[4];
+      break;
+    case 5:  // Matern5/2: amp, timescale
+      p.a2 = hp[0] * hp[0];
+      p.c1 = sqrt(5.0) / hp[1];
+      if (variant == 1) {
+        p.kind = 7;
+        p.c2 = 5.0 / (3.0 * hp[1] * hp[1]);
+      } else {
+        p.c2 = hp[1] * hp[1];  // as coded: (5 d^4 / 3) * ts^2
+      }
+      break;
+    case 6:  // Matern3/2: amp, timescale, jit
+      p.a2 = hp[0] * hp[0];
+      p.c1 = sqrt(3.0) / hp[1];
+      p.jit2 = hp[2] * hp[2];
+      break;
+  }
+  return p;
+}
+
+// k(d) for d = |t - t'| >= 0 and d2 = (t - t')^2 (off-diagonal part; no error/jitter terms).
+__device__ __forceinline__ double cov_from_dist(const CovParams& p, double d, double d2) {
+  switch (p.kind) {
+    case 0:
+      return p.a2 * cos(p.c1 * d);
+    case 1:
+      return p.a2 * exp(p.c1 * (d * d));
+    case 2: {
+      double s = sin(p.c2 * d);
+      return p.a2 * exp(p.c1 * (s * s));
+    }
+    case 3:
+    case 4: {
+      double s = sin(p.c2 * d);
+      return p.a2 * exp(p.c1 * d2 + p.c3 * (s * s));
+    }
+    case 5: {  // reference as coded (kernels.py:909)
+      double x = p.c1 * d;
+      return p.a2 * (1.0 + x + ((5.0 * (d2 * d2)) / 3.0 * p.c2) * exp(-x));
+    }
+    case 7: {  // textbook Matern 5/2
+      double x = p.c1 * d;
+      return p.a2 * (1.0 + x + p.c2 * d2) * exp(-x);
+    }
+    case 6: {
+      double x = p.c1 * d;
+      return p.a2 * (1.0 + x) * exp(-x);
+    }
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ double cov_eval(const CovParams& p, double ti, double tj) {
+  double dt = ti - tj;
+  return cov_from_dist(p, fabs(dt), dt * dt);
+}
+
+// Full K_ii: kernel value at zero lag, then + jit^2, then + yerr_i^2 -- the reference's order
+// (kernels.py:778-789).
+__device__ __forceinline__ double cov_diag(const CovParams& p, double yerr) {
+  double k0 = cov_from_dist(p, 0.0, 0.0);
+  return (k0 + p.jit2) + yerr * yerr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Priors (reference src/magpy_rv/parameters.py:328, 395-402, 472-479, 539-544)
+// ------------------------------------------------------------------------------------------------
+__device__ inline double prior_logprob(const PriorSpec& s, double x) {
+  switch (s.type) {
+    case 0:  // Gaussian: -0.5((x-mu)/sigma)^2 - ln(sqrt(2pi) sigma)
+    {
+      double z = (x - s.p0) / s.p1;
+      return -0.5 * (z * z) - log(sqrt(2.0 * MRV_PI) * s.p1);
+    }
+    case 1:  // Jeffrey
+      if (x < s.p0 || x > s.p1) return -10e5;
+      return log(1.0 / log(s.p1 / s.p0) * 1.0 / x);
+    case 2:  // Modified Jeffrey
+      if (x < s.p0 || x > s.p1) return -10e5;
+      return log(1.0 / log((s.p1 + s.p2) / s.p2) * 1.0 / (x - s.p2));
+    case 3:  // Uniform
+      if (x < s.p0 || x > s.p1) return -10e5;
+      return 0.0;
+  }
+  return 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Deterministic block-wide sum (fixed tree => bitwise reproducible, independent of shard count).
+// `scratch` must hold >= 32 doubles.  All threads of the block must call; result on every thread.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ inline double block_sum(double v, double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect scratch from a previous use
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double r = (lane < nwarps) ? scratch[lane] : 0.0;
+  r = warp_sum(r);
+  return r;
+}
+
+__device__ inline int block_max_int(int v, int* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  int r = (lane < nwarps) ? scratch[lane] : INT_MIN;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) r = max(r, __shfl_xor_sync(0xffffffffu, r, o));
+  return r;
+}

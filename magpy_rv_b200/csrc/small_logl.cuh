@@ -1,0 +1,118 @@
+// Fused small-N log-likelihood: ONE CTA PER WALKER, the covariance never leaves shared memory.
+//
+// Pipeline inside the CTA (reference call stack: mcmc.py:421-458 -> get_model -> GPLikelihood.LogL
+// -> compute_kernel -> slogdet/cho_factor/cho_solve, gp_likelihood.py:250-278, 357-402):
+//   1. mean models + residual r = y - model            (mean_model.cuh)
+//   2. lower triangle of K built in smem from t, yerr  (common.cuh cov_eval / cov_diag)
+//   3. in-place square-root-free Cholesky (LDL^T) of the matrix augmented with r as an extra row:
+//        for j: A[i][c] -= A[i][j] * A[c][j] / A[j][j]     (c > j, i >= c, i == N is the r row)
+//      one barrier per column; afterwards A[j][j] = d_j (pivots), A[N][j] = (L^-1 r)_j * sqrt(d_j)
+//   4. logdet = sum ln d_j,  quad = sum A[N][j]^2 / d_j   (deterministic block reductions)
+//   5. logL = -N/2 ln 2pi - logdet/2 - quad/2, then + priors in list order.
+// Non-PD K shows up as a pivot d_j <= 0 exactly where LAPACK potrf reports info = j+1.
+//
+// smem: column-major (N+1) x N with an odd leading dimension (bank-conflict-free rows and
+// columns) + t + r + small vectors.  N <= 168 fits the 227 KB opt-in limit.
+#pragma once
+#include "mean_model.cuh"
+
+#define MRV_SMALL_THREADS 256
+
+__host__ __device__ inline int small_ld(int N) { return (N + 1) | 1; }
+__host__ inline size_t small_smem_bytes(int N) {
+  return ((size_t)small_ld(N) * N + 2 * (size_t)N + MRV_MAX_MODPAR + MRV_MAX_HP + 40) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(MRV_SMALL_THREADS)
+fused_small_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __restrict__ y,
+                        const double* __restrict__ yerr, const double* __restrict__ flags,
+                        const double* __restrict__ hp_all, const double* __restrict__ modpar_all,
+                        const double* __restrict__ model_given, int to_ecc, double* __restrict__ logl_out,
+                        int* __restrict__ status_out) {
+  extern __shared__ double smem[];
+  const int N = D.N, ld = small_ld(N);
+  double* S = smem;                         // ld x N, column major; row N = residual row
+  double* ts = S + (size_t)ld * N;          // N
+  double* r = ts + N;                       // N
+  double* phys = r + N;                     // MRV_MAX_MODPAR
+  double* hpv = phys + MRV_MAX_MODPAR;      // MRV_MAX_HP
+  double* red = hpv + MRV_MAX_HP;           // 32
+  int* ired = (int*)(red + 32);             // 32 ints
+  const int w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+
+  if (tid == 0) {
+    for (int i = 0; i < D.nh; ++i) hpv[i] = hp_all[(size_t)w * D.nh + i];
+    for (int i = 0; i < D.nm; ++i) phys[i] = modpar_all[(size_t)w * D.nm + i];
+    if (model_given == nullptr) convert_to_ecc(D, phys, to_ecc);
+  }
+  for (int i = tid; i < N; i += nt) ts[i] = t[i];
+  __syncthreads();
+
+  // 1. residual
+  if (model_given != nullptr) {
+    for (int i = tid; i < N; i += nt) r[i] = model_given[(size_t)w * N + i];
+    __syncthreads();
+  } else {
+    cta_mean_model(D, ts, flags, phys, r, /*E scratch=*/S, red);
+  }
+  int bad = 0;
+  for (int i = tid; i < N; i += nt) {
+    const double v = __dsub_rn(y[i], r[i]);
+    r[i] = v;
+    bad |= !isfinite(v);
+  }
+  __syncthreads();
+
+  // 2. K (lower triangle) + residual row
+  const CovParams cp = make_cov_params(D.kernel_id, D.variant, hpv);
+  for (int c = warp; c < N; c += nwarps) {
+    double* col = S + (size_t)c * ld;
+    const double tc = ts[c];
+    for (int i = c + lane; i < N; i += 32) {
+      const double v = (i == c) ? cov_diag(cp, yerr[i]) : cov_eval(cp, ts[i], tc);
+      bad |= !isfinite(v);
+      col[i] = v;
+    }
+    if (lane == 0) col[N] = r[c];
+  }
+
+  // 3. right-looking LDL^T with the residual row carried along
+  for (int j = 0; j < N - 1; ++j) {
+    __syncthreads();
+    const double* cj = S + (size_t)j * ld;
+    const double winv = 1.0 / cj[j];
+    for (int c = j + 1 + warp; c < N; c += nwarps) {
+      double* col = S + (size_t)c * ld;
+      const double beta = cj[c] * winv;
+      for (int i = c + lane; i <= N; i += 32) col[i] = fma(-cj[i], beta, col[i]);
+    }
+  }
+  __syncthreads();
+
+  // 4. reductions over the pivots
+  double ld_part = 0.0, q_part = 0.0;
+  int first_bad = 0x7fffffff;
+  for (int j = tid; j < N; j += nt) {
+    const double d = S[(size_t)j * ld + j];
+    const double zr = S[(size_t)j * ld + N];
+    if (!(d > 0.0)) first_bad = min(first_bad, j + 1);
+    ld_part += log(d);
+    q_part += (zr * zr) / d;
+  }
+  const double logdet = block_sum(ld_part, red);
+  const double quad = block_sum(q_part, red);
+  const int fb = -block_max_int(-first_bad, ired);
+  const int anybad = block_max_int(bad, ired);
+
+  // 5. closed form + priors
+  if (tid == 0) {
+    double v = -((double)N / 2.0) * log(2.0 * MRV_PI) - 0.5 * logdet - 0.5 * quad;
+    v = add_priors(D, hpv, phys, v);
+    int st = 0;
+    if (anybad) st = -1;
+    else if (fb != 0x7fffffff) st = fb;
+    logl_out[w] = v;
+    status_out[w] = st;
+  }
+}

@@ -1,0 +1,381 @@
+"""Affine-invariant stretch-move ensemble sampler -- host mirror of the reference's
+``magpy_rv.mcmc`` (class MCMC :34, run_MCMC :676).
+
+The proposal (``split_step``), accept/reject (``compare``) and bookkeeping (``reset``) logic stays
+on the host and consumes the two global RNG streams (Python ``random`` and legacy ``np.random``)
+in exactly the reference's call order, so a shared
+``random.seed(s); np.random.seed(s)`` reproduces the reference's chains step for step.  The
+per-walker likelihood loop of the reference (``MCMC.compute``, mcmc.py:410-461, and the initial
+loop of ``__init__``, mcmc.py:221-261) is replaced by ONE batched GPU call per iteration
+(``mrv_logl_batch``); with ``torch.distributed`` initialised the ensemble is sharded across ranks
+and only log-probabilities and status words are all-gathered (``sharding.py``).
+"""
+import os
+import random
+import time
+
+import numpy as np
+
+from . import auxiliary as aux
+from . import engine
+from . import mcmc_aux as mcmcx
+from . import models as modl
+from . import parameters as par
+
+get_model = mcmcx.get_model
+numb_param_per_model = mcmcx.numb_param_per_model
+parameter_check = mcmcx.parameter_check
+
+
+def _default_backend(t, rv, rv_err, kernel_name, model_name, prior_list, hparam_names, modpar_names, flags):
+    """The batched GPU evaluator for one MCMC problem (sharded when torch.distributed is up)."""
+    from .sharding import ShardedEvaluator
+    return ShardedEvaluator(t, rv, rv_err, kernel_name, model_name, prior_list, hparam_names, modpar_names, flags)
+
+
+# test hook: tests replace this factory to check the host logic without a GPU
+_BACKEND_FACTORY = _default_backend
+
+
+class _History:
+    """Append-only [steps, W, k] store with amortised O(1) append (the reference re-allocates the
+    whole history with np.concatenate every step, mcmc.py:530-534)."""
+
+    def __init__(self, first):
+        self._buf = np.array(first, dtype=np.float64, copy=True)
+        self._n = self._buf.shape[0]
+
+    def append(self, step):
+        if self._n == self._buf.shape[0]:
+            grown = np.zeros((max(4, 2 * self._buf.shape[0]),) + self._buf.shape[1:], dtype=np.float64)
+            grown[:self._n] = self._buf[:self._n]
+            self._buf = grown
+        self._buf[self._n] = step[0]
+        self._n += 1
+
+    @property
+    def array(self):
+        return self._buf[:self._n]
+
+
+class MCMC:
+    """Ensemble sampler state machine (reference mcmc.py:34-567)."""
+
+    def __init__(self, t, rv, rv_err, hparam0, kernel_name, model_par0, model_name, prior_list, numb_chains=100, flags=None, Mstar=0):
+        self.t = t
+        self.rv = rv
+        self.rv_err = rv_err
+        self.kernel_name = kernel_name
+        self.model_name = model_name
+        self.Mstar = Mstar
+        self.flags = flags if flags is not None else None
+
+        if isinstance(self.model_name, list):
+            self.numb_models = len(self.model_name)
+        elif isinstance(self.model_name, str):
+            self.numb_models = 1
+            self.model_name = [model_name]
+        else:
+            raise TypeError("model_name must be a string or a list of strings")
+        self.prior_list = prior_list
+        self.numb_chains = int(numb_chains)
+
+        self.hlen = len(hparam0)
+        self.plen = len(model_par0)
+        W = self.numb_chains
+
+        # number of mass columns = number of Keplerians (reference mcmc.py:134-147)
+        try:
+            model_par0['P'].value
+            n_planets = 1
+        except KeyError:
+            n_planets = sum(1 for i in range(len(self.model_name)) if ('P_' + str(i)) in model_par0)
+        self._n_planets = n_planets
+
+        self.single_hp0 = [hparam0[k].value for k in hparam0.keys()]
+        self.hp_err = [hparam0[k].error for k in hparam0.keys()]
+        self.hp_vary = [hparam0[k].vary for k in hparam0.keys()]
+        self.hparam_names = list(hparam0.keys())
+        self.single_modpar0 = [model_par0[k].value for k in model_par0.keys()]
+        self.modpar_err = [model_par0[k].error for k in model_par0.keys()]
+        self.modpar_vary = [model_par0[k].vary for k in model_par0.keys()]
+        self.modpar_names = list(model_par0.keys())
+
+        for pr in prior_list:
+            assert pr[0] in self.modpar_names or pr[0] in hparam0.keys(), "mispelt or incorrect parameter name: " + str(pr[0])
+
+        which_model, name = [], []
+        for b, mod in enumerate(self.model_name):
+            for _ in range(numb_param_per_model(mod)):
+                which_model.append(b)
+                name.append(mod + str(b))
+        self.modpar_info = [self.modpar_names, which_model, name]
+
+        self.k_numb_param = len(self.single_hp0)
+        self.mod_numb_param = len(self.single_modpar0)
+        self.numb_param = self.k_numb_param + self.mod_numb_param
+
+        # Keplerian ecc, omega -> Sk, Ck (Ford 2006), with errors (reference mcmc.py:196-198)
+        for g in range(len(self.single_modpar0)):
+            if self.modpar_info[0][g].startswith('ecc') and self.modpar_info[2][g].startswith(('kep', 'Kep')):
+                (self.single_modpar0[g], self.single_modpar0[g + 1], self.modpar_err[g],
+                 self.modpar_err[g + 1]) = aux.to_SkCk(self.single_modpar0[g], self.single_modpar0[g + 1],
+                                                       self.modpar_err[g], self.modpar_err[g + 1])
+
+        if self.numb_chains < (len(self.single_hp0) + len(self.single_modpar0)) * 2:
+            # the reference *returns* a RuntimeWarning from __init__ here (mcmc.py:201-202), which
+            # Python turns into this TypeError
+            raise TypeError("__init__() should return None, not 'RuntimeWarning'")
+
+        # starting positions: two np.random-consuming calls, hyper-parameters first (mcmc.py:205-206)
+        self.hp0 = mcmcx.initial_pos_creator(self.single_hp0, self.hp_err, self.numb_chains)
+        self.modpar0 = mcmcx.initial_pos_creator(self.single_modpar0, self.modpar_err, self.numb_chains)
+
+        self._backend = _BACKEND_FACTORY(self.t, self.rv, self.rv_err, self.kernel_name, self.model_name,
+                                         self.prior_list, self.hparam_names, self.modpar_names, self.flags)
+
+        # initial likelihoods and masses of all walkers: one batched call (reference loop mcmc.py:221-261)
+        self.logL0 = np.zeros(shape=(1, W, 1))
+        self.logL0[0, :, 0] = self._evaluate(self.hp0[0], self.modpar0[0])
+        self.mass0_list = self._masses(self.modpar0[0])
+
+        self._hist_hp = _History(self.hp0)
+        self._hist_mod = _History(self.modpar0)
+        self._hist_logL = _History(self.logL0)
+        self._hist_acc = _History(np.ones(shape=(1, W, 1)))
+        self._hist_mass = _History(self.mass0_list)
+
+        print("Initial hyper-parameter guesses: ")
+        print(self.single_hp0)
+        print()
+        print("Initial model parameter guesses (ecc and omega are replaced by Sk and Ck): ")
+        print(self.single_modpar0)
+        print()
+        print("Initial Log Likelihood: ", self.logL_list[0, 0, 0])
+        print()
+        print("Number of chains: ", self.numb_chains)
+        print()
+
+    # -- history views (same attribute names / shapes as the reference) ---------------------------
+    @property
+    def hparameter_list(self):
+        return self._hist_hp.array
+
+    @property
+    def model_parameter_list(self):
+        return self._hist_mod.array
+
+    @property
+    def logL_list(self):
+        return self._hist_logL.array
+
+    @property
+    def accepted(self):
+        return self._hist_acc.array
+
+    @property
+    def mass_list(self):
+        return self._hist_mass.array
+
+    # -- batched evaluation ------------------------------------------------------------------------
+    def _evaluate(self, hp, modpar):
+        """log L + log priors of all walkers: the reference's per-chain loop body
+        (mcmc.py:421-458) as one GPU call.  A non-zero status raises what the reference's
+        cho_factor would have raised, ending the run as the reference does."""
+        logl, status = self._backend.logl(np.ascontiguousarray(hp), np.ascontiguousarray(modpar))
+        engine.raise_for_status(status)
+        return logl
+
+    def _masses(self, modpar):
+        """[1, W, n_planets] minimum masses with the reference's argument-order quirk: mass_calc
+        receives [P, K, omega, ecc] but unpacks the third entry as ecc, and runs BEFORE the
+        Sk,Ck -> ecc,omega conversion, so the 'eccentricity' in the formula is the chain's Ck
+        (mcmc.py:438-444, auxiliary.py:242-245)."""
+        W = self.numb_chains
+        out = np.zeros(shape=(1, W, self._n_planets))
+        if self._n_planets == 0:
+            return out
+        names = self.modpar_names
+        for i in range(self._n_planets):
+            sfx = "" if "P" in names else "_" + str(i)
+            iP, iK = names.index("P" + sfx), names.index("K" + sfx)
+            iO, iE = names.index("omega" + sfx), names.index("ecc" + sfx)
+            out[0, :, i] = aux.mass_calc([modpar[:, iP], modpar[:, iK], modpar[:, iO], modpar[:, iE]], self.Mstar)
+        return out
+
+    # -- proposal ----------------------------------------------------------------------------------
+    def split_step(self, n_splits=2, a=2., Rstar=None, Mstar=None):
+        """Stretch-move proposals for ALL walkers from the snapshot hp0/modpar0 (reference
+        mcmc.py:286-403).  RNG call order kept: one random.shuffle, then per walker
+        of each split one random.randint followed by np.random.rand draws (redrawn while a
+        hyper-parameter is negative or parameter_check fails)."""
+        W = self.numb_chains
+        inds = np.arange(W) % n_splits
+        random.shuffle(inds)
+
+        self.hp = np.zeros_like(self.hp0)
+        self.modpar = np.zeros_like(self.modpar0)
+        self.logz = np.zeros(W)
+
+        hp0 = self.hp0[0]
+        mod0 = self.modpar0[0]
+        # the reference locates each walker again by matching the first hyper-parameter and first
+        # model parameter, keeping the LAST match (mcmc.py:378-381); same rule, O(W) instead of O(W^2)
+        last_match = {}
+        for o in range(W):
+            last_match[(hp0[o, 0], mod0[o, 0])] = o
+        hp_vary = np.array(self.hp_vary, dtype=bool)
+        mod_vary = np.array(self.modpar_vary, dtype=bool)
+        check_args = (Rstar, Mstar) if (Rstar is not None and Mstar is not None) else ()
+
+        for split in range(n_splits):
+            in_s1 = inds == split
+            S1_hp, S2_hp = hp0[in_s1], hp0[~in_s1]
+            S1_mod, S2_mod = mod0[in_s1], mod0[~in_s1]
+            N_chains1, N_chains2 = len(S1_hp), len(S2_hp)
+            S1_hp[0]                      # an empty first set is an IndexError in the reference too
+            for chain in range(N_chains1):
+                rint = random.randint(0, N_chains2 - 1)
+                Xj, Xj_mod = S2_hp[rint], S2_mod[rint]
+                while True:
+                    z = (np.random.rand() * (a - 1) + 1) ** 2 / a
+                    Xk_new = Xj + (S1_hp[chain] - Xj) * z
+                    Xk_new_mod = Xj_mod + (S1_mod[chain] - Xj_mod) * z
+                    if not (np.min(Xk_new) < 0) and parameter_check(Xk_new_mod, self.model_name, *check_args):
+                        break
+                position = last_match[(S1_hp[chain, 0], S1_mod[chain, 0])]
+                self.hp[0, position] = np.where(hp_vary, Xk_new, S1_hp[chain])
+                self.modpar[0, position] = np.where(mod_vary, Xk_new_mod, S1_mod[chain])
+                self.logz[position] = np.log(z)
+
+    # -- likelihood ----------------------------------------------------------------------------------
+    def compute(self):
+        """log L (+ priors) and masses of the proposed positions (reference mcmc.py:410-461): one
+        batched GPU evaluation of all walkers."""
+        W = self.numb_chains
+        self.logL = np.zeros(shape=(1, W, 1))
+        self.logL[0, :, 0] = self._evaluate(self.hp[0], self.modpar[0])
+        self.mass = self._masses(self.modpar[0])
+
+    # -- accept / reject -------------------------------------------------------------------------------
+    def compare(self):
+        """Metropolis decision per walker (reference mcmc.py:467-535): diff > 1
+        accept, diff < -35 reject, otherwise accept iff random.uniform(0,1) <= exp(diff) -- the
+        uniform is drawn ONLY in the middle band, in walker order.  A NaN diff matches no branch
+        and records zeros, as in the reference.  The z^(n-1) factor is (as there) not applied."""
+        W = self.numb_chains
+        diff = self.logL[0, :, 0] - self.logL0[0, :, 0]
+        accept = diff > 1
+        reject = diff < -35.
+        middle = (diff >= -35.) & (diff <= 1.)
+        idx = np.nonzero(middle)[0]
+        if idx.size:
+            u = np.array([random.uniform(0, 1) for _ in range(idx.size)])
+            ok = u <= np.exp(diff[idx])
+            accept = accept.copy()
+            reject = reject.copy()
+            accept[idx[ok]] = True
+            reject[idx[~ok]] = True
+
+        hp_decision = np.zeros(shape=(1, W, self.hlen))
+        modpar_decision = np.zeros(shape=(1, W, self.plen))
+        logL_decision = np.zeros(shape=(1, W, 1))
+        self.acceptance_chain = np.zeros(shape=(1, W, 1))
+        self.mass_decision = np.zeros_like(self.mass)
+
+        hp_decision[0, accept] = self.hp[0, accept]
+        modpar_decision[0, accept] = self.modpar[0, accept]
+        logL_decision[0, accept] = self.logL[0, accept]
+        self.mass_decision[0, accept] = self.mass[0, accept]
+        self.acceptance_chain[0, accept, 0] = True
+        hp_decision[0, reject] = self.hp0[0, reject]
+        modpar_decision[0, reject] = self.modpar0[0, reject]
+        logL_decision[0, reject] = self.logL0[0, reject]
+        self.mass_decision[0, reject] = self.mass0_list[0, reject]
+
+        self._hist_logL.append(logL_decision)
+        self._hist_mass.append(self.mass_decision)
+        self._hist_acc.append(self.acceptance_chain)
+        self._hist_hp.append(hp_decision)
+        self._hist_mod.append(modpar_decision)
+
+    def reset(self):
+        """Accepted proposals become the new current state (reference mcmc.py:540-567); returns
+        (logL_list, hparameter_list, model_parameter_list, accepted, mass_list)."""
+        acc = self.acceptance_chain[0, :, 0] == True  # noqa: E712
+        self.logL0[0, acc] = self.logL[0, acc]
+        self.hp0[0, acc] = self.hp[0, acc]
+        self.modpar0[0, acc] = self.modpar[0, acc]
+        self.mass0_list[0, acc] = self.mass[0, acc]
+        return self.logL_list, self.hparameter_list, self.model_parameter_list, self.accepted, self.mass_list
+
+    def gelman_rubin_calc(self, burn_in=200):
+        """The reference's implementation (mcmc.py:571-662) is broken (mislabelled axes, drops
+        into pdb) and is out of the hot-path scope."""
+        raise NotImplementedError("gelman_rubin_calc is out of scope (SURVEY.md F10 / 8(f) item 4)")
+
+
+def run_MCMC(iterations, t, rv, rv_err, hparam0, kernel_name, model_param0=None, model_name=["no_model"], prior_list=[], numb_chains=None, n_splits=None, a=None, Rstar=None, Mstar=None, flags=None, plot_convergence=False, saving_folder=None, gelman_rubin_limit=1.1):
+    """Run the ensemble MCMC (reference mcmc.py:676-874; same arguments, prints and return tuple:
+    ``(logL_list, hparameter_list, model_parameter_list, completed_iterations)`` and additionally
+    ``mass`` as the last element when ``Mstar`` is given)."""
+    if model_param0 == None:  # noqa: E711
+        if model_name[0].startswith("no") or model_name[0].startswith("No"):
+            model_param0 = modl.mod_create(["no_model"])
+            model_param0["no"] = par.parameter(value=0., error=0., vary=False)
+        else:
+            raise KeyError("model parameters and model list must be provided when using a model")
+
+    if numb_chains is not None:
+        assert numb_chains > (len(model_param0) + len(hparam0)) * 2, "number of chains should be larger than the number of free parameters"
+
+    kwargs = {}
+    if flags is not None:
+        kwargs["flags"] = flags
+    if Mstar is not None:
+        kwargs["Mstar"] = Mstar
+    if numb_chains is None:
+        _ = MCMC(t, rv, rv_err, hparam0, kernel_name, model_param0, model_name, prior_list, **kwargs)
+        numb_chains = 100
+    else:
+        _ = MCMC(t, rv, rv_err, hparam0, kernel_name, model_param0, model_name, prior_list, numb_chains, **kwargs)
+
+    print("Start Iterations")
+    print()
+    start = time.time()
+
+    if plot_convergence:
+        # needs gelman_rubin_calc + matplotlib, both outside the accelerated path
+        raise NotImplementedError("plot_convergence=True is out of scope (reference path is broken, SURVEY.md F10)")
+
+    step_kwargs = {}
+    if n_splits is not None:
+        step_kwargs["n_splits"] = n_splits
+    if a is not None:
+        step_kwargs["a"] = a
+
+    for iteration in range(iterations):
+        _.split_step(**step_kwargs)
+        _.compute()
+        if Rstar is not None and Mstar is not None:
+            _.compare(Rstar=Rstar, Mstar=Mstar)      # TypeError, exactly as in the reference (F10)
+        else:
+            _.compare()
+        logL_list, hparameter_list, model_parameter_list, accepted, mass = _.reset()
+        if (iteration % 2 == 0) or iteration == iterations - 1:
+            aux.printProgressBar(iteration, iterations - 1, length=50)
+    completed_iterations = iterations
+
+    print()
+    print()
+    print("{} iterations have been completed with {} contemporaneous chains".format(iterations, numb_chains))
+    print()
+
+    passed = int(np.count_nonzero(accepted))
+    ratio = passed / (iterations * numb_chains + numb_chains)
+    print("Acceptance Rate = ", ratio)
+    print(" ---- %s minutes ----" % ((time.time() - start) / 60))
+
+    if Mstar is None:
+        return logL_list, hparameter_list, model_parameter_list, completed_iterations
+    return logL_list, hparameter_list, model_parameter_list, completed_iterations, mass

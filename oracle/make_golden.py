@@ -1,0 +1,247 @@
+"""Generate tests/golden/*.npz by running the REAL, UNMODIFIED reference (matplotlib/seaborn
+stubbed) in the build container.
+
+TEST INFRASTRUCTURE ONLY.  Usage (build container, /root/reference present):
+
+    python -m oracle.make_golden            # everything
+    python -m oracle.make_golden kat cases  # selected groups: kat, cases, cov, chains
+
+Outputs (all small):
+    tests/golden/kat_tutorial3.npz   51 Peg HAMILTON-1997 data + tutorial-3 known answer
+    tests/golden/logl_cases.npz      per-walker LogL / model curves for kernel x model x prior cases
+    tests/golden/cov_cases.npz       compute_covmatrix outputs (square, rectangular, as-coded Matern5)
+    tests/golden/chain_C*.npz        seeded run_MCMC chains (random.seed(s); np.random.seed(s))
+"""
+import contextlib
+import io
+import json
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+PEG = "/root/reference/source/tutorials/51Peg_timeseries/51 Peg_HAMILTON_Pub-1997.rdb"
+
+
+# ---------------------------------------------------------------------------------------------
+def ref_logl_walker(ref, t, y, yerr, kernel, hp_row, model_list, mp_row, prior_list, flags):
+    """One walker through the reference exactly as MCMC.compute does (mcmc.py:421-458)."""
+    hp = ref.par.par_create(kernel)
+    for i, k in enumerate(hp):
+        hp[k] = ref.par.parameter(value=float(hp_row[i]), error=1., vary=True)
+    mp = ref.mod.mod_create(list(model_list))
+    for i, k in enumerate(mp):
+        mp[k] = ref.par.parameter(value=float(mp_row[i]), error=1., vary=True)
+    if flags is None:
+        my = ref.mcmcx.get_model(list(model_list), t, mp, flags=None, to_ecc=True)
+    else:
+        my = ref.mcmcx.get_model(list(model_list), t, mp, flags=flags, to_ecc=True)
+    like = ref.gp.GPLikelihood(t, y, yerr, hp, kernel, my, mp)
+    return like.LogL(list(prior_list)), my
+
+
+def make_kat(ref):
+    raw = np.genfromtxt(PEG, delimiter=None, skip_header=2)
+    time = raw[:, 0] + 2450000
+    rv = raw[:, 1] - np.mean(raw[:, 1])
+    rv_err = raw[:, 2]
+    hp = np.array([40., 0.5, 30., 5., 1.])
+    Sk, Ck = ref.aux.to_SkCk(0.013, 1.)
+    mp = np.array([4.2, 55., Sk, Ck, 2450001.])
+    pri = [("gp_amp", "Uniform", [0., 20.]), ("gp_explength", "Uniform", [0., 60.]), ("gp_per", "Uniform", [0., 80.]),
+           ("gp_perlength", "Uniform", [0., 10.]), ("gp_jit", "Uniform", [0., 10.]), ("P", "Uniform", [0., 20.]),
+           ("K", "Uniform", [0., 60.]), ("ecc", "Uniform", [0., 80.]), ("omega", "Uniform", [0., 10.]),
+           ("t0", "Uniform", [2450000., 2450010.])]
+    prior_list = [ref.par.pri_create(a, b, c) for a, b, c in pri]
+    val, my = ref_logl_walker(ref, time, rv, rv_err, "JitterQuasiPer", hp, ["Keplerian"], mp, prior_list, None)
+    print("tutorial-3 KAT: reference here = %.16g, notebook = -1719.4341758413852" % val)
+    np.savez(os.path.join(GOLD, "kat_tutorial3.npz"), t=time, rv=rv, rv_err=rv_err, hp=hp, modpar=mp, Sk=Sk, Ck=Ck,
+             logL_reference_here=val, logL_notebook=-1719.4341758413852, model_y=my,
+             priors=json.dumps(pri))
+
+
+# ---------------------------------------------------------------------------------------------
+KERNEL_GUESS = {
+    "Cosine": [(3.0, 0.3), (17.0, 2.0)],
+    "ExpSquared": [(4.0, 0.5), (9.0, 1.5)],
+    "ExpSinSquared": [(4.0, 0.5), (1.3, 0.2), (19.0, 2.0)],
+    "QuasiPer": [(21.0, 2.0), (0.6, 0.1), (35.0, 5.0), (6.0, 1.0)],
+    "JitterQuasiPer": [(21.0, 2.0), (0.6, 0.1), (35.0, 5.0), (6.0, 1.0), (1.2, 0.3)],
+    "Matern3/2": [(5.0, 0.5), (12.0, 2.0), (0.8, 0.2)],
+    "Matern5/2": [(5.0, 0.5), (12.0, 2.0)],
+}
+
+MODEL_GUESS = {  # (value, scatter) per parameter, chain representation (Sk, Ck for Keplerians)
+    "no_model": [(0.0, 0.0)],
+    "Polynomial": [(1.5, 0.5), (0.02, 0.01), (3e-4, 1e-4), (1e-6, 5e-7)],
+    "Offset": [(2.0, 0.7)],
+    "Keplerian": [(6.3, 0.4), (12.0, 2.0), (0.35, 0.1), (0.25, 0.1), (3.0, 1.0)],
+}
+
+
+def build_case(rng, name, N, W, kernel, model_list, priors, t_offset=0.0, n_instr=1, span=120.0):
+    t = np.sort(rng.uniform(0, span, N)) + t_offset
+    yerr = rng.uniform(0.4, 1.4, N)
+    y = 5.0 * np.sin(2 * np.pi * t / 21.0) + rng.normal(0, 1.0, N)
+    flags = None
+    if n_instr > 1:
+        flags = rng.integers(0, n_instr, N).astype(float)
+        y = y + 1.7 * flags
+    hp = np.array([[v + s * rng.uniform(-1, 1) for v, s in KERNEL_GUESS[kernel]] for _ in range(W)])
+    rows = []
+    for _ in range(W):
+        row = []
+        for m in model_list:
+            g = MODEL_GUESS["Keplerian" if m.lower().startswith("kep") else "Polynomial" if m.lower().startswith("poly")
+                            else "Offset" if m.lower().startswith("off") else "no_model"]
+            vals = [v + s * rng.uniform(-1, 1) for v, s in g]
+            if m.lower().startswith("kep"):
+                vals[4] += t_offset - (0.0 if t_offset == 0 else 5.0e4)   # huge unreduced M when t_offset is a BJD
+            row += vals
+        rows.append(row)
+    modpar = np.array(rows)
+    return dict(name=name, N=N, W=W, kernel=kernel, model_list=list(model_list), priors=priors, t=t, y=y, yerr=yerr,
+                flags=flags, hp=hp, modpar=modpar)
+
+
+def make_cases(ref):
+    rng = np.random.default_rng(987654321)
+    cases = []
+    uni = lambda n, lo, hi: (n, "Uniform", [lo, hi])  # noqa: E731
+    # every kernel, no model, no priors; small-N fused path sizes
+    for kern in ("Cosine", "ExpSquared", "ExpSinSquared", "QuasiPer", "JitterQuasiPer", "Matern3/2"):
+        cases.append(build_case(rng, "kern_" + kern.replace("/", ""), 64, 5, kern, ["no_model"], []))
+    # mean models one by one and combined (multi-model key naming P_0, offset_0, a0_0 ...)
+    cases.append(build_case(rng, "poly", 48, 4, "QuasiPer", ["Polynomial"], [uni("a0", 0., 5.), ("a1", "Gaussian", [0.02, 0.01])]))
+    cases.append(build_case(rng, "offset2", 57, 4, "QuasiPer", ["Offset", "Offset"],
+                            [("offset_1", "Gaussian", [2., 1.]), ("gp_amp", "Jeffrey", [0.1, 50.])], n_instr=3))
+    cases.append(build_case(rng, "kepler_smallM", 90, 5, "JitterQuasiPer", ["Keplerian"],
+                            [uni("ecc", 0., 0.5), uni("omega", -4., 4.), ("K", "Modified_Jeffrey", [0.5, 60., 1.0]),
+                             ("gp_jit", "Modified_Jeffrey", [0.01, 10., 0.5]), uni("P", 6.0, 6.5)]))
+    cases.append(build_case(rng, "kepler_bigM", 111, 4, "JitterQuasiPer", ["Keplerian"],
+                            [uni("gp_amp", 0., 20.), uni("ecc", 0., 80.), uni("omega", 0., 10.)], t_offset=2450000.0))
+    cases.append(build_case(rng, "combo", 75, 4, "Matern3/2", ["Keplerian", "Offset", "Polynomial", "Keplerian"],
+                            [uni("ecc_1", 0., 1.), uni("omega_0", -4., 4.), ("offset_0", "Gaussian", [2., 1.]),
+                             ("a0_0", "Jeffrey", [0.01, 10.]), uni("gp_timescale", 0., 13.)], n_instr=2))
+    # sizes around the fused / blocked crossover and the configs' sizes
+    for N in (23, 128, 168, 169, 256, 300, 500):
+        cases.append(build_case(rng, "size_%d" % N, N, 3, "QuasiPer", ["Keplerian"],
+                                [uni("gp_per", 0., 50.), uni("ecc", 0., 1.)], span=1.2 * N))
+    cases.append(build_case(rng, "size_1000_exps", 1000, 2, "ExpSquared", ["Polynomial"], [], span=900.0))
+
+    out = {}
+    manifest = []
+    for c in cases:
+        t, y, yerr, flags = c["t"], c["y"], c["yerr"], c["flags"]
+        prior_list = [ref.par.pri_create(a, b, v) for a, b, v in c["priors"]]
+        logl = np.empty(c["W"])
+        model = np.empty((c["W"], c["N"]))
+        for w in range(c["W"]):
+            logl[w], model[w] = ref_logl_walker(ref, t, y, yerr, c["kernel"], c["hp"][w], c["model_list"],
+                                                c["modpar"][w], prior_list, flags)
+        pre = c["name"] + "__"
+        for key in ("t", "y", "yerr", "hp", "modpar"):
+            out[pre + key] = c[key]
+        if flags is not None:
+            out[pre + "flags"] = flags
+        out[pre + "logL"] = logl
+        out[pre + "model_y"] = model
+        manifest.append(dict(name=c["name"], N=c["N"], W=c["W"], kernel=c["kernel"], model_list=c["model_list"],
+                             priors=c["priors"], has_flags=flags is not None))
+        print("case %-16s N=%4d W=%d logL[0]=%.12g" % (c["name"], c["N"], c["W"], logl[0]))
+    out["manifest"] = np.array(json.dumps(manifest))
+    np.savez_compressed(os.path.join(GOLD, "logl_cases.npz"), **out)
+
+
+def make_cov(ref):
+    rng = np.random.default_rng(24680)
+    x = np.sort(rng.uniform(0, 60, 23))
+    xp = np.sort(rng.uniform(0, 60, 5))
+    xq = np.sort(rng.uniform(0, 60, 23))
+    err = rng.uniform(0.3, 1.2, 23)
+    out = dict(x=x, xp=xp, xq=xq, err=err)
+    classes = {"Cosine": ref.ker.Cosine, "ExpSquared": ref.ker.ExpSquared, "ExpSinSquared": ref.ker.ExpSinSquared,
+               "QuasiPer": ref.ker.QuasiPer, "JitterQuasiPer": ref.ker.JitterQuasiPer, "Matern5/2": ref.ker.Matern5,
+               "Matern3/2": ref.ker.Matern3}
+    for kern, cls in classes.items():
+        hp = ref.par.par_create(kern)
+        vals = [v for v, _ in KERNEL_GUESS[kern]]
+        for i, k in enumerate(hp):
+            hp[k] = ref.par.parameter(value=vals[i], error=1., vary=True)
+        key = kern.replace("/", "")
+        out[key + "__hp"] = np.array(vals)
+        de, dse = ref.ker.compute_distances(x, x)
+        out[key + "__square_err"] = cls(hp).compute_covmatrix(de, dse, err).copy()
+        out[key + "__square_zero"] = cls(hp).compute_covmatrix(de, dse, 0.).copy()
+        de, dse = ref.ker.compute_distances(xp, x)
+        out[key + "__rect"] = cls(hp).compute_covmatrix(de, dse, 0.).copy()
+        de, dse = ref.ker.compute_distances(xq, x)      # square but x1 != x2
+        out[key + "__square_other"] = cls(hp).compute_covmatrix(de, dse, 0.).copy()
+        de1, dse1 = ref.ker.compute_distances(x[:1], x)  # n1 == 1 broadcasting corner case
+        out[key + "__row"] = cls(hp).compute_covmatrix(de1, dse1, 0.).copy()
+    de, dse = ref.ker.compute_distances(xp, x)
+    out["dist_e"], out["dist_se"] = de, dse
+    # as-coded Matern5 LogL raises LinAlgError
+    hp = ref.par.par_create("Matern5/2")
+    for i, k in enumerate(hp):
+        hp[k] = ref.par.parameter(value=[5.0, 12.0][i], error=1., vary=True)
+    raised = ""
+    try:
+        ref.gp.GPLikelihood(x, np.sin(x), err, hp, "Matern5/2").LogL([])
+    except Exception as exc:  # noqa: BLE001
+        raised = type(exc).__name__
+    out["matern5_logl_raises"] = np.array(raised)
+    print("as-coded Matern5 LogL raises:", raised)
+    np.savez_compressed(os.path.join(GOLD, "cov_cases.npz"), **out)
+
+
+def make_chains(ref, which=("C1", "C2", "C3")):
+    import workloads
+    plan = {"C1": (100, 50, None), "C2": (100, 30, None), "C3": (64, 12, 200)}   # (walkers, iterations, N override)
+    for name in which:
+        W, iters, N = plan[name]
+        cfg = workloads.make_config(name, W=W, N=N)
+        seed = cfg["seed"]
+        hp0 = ref.par.par_create(cfg["kernel"])
+        for k in hp0:
+            src = cfg["hparam0"][k]
+            hp0[k] = ref.par.parameter(value=src.value, error=src.error, vary=src.vary)
+        mp0 = ref.mod.mod_create(cfg["model_list"])
+        for k in mp0:
+            src = cfg["model_par0"][k]
+            mp0[k] = ref.par.parameter(value=src.value, error=src.error, vary=src.vary)
+        prior_list = [ref.par.pri_create(a, b, [d[x] for x in d]) for a, b, d in cfg["prior_list"]]
+        random.seed(seed)
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            logL, hps, mps, done = ref.mcmc.run_MCMC(iters, cfg["t"], cfg["y"], cfg["yerr"], hp0, cfg["kernel"], mp0,
+                                                     cfg["model_list"], prior_list, numb_chains=W, flags=cfg["flags"])
+        print("chain %s: W=%d it=%d N=%d final mean logL %.6f" % (name, W, iters, cfg["N"], logL[-1].mean()))
+        np.savez_compressed(os.path.join(GOLD, "chain_%s.npz" % name), logL=logL, hp=hps, modpar=mps, iterations=iters,
+                            W=W, N=cfg["N"], seed=seed)
+
+
+def main(argv):
+    groups = set(argv) or {"kat", "cases", "cov", "chains"}
+    os.makedirs(GOLD, exist_ok=True)
+    ref = ref_loader.load()
+    if "kat" in groups:
+        make_kat(ref)
+    if "cases" in groups:
+        make_cases(ref)
+    if "cov" in groups:
+        make_cov(ref)
+    if "chains" in groups:
+        make_chains(ref)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
