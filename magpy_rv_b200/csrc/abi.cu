@@ -234,7 +234,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   double* quad = p->quad.as<double>() + w0;
   int* fstatus = p->fstatus.as<int>() + w0;
   const double* hp_wave = d_hp + (size_t)w0 * D.nh;
-  const int PW = std::max(1, p->panel_opt > 0 ? p->panel_opt : 1);
+  const int PW = std::max(1, p->panel_opt > 0 ? p->panel_opt : 4);
 
   GemmArgs g;
   memset(&g, 0, sizeof g);

@@ -1,0 +1,29 @@
+"""Quick GPU probe: FP64 DMMA/DFMA issue peaks and coarse LogL timings by size (CUDA events via torch)."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import workloads
+from magpy_rv_b200 import _native, engine
+
+lib = _native.lib()
+print("DMMA peak TF/s:", lib.mrv_fp64_mma_peak(0, 20000) / 1e12, " DFMA peak TF/s:", lib.mrv_fp64_fma_peak(0, 20000) / 1e12, flush=True)
+sizes = [(100, 1024), (168, 1024), (300, 512), (500, 512), (1024, 512), (2048, 128), (4096, 64), (8192, 16)]
+if len(sys.argv) > 1:
+    sizes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
+for N, W in sizes:
+    cfg = workloads.make_config("C5", W=W, N=N)
+    prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"])
+    for panel in ((1, 2, 4) if N > 168 else (1,)):
+        prob.set_option("panel_tiles", panel)
+        prob.logl(cfg["hp"], cfg["modpar"])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            got, st = prob.logl(cfg["hp"], cfg["modpar"])
+        dt = (time.perf_counter() - t0) / reps
+        fl = workloads.flops_per_eval(N) * W
+        print("N=%5d W=%4d panel=%d path=%d wave=%d: %.3f ms/batch  %.1f evals/s  %.2f TF/s  status_ok=%s"
+              % (N, W, panel, prob.info("path"), prob.info("wave_walkers"), dt * 1e3, W / dt, fl / dt / 1e12, bool(np.all(st == 0))), flush=True)
+    prob.close()
