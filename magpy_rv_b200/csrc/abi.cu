@@ -60,8 +60,68 @@ struct DevBuf {
   T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// Optional per-category kernel timing with CUDA events on the launching stream (bench.py roofline).
+enum { CAT_GEN = 0, CAT_POTRF, CAT_TRSM, CAT_UPDATE_PANEL, CAT_UPDATE_TRAIL, CAT_MEAN, CAT_FINAL, CAT_FUSED, CAT_COUNT };
+static const char* const kCatNames[CAT_COUNT] = {"gen", "potrf", "trsm", "update_panel", "update_trail", "mean", "final", "fused"};
+struct ProfRec {
+  int cat;
+  cudaEvent_t e0, e1;
+  double alg_flops, exec_flops;
+};
+struct Prof {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ns[CAT_COUNT] = {0}, alg[CAT_COUNT] = {0}, exec[CAT_COUNT] = {0};
+  int64_t n[CAT_COUNT] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+  }
+  void begin(int cat, cudaStream_t st, double alg_f, double exec_f) {
+    if (!on) return;
+    ProfRec r{cat, get(), get(), alg_f, exec_f};
+    cudaEventRecord(r.e0, st);
+    recs.push_back(r);
+  }
+  void end(cudaStream_t st) {
+    if (!on) return;
+    cudaEventRecord(recs.back().e1, st);
+  }
+  void collect() {  // call after the stream has been synchronised
+    for (ProfRec& r : recs) {
+      float ms = 0.f;
+      if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) {
+        ns[r.cat] += (double)ms * 1e6;
+        alg[r.cat] += r.alg_flops;
+        exec[r.cat] += r.exec_flops;
+        n[r.cat]++;
+      }
+      pool.push_back(r.e0);
+      pool.push_back(r.e1);
+    }
+    recs.clear();
+  }
+  void reset() {
+    collect();
+    for (int c = 0; c < CAT_COUNT; ++c) ns[c] = alg[c] = exec[c] = 0.0, n[c] = 0;
+  }
+  void destroy() {
+    collect();
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+    pool.clear();
+  }
+};
+
 struct mrv_problem {
   int device = 0;
+  Prof prof;
   ProblemDesc desc;
   bool has_kepler = false;
   int n_pad = 0, nt = 0;
@@ -199,6 +259,7 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
   DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
                     &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor};
   for (DevBuf* b : bufs) b->release();
+  p->prof.destroy();
   if (p->stream) cudaStreamDestroy(p->stream);
   delete p;
 }
@@ -258,8 +319,22 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
     return (unsigned)n;
   };
 
+  const double T3 = (double)TILE * TILE * TILE;
+  // algorithmic / executed FLOPs of an UPDATE launch over target columns [c0, c1) with np operand columns
+  auto update_flops = [&](int c0, int c1, int np, double* exec_f) {
+    double alg_f = 0.0, ex = 0.0;
+    for (int j = c0; j < c1; ++j) {
+      const double offdiag = (double)(nt - j - 1);
+      alg_f += (offdiag * 2.0 * T3 + (double)TILE * (TILE + 1) * TILE) * np;
+      ex += (offdiag + 1.0) * 2.0 * T3 * np;
+    }
+    *exec_f = ex * (double)B;
+    return alg_f * (double)B;
+  };
+  p->prof.begin(CAT_GEN, st, 0.0, 0.0);
   gen_column_kernel<<<dim3(nt, (unsigned)B), 256, 0, st>>>(N, nt, 0, D.kernel_id, D.variant, D.nh, p->d_t, p->d_yerr,
                                                             hp_wave, A, walker_stride);
+  p->prof.end(st);
   p->launches++;
   for (int p0 = 0; p0 < nt; p0 += PW) {
     const int p1 = std::min(p0 + PW, nt);
@@ -271,16 +346,25 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
         g.p_begin = p0;
         g.p_end = k;
         g.gen = (p0 == 0);
+        double ex = 0.0;
+        const double al = update_flops(k, k + 1, k - p0, &ex);
+        p->prof.begin(CAT_UPDATE_PANEL, st, al, ex);
         gemm_tile_kernel<<<dim3(tiles_in_cols(k, k + 1), (unsigned)B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+        p->prof.end(st);
         p->launches++;
       }
+      p->prof.begin(CAT_POTRF, st, (T3 / 3.0 + 2.0 * TILE * TILE) * (double)B, 1.5 * T3 * (double)B);
       potrf_tile_kernel<<<(unsigned)B, 256, POTRF_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad, zbuf,
                                                                     logdet, quad, fstatus);
+      p->prof.end(st);
       p->launches++;
       if (k + 1 < nt) {
         g.mode = GEMM_TRSM;
         g.k = k;
+        p->prof.begin(CAT_TRSM, st, (T3 + 2.0 * TILE * TILE) * (nt - k - 1) * (double)B,
+                      2.0 * T3 * (nt - k - 1) * (double)B);
         gemm_tile_kernel<<<dim3(nt - k - 1, (unsigned)B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+        p->prof.end(st);
         p->launches++;
       }
     }
@@ -291,7 +375,11 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
       g.p_begin = p0;
       g.p_end = p1;
       g.gen = (p0 == 0);
+      double ex = 0.0;
+      const double al = update_flops(p1, nt, p1 - p0, &ex);
+      p->prof.begin(CAT_UPDATE_TRAIL, st, al, ex);
       gemm_tile_kernel<<<dim3(tiles_in_cols(p1, nt), (unsigned)B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+      p->prof.end(st);
       p->launches++;
     }
   }
@@ -312,9 +400,12 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   if (path == MRV_PATH_FUSED_SMEM) {
     if (D.N > SMALL_N_MAX) return fail(-1, "fused shared-memory path needs N <= %d (N=%d)", SMALL_N_MAX, D.N);
     const size_t smem = small_smem_bytes(D.N);
+    const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)W;
+    p->prof.begin(CAT_FUSED, st, fl, fl);
     fused_small_logl_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp,
                                                                           d_modpar, d_model_given, to_ecc, d_logl,
                                                                           d_status);
+    p->prof.end(st);
     p->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -348,18 +439,22 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   CU(cudaMemsetAsync(p->logdet.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->quad.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->fstatus.p, 0, (size_t)W * sizeof(int), st));
+  p->prof.begin(CAT_MEAN, st, 0.0, 0.0);
   mean_residual_kernel<<<(unsigned)W, 256, 0, st>>>(D, p->d_t, p->d_y, p->d_flags, d_modpar, d_model_given, to_ecc,
                                                     p->resid.as<double>(), p->n_pad, p->escratch.as<double>(),
                                                     p->phys.as<double>(), p->nonfinite.as<int>());
+  p->prof.end(st);
   p->launches++;
   CU(cudaGetLastError());
   for (int64_t w0 = 0; w0 < W; w0 += B) {
     if ((rc = run_wave(p, d_hp, w0, std::min<int64_t>(B, W - w0), st))) return rc;
   }
+  p->prof.begin(CAT_FINAL, st, 0.0, 0.0);
   finalize_logl_kernel<<<(unsigned)((W + 127) / 128), 128, 0, st>>>(D, (int)W, d_hp, p->phys.as<double>(),
                                                                     p->logdet.as<double>(), p->quad.as<double>(),
                                                                     p->nonfinite.as<int>(), p->fstatus.as<int>(), d_logl,
                                                                     d_status);
+  p->prof.end(st);
   p->launches++;
   CU(cudaGetLastError());
   return 0;
@@ -565,6 +660,10 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->wave_opt = value;
   } else if (!strcmp(key, "panel_tiles")) {
     p->panel_opt = (int)value;
+  } else if (!strcmp(key, "profile")) {
+    cudaSetDevice(p->device);
+    p->prof.reset();
+    p->prof.on = value != 0;
   } else {
     return fail(-1, "unknown option '%s'", key);
   }
@@ -578,6 +677,24 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "wave_walkers")) return p->wave_cur;
   if (!strcmp(key, "n_pad")) return p->n_pad;
   if (!strcmp(key, "small_n_max")) return SMALL_N_MAX;
+  if (!strncmp(key, "prof_", 5)) {
+    // prof_<ns|alg|exec|n>_<category>; the caller must have synchronised the stream it launched on
+    cudaSetDevice(p->device);
+    p->prof.collect();
+    const char* rest = key + 5;
+    const char* us = strchr(rest, '_');
+    if (!us) return -1;
+    const std::string what(rest, us - rest);
+    for (int c = 0; c < CAT_COUNT; ++c) {
+      if (!strcmp(us + 1, kCatNames[c])) {
+        if (what == "ns") return (int64_t)p->prof.ns[c];
+        if (what == "alg") return (int64_t)p->prof.alg[c];
+        if (what == "exec") return (int64_t)p->prof.exec[c];
+        if (what == "n") return p->prof.n[c];
+      }
+    }
+    return -1;
+  }
   if (!strcmp(key, "workspace_bytes")) {
     int64_t s = 0;
     DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
