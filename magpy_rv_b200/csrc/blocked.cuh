@@ -49,6 +49,14 @@ __device__ __forceinline__ void dmma_16816(double (&d)[4], const double (&a)[8],
         "d"(b[1]), "d"(b[2]), "d"(b[3]));
 }
 
+// D(16x8) += A(16x4) * B(4x8): a0 = A[g][tig], a1 = A[g+8][tig], b0 = B[tig][g]  (2 x DMMA.8x8x4)
+__device__ __forceinline__ void dmma_1684(double (&d)[4], double a0, double a1, double b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+      : "d"(a0), "d"(a1), "d"(b0));
+}
+
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
@@ -60,8 +68,10 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ------------------------------------------------------------------------------------------------
 // Covariance value of global element (gi, gj) of the padded matrix.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double gen_element(const CovParams& cp, int N, int gi, int gj, double ti, double tj,
-                                              const double* __restrict__ yerr) {
+// (deliberately not inlined: the GEMM epilogue calls it from 64 unrolled sites and the covariance
+// switch with its fp64 sin/exp expansions would otherwise be replicated 64 times)
+__device__ __noinline__ double gen_element(const CovParams& cp, int N, int gi, int gj, double ti, double tj,
+                                           const double* __restrict__ yerr) {
   if (gi < N && gj < N) return (gi == gj) ? cov_diag(cp, yerr[gi]) : cov_eval(cp, ti, tj);
   return (gi == gj) ? 1.0 : 0.0;
 }
@@ -285,47 +295,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) 
   }
   if (g.mode == GEMM_TRSM && tid < TILE) zs[tid] = g.zbuf[(size_t)b * TILE + tid];
 
-  double acc[4][4][4];
-#pragma unroll
-  for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-      for (int v = 0; v < 4; ++v) acc[mi][ni][v] = 0.0;
-
-  for (int q = 0; q < nslices; ++q) {
-    cp_async_wait<GEMM_STAGES - 2>();
-    __syncthreads();
-    {
-      const int qn = q + GEMM_STAGES - 1;
-      if (qn < nslices) load_slice(stages + (qn % GEMM_STAGES) * GEMM_STAGE_DOUBLES, a_src(qn), b_src(qn), tid);
-      cp_async_commit();
-    }
-    const double* As = stages + (q % GEMM_STAGES) * GEMM_STAGE_DOUBLES;
-    const double* Bs = As + SLICE_ELEMS;
-    double bf[4][4];
-#pragma unroll
-    for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-      for (int v = 0; v < 4; ++v) bf[ni][v] = Bs[((v * 16 + (wn * 4 + ni)) << 5) + lane];
-#pragma unroll
-    for (int mi = 0; mi < 4; ++mi) {
-      double af[8];
-#pragma unroll
-      for (int v = 0; v < 8; ++v) af[v] = As[(((v >> 1) * 16 + (wm * 8 + mi * 2 + (v & 1))) << 5) + lane];
-#pragma unroll
-      for (int ni = 0; ni < 4; ++ni) dmma_16816(acc[mi][ni], af, bf[ni]);
-    }
-  }
-  cp_async_wait<0>();
-  __syncthreads();
-
-  // epilogue ------------------------------------------------------------------------------------
+  // Accumulators start at -C_old (UPDATE: loaded from HBM, or generated from t on first touch) so the
+  // epilogue is a pure negate-and-store: acc = A B^T - C_old  ->  C_new = -acc.  The 32 16-byte loads
+  // per thread land directly in the accumulator registers (maximum memory-level parallelism) and
+  // overlap with the cp.async pipeline fill.  TRSM starts from zero.
   double* Ct = Aw + tile_index(ti, tj) * TILE_ELEMS;
-  // element (R, C): R = wm*64 + mi*16 + gq + 8*v1, C = wn*32 + ni*8 + 2*tig + v0
-  if (g.mode == GEMM_UPDATE) {
-    CovParams cp;
-    if (g.gen) cp = make_cov_params(g.kernel_id, g.variant, g.hp_wave + (size_t)b * g.nh);
+  double acc[4][4][4];
+  if (g.mode == GEMM_UPDATE && !g.gen) {
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -334,20 +310,88 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) 
         for (int v1 = 0; v1 < 2; ++v1) {
           const int R = wm * 64 + mi * 16 + gq + 8 * v1;
           const int C = wn * 32 + ni * 8 + 2 * tig;
-          double2* p = reinterpret_cast<double2*>(Ct + tile_off(R, C));
-          double2 old;
-          if (g.gen) {
-            old.x = gen_element(cp, g.N, ti * TILE + R, tj * TILE + C, tis[R], tjs[C], g.yerr);
-            old.y = gen_element(cp, g.N, ti * TILE + R, tj * TILE + C + 1, tis[R], tjs[C + 1], g.yerr);
-          } else {
-            old = *p;
-          }
-          old.x -= acc[mi][ni][2 * v1 + 0];
-          old.y -= acc[mi][ni][2 * v1 + 1];
-          *p = old;
+          const double2 old = __ldcs(reinterpret_cast<const double2*>(Ct + tile_off(R, C)));
+          acc[mi][ni][2 * v1 + 0] = -old.x;
+          acc[mi][ni][2 * v1 + 1] = -old.y;
+        }
+  } else if (g.mode == GEMM_UPDATE) {
+    __syncthreads();  // tis / tjs
+    const CovParams cp = make_cov_params(g.kernel_id, g.variant, g.hp_wave + (size_t)b * g.nh);
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int R = wm * 64 + mi * 16 + gq + 8 * (v >> 1);
+          const int C = wn * 32 + ni * 8 + 2 * tig + (v & 1);
+          acc[mi][ni][v] = -gen_element(cp, g.N, ti * TILE + R, tj * TILE + C, tis[R], tjs[C], g.yerr);
+        }
+  } else {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[mi][ni][v] = 0.0;
+  }
+
+  // main loop: per k16 slice four k4 steps; within a k4 step the 16 m16n8k4 MMAs (= 32 DMMA.8x8x4)
+  // touch 16 different accumulators, so no DMMA ever waits on the previous one's result; the
+  // fragments of step kk+1 are fetched from smem while step kk issues.
+  const int a_lane = ((wm * 8) << 5) + lane;
+  const int b_lane = ((wn * 4) << 5) + lane;
+  for (int q = 0; q < nslices; ++q) {
+    cp_async_wait<GEMM_STAGES - 2>();
+    __syncthreads();
+    {
+      const int qn = q + GEMM_STAGES - 1;
+      if (qn < nslices) load_slice(stages + (qn % GEMM_STAGES) * GEMM_STAGE_DOUBLES, a_src(qn), b_src(qn), tid);
+      cp_async_commit();
+    }
+    const double* As = stages + (q % GEMM_STAGES) * GEMM_STAGE_DOUBLES + a_lane;
+    const double* Bs = stages + (q % GEMM_STAGES) * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
+    double af[2][8], bf[2][4];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) af[0][v] = As[v << 5];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) bf[0][v] = Bs[v << 5];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int cur = kk & 1, nxt = cur ^ 1;
+      if (kk < 3) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) af[nxt][v] = As[(((kk + 1) * 16 + v) << 5)];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bf[nxt][v] = Bs[(((kk + 1) * 16 + v) << 5)];
+      }
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
+    }
+  }
+  cp_async_wait<0>();
+
+  // epilogue ------------------------------------------------------------------------------------
+  // element (R, C): R = wm*64 + mi*16 + gq + 8*v1, C = wn*32 + ni*8 + 2*tig + v0
+  if (g.mode == GEMM_UPDATE) {
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int v1 = 0; v1 < 2; ++v1) {
+          const int R = wm * 64 + mi * 16 + gq + 8 * v1;
+          const int C = wn * 32 + ni * 8 + 2 * tig;
+          double2 o;
+          o.x = -acc[mi][ni][2 * v1 + 0];
+          o.y = -acc[mi][ni][2 * v1 + 1];
+          *reinterpret_cast<double2*>(Ct + tile_off(R, C)) = o;
         }
   } else {
     // TRSM: X = acc is L(i,k); store it and fold r_i -= X z_k
+    __syncthreads();  // zs
     double rowsum[4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)

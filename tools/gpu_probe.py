@@ -14,7 +14,7 @@ if len(sys.argv) > 1:
 for N, W in sizes:
     cfg = workloads.make_config("C5", W=W, N=N)
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"])
-    for panel in ((1, 2, 4) if N > 168 else (1,)):
+    for panel in ((2, 4, 8, 16) if N > 168 else (1,)):
         prob.set_option("panel_tiles", panel)
         prob.logl(cfg["hp"], cfg["modpar"])
         torch.cuda.synchronize()
