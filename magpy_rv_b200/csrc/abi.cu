@@ -131,6 +131,7 @@ struct mrv_problem {
   int path_opt = MRV_PATH_AUTO;
   int64_t wave_opt = 0;
   int panel_opt = 0;
+  int gemm_impl = 0;  // 0 = bulk-copy (TMA) + mbarrier pipeline, 1 = cp.async pipeline
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging
   DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor;
@@ -272,7 +273,8 @@ static int set_attrs(mrv_problem* p) {
   if (p->attrs_set) return 0;
   CU(cudaFuncSetAttribute(fused_small_logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(gemm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TMA_SMEM_BYTES));
   p->attrs_set = true;
   return 0;
 }
@@ -295,7 +297,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   double* quad = p->quad.as<double>() + w0;
   int* fstatus = p->fstatus.as<int>() + w0;
   const double* hp_wave = d_hp + (size_t)w0 * D.nh;
-  const int PW = std::max(1, p->panel_opt > 0 ? p->panel_opt : 4);
+  const int PW = std::max(1, p->panel_opt > 0 ? p->panel_opt : 8);
 
   GemmArgs g;
   memset(&g, 0, sizeof g);
@@ -319,6 +321,11 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
     return (unsigned)n;
   };
 
+  const bool use_tma = p->gemm_impl == 0;
+  auto launch_gemm = [&](dim3 grid) {
+    if (use_tma) gemm_tile_kernel<true><<<grid, GEMM_TMA_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g);
+    else gemm_tile_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+  };
   const double T3 = (double)TILE * TILE * TILE;
   // algorithmic / executed FLOPs of an UPDATE launch over target columns [c0, c1) with np operand columns
   auto update_flops = [&](int c0, int c1, int np, double* exec_f) {
@@ -349,7 +356,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
         double ex = 0.0;
         const double al = update_flops(k, k + 1, k - p0, &ex);
         p->prof.begin(CAT_UPDATE_PANEL, st, al, ex);
-        gemm_tile_kernel<<<dim3(tiles_in_cols(k, k + 1), (unsigned)B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+        launch_gemm(dim3(tiles_in_cols(k, k + 1), (unsigned)B));
         p->prof.end(st);
         p->launches++;
       }
@@ -363,7 +370,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
         g.k = k;
         p->prof.begin(CAT_TRSM, st, (T3 + 2.0 * TILE * TILE) * (nt - k - 1) * (double)B,
                       2.0 * T3 * (nt - k - 1) * (double)B);
-        gemm_tile_kernel<<<dim3(nt - k - 1, (unsigned)B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+        launch_gemm(dim3(nt - k - 1, (unsigned)B));
         p->prof.end(st);
         p->launches++;
       }
@@ -378,7 +385,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
       double ex = 0.0;
       const double al = update_flops(p1, nt, p1 - p0, &ex);
       p->prof.begin(CAT_UPDATE_TRAIL, st, al, ex);
-      gemm_tile_kernel<<<dim3(tiles_in_cols(p1, nt), (unsigned)B), GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+      launch_gemm(dim3(tiles_in_cols(p1, nt), (unsigned)B));
       p->prof.end(st);
       p->launches++;
     }
@@ -660,6 +667,9 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->wave_opt = value;
   } else if (!strcmp(key, "panel_tiles")) {
     p->panel_opt = (int)value;
+  } else if (!strcmp(key, "gemm_impl")) {
+    if (value < 0 || value > 1) return fail(-1, "gemm_impl must be 0 (bulk copy + mbarrier) or 1 (cp.async)");
+    p->gemm_impl = (int)value;
   } else if (!strcmp(key, "profile")) {
     cudaSetDevice(p->device);
     p->prof.reset();

@@ -235,16 +235,65 @@ __device__ __forceinline__ void load_slice(double* stage, const double* __restri
   }
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) {
+// ---- mbarrier / bulk-copy (TMA engine, 1-D) primitives -------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+#define GEMM_TMA_STAGES 4
+#define GEMM_TMA_THREADS GEMM_THREADS
+#define GEMM_TMA_SMEM_BYTES \
+  ((size_t)GEMM_TMA_STAGES * GEMM_STAGE_DOUBLES * sizeof(double) + (2 * TILE + 4 * TILE + TILE) * sizeof(double) + 2 * GEMM_TMA_STAGES * sizeof(unsigned long long))
+
+// One kernel body, two operand-feed variants:
+//   TMA = true : one elected lane streams the k16 operand slices with
+//                1-D bulk copies (cp.async.bulk, the TMA engine) into a 4-stage ring guarded by
+//                full/empty mbarriers; the 8 consumer warps never meet at a CTA-wide barrier and
+//                fetch the first fragments of slice q+1 while the last MMAs of slice q issue.
+//   TMA = false: all 256 threads issue 16-byte cp.async (LDGSTS) into a 3-stage ring with one
+//                __syncthreads per slice (kept as an A/B reference, option "gemm_impl" = 1).
+template <bool TMA>
+__global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) {
   extern __shared__ double smem[];
+  constexpr int NST = TMA ? GEMM_TMA_STAGES : GEMM_STAGES;
   double* stages = smem;
-  double* tis = smem + GEMM_STAGES * GEMM_STAGE_DOUBLES;  // 128: t of the tile rows
-  double* tjs = tis + TILE;                               // 128: t of the tile cols
-  double* part = tjs + TILE;                              // 4 x 128 GEMV partials
-  double* zs = part + 4 * TILE;                           // 128: z_k
+  double* tis = smem + NST * GEMM_STAGE_DOUBLES;  // 128: t of the tile rows
+  double* tjs = tis + TILE;                       // 128: t of the tile cols
+  double* part = tjs + TILE;                      // 4 x 128 GEMV partials
+  double* zs = part + 4 * TILE;                   // 128: z_k
+  unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(zs + TILE);
+  unsigned long long* empty_bar = full_bar + GEMM_TMA_STAGES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 2, wn = warp & 3;  // 2 x 4 warp grid
+  const int wm = (warp >> 2) & 1, wn = warp & 3;  // 2 x 4 consumer warp grid
   const int gq = lane >> 2, tig = lane & 3;
   const int b = blockIdx.y;
   double* Aw = g.Abase + (size_t)b * g.walker_stride;
@@ -278,12 +327,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) 
     return Aw + tix * TILE_ELEMS + s * SLICE_ELEMS;
   };
 
-  // prologue
+  if (TMA) {
+    if (tid == 0) {
+      for (int s = 0; s < GEMM_TMA_STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);   // one arrive (the producer's expect_tx) + 32 KiB of bytes
+        mbar_init(&empty_bar[s], 8);  // one arrive per consumer warp
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+      asm volatile("fence.proxy.async;\n" ::: "memory");
+    }
+    __syncthreads();
+    // No dedicated producer warp: 9 warps would be allocated registers as 12 (warp-allocation
+    // granularity 4), capping the kernel at 168 registers and spilling the 64-double accumulator.
+    // Instead one elected lane of warp 0 issues the two bulk copies per slice, two slices ahead.
+    if (tid == 0) {
+      for (int q = 0; q < 2 && q < nslices; ++q) {
+        double* dst = stages + q * GEMM_STAGE_DOUBLES;
+        mbar_expect_tx(&full_bar[q], 2 * SLICE_ELEMS * sizeof(double));
+        bulk_g2s(dst, a_src(q), SLICE_ELEMS * sizeof(double), &full_bar[q]);
+        bulk_g2s(dst + SLICE_ELEMS, b_src(q), SLICE_ELEMS * sizeof(double), &full_bar[q]);
+      }
+    }
+  } else {
 #pragma unroll
-  for (int s = 0; s < GEMM_STAGES - 1; ++s) {
-    if (s < nslices) load_slice(stages + s * GEMM_STAGE_DOUBLES, a_src(s), b_src(s), tid);
-    cp_async_commit();
+    for (int s = 0; s < GEMM_STAGES - 1; ++s) {
+      if (s < nslices) load_slice(stages + s * GEMM_STAGE_DOUBLES, a_src(s), b_src(s), tid);
+      cp_async_commit();
+    }
   }
+
   if (g.mode == GEMM_UPDATE && g.gen) {
     if (tid < TILE) {
       const int gi = ti * TILE + tid;
@@ -298,7 +370,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) 
   // Accumulators start at -C_old (UPDATE: loaded from HBM, or generated from t on first touch) so the
   // epilogue is a pure negate-and-store: acc = A B^T - C_old  ->  C_new = -acc.  The 32 16-byte loads
   // per thread land directly in the accumulator registers (maximum memory-level parallelism) and
-  // overlap with the cp.async pipeline fill.  TRSM starts from zero.
+  // overlap with the operand pipeline fill.  TRSM starts from zero.
   double* Ct = Aw + tile_index(ti, tj) * TILE_ELEMS;
   double acc[4][4][4];
   if (g.mode == GEMM_UPDATE && !g.gen) {
@@ -315,7 +387,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) 
           acc[mi][ni][2 * v1 + 1] = -old.y;
         }
   } else if (g.mode == GEMM_UPDATE) {
-    __syncthreads();  // tis / tjs
+    consumer_sync();  // tis / tjs
     const CovParams cp = make_cov_params(g.kernel_id, g.variant, g.hp_wave + (size_t)b * g.nh);
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
@@ -341,21 +413,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) 
   // fragments of step kk+1 are fetched from smem while step kk issues.
   const int a_lane = ((wm * 8) << 5) + lane;
   const int b_lane = ((wn * 4) << 5) + lane;
-  for (int q = 0; q < nslices; ++q) {
-    cp_async_wait<GEMM_STAGES - 2>();
-    __syncthreads();
-    {
-      const int qn = q + GEMM_STAGES - 1;
-      if (qn < nslices) load_slice(stages + (qn % GEMM_STAGES) * GEMM_STAGE_DOUBLES, a_src(qn), b_src(qn), tid);
-      cp_async_commit();
-    }
-    const double* As = stages + (q % GEMM_STAGES) * GEMM_STAGE_DOUBLES + a_lane;
-    const double* Bs = stages + (q % GEMM_STAGES) * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
-    double af[2][8], bf[2][4];
+  double af[2][8], bf[2][4];
+  if (TMA) {
+    mbar_wait(&full_bar[0], 0u);
+    const double* As = stages + a_lane;
+    const double* Bs = stages + SLICE_ELEMS + b_lane;
 #pragma unroll
     for (int v = 0; v < 8; ++v) af[0][v] = As[v << 5];
 #pragma unroll
     for (int v = 0; v < 4; ++v) bf[0][v] = Bs[v << 5];
+  }
+  for (int q = 0; q < nslices; ++q) {
+    const int st = q % NST;
+    if (TMA) {
+      // refill: slice q+2 goes into the stage consumed two iterations ago (one full iteration of
+      // slack, so the wait on its empty barrier is normally already satisfied)
+      const int qn = q + 2;
+      if (tid == 0 && qn < nslices) {
+        const int sn = qn % NST, u = qn / NST;
+        if (u > 0) mbar_wait(&empty_bar[sn], (unsigned)((u - 1) & 1));
+        double* dst = stages + sn * GEMM_STAGE_DOUBLES;
+        mbar_expect_tx(&full_bar[sn], 2 * SLICE_ELEMS * sizeof(double));
+        bulk_g2s(dst, a_src(qn), SLICE_ELEMS * sizeof(double), &full_bar[sn]);
+        bulk_g2s(dst + SLICE_ELEMS, b_src(qn), SLICE_ELEMS * sizeof(double), &full_bar[sn]);
+      }
+      __syncwarp();
+    }
+    if (!TMA) {
+      cp_async_wait<GEMM_STAGES - 2>();
+      __syncthreads();
+      const int qn = q + GEMM_STAGES - 1;
+      if (qn < nslices) load_slice(stages + (qn % GEMM_STAGES) * GEMM_STAGE_DOUBLES, a_src(qn), b_src(qn), tid);
+      cp_async_commit();
+    }
+    const double* As = stages + st * GEMM_STAGE_DOUBLES + a_lane;
+    const double* Bs = stages + st * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
+    if (!TMA) {
+#pragma unroll
+      for (int v = 0; v < 8; ++v) af[0][v] = As[v << 5];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bf[0][v] = Bs[v << 5];
+    }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const int cur = kk & 1, nxt = cur ^ 1;
@@ -364,14 +462,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) 
         for (int v = 0; v < 8; ++v) af[nxt][v] = As[(((kk + 1) * 16 + v) << 5)];
 #pragma unroll
         for (int v = 0; v < 4; ++v) bf[nxt][v] = Bs[(((kk + 1) * 16 + v) << 5)];
+      } else if (TMA && q + 1 < nslices) {
+        // first fragments of the next slice (its stage was filled by the producer long ago)
+        const int sn = (q + 1) % NST;
+        mbar_wait(&full_bar[sn], (unsigned)(((q + 1) / NST) & 1));
+        const double* An = stages + sn * GEMM_STAGE_DOUBLES + a_lane;
+        const double* Bn = stages + sn * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) af[nxt][v] = An[v << 5];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bf[nxt][v] = Bn[v << 5];
       }
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
     }
+    if (TMA) {
+      // this warp has read everything it needs from stage `st`: hand it back to the producer
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[st]);
+    }
   }
-  cp_async_wait<0>();
+  if (!TMA) cp_async_wait<0>();
 
   // epilogue ------------------------------------------------------------------------------------
   // element (R, C): R = wm*64 + mi*16 + gq + 8*v1, C = wn*32 + ni*8 + 2*tig + v0
@@ -391,7 +504,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) 
         }
   } else {
     // TRSM: X = acc is L(i,k); store it and fold r_i -= X z_k
-    __syncthreads();  // zs
+    consumer_sync();  // zs
     double rowsum[4][2];
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
@@ -420,7 +533,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) 
 #pragma unroll
         for (int v1 = 0; v1 < 2; ++v1) part[wn * TILE + wm * 64 + mi * 16 + gq + 8 * v1] = rowsum[mi][v1];
     }
-    __syncthreads();
+    consumer_sync();
     if (tid < TILE) {
       const double s = ((part[tid] + part[TILE + tid]) + part[2 * TILE + tid]) + part[3 * TILE + tid];
       double* ri = g.resid + (size_t)b * g.ldr + (size_t)ti * TILE;

@@ -14,8 +14,9 @@ if len(sys.argv) > 1:
 for N, W in sizes:
     cfg = workloads.make_config("C5", W=W, N=N)
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"])
-    for panel in ((2, 4, 8, 16) if N > 168 else (1,)):
+    for panel, impl in (((8, 0), (8, 1), (16, 0)) if N > 168 else ((1, 0),)):
         prob.set_option("panel_tiles", panel)
+        prob.set_option("gemm_impl", impl)
         prob.logl(cfg["hp"], cfg["modpar"])
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -24,6 +25,6 @@ for N, W in sizes:
             got, st = prob.logl(cfg["hp"], cfg["modpar"])
         dt = (time.perf_counter() - t0) / reps
         fl = workloads.flops_per_eval(N) * W
-        print("N=%5d W=%4d panel=%d path=%d wave=%d: %.3f ms/batch  %.1f evals/s  %.2f TF/s  status_ok=%s"
-              % (N, W, panel, prob.info("path"), prob.info("wave_walkers"), dt * 1e3, W / dt, fl / dt / 1e12, bool(np.all(st == 0))), flush=True)
+        print("N=%5d W=%4d panel=%d impl=%d path=%d wave=%d: %.3f ms/batch  %.1f evals/s  %.2f TF/s  status_ok=%s"
+              % (N, W, panel, impl, prob.info("path"), prob.info("wave_walkers"), dt * 1e3, W / dt, fl / dt / 1e12, bool(np.all(st == 0))), flush=True)
     prob.close()
