@@ -431,6 +431,10 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   }
   B = std::min<int64_t>(B, W);
   B = std::min<int64_t>(B, 65535);
+  {  // equal-sized waves (e.g. 128 walkers with room for 39 -> 4 x 32, not 39+39+39+11)
+    const int64_t nwaves = (W + B - 1) / B;
+    B = (W + nwaves - 1) / nwaves;
+  }
   p->wave_cur = B;
   int rc = 0;
   if ((rc = p->resid.ensure((size_t)W * p->n_pad * sizeof(double)))) return rc;

@@ -14,7 +14,7 @@ if len(sys.argv) > 1:
 for N, W in sizes:
     cfg = workloads.make_config("C5", W=W, N=N)
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"])
-    for panel, impl in (((8, 0), (8, 1), (16, 0)) if N > 168 else ((1, 0),)):
+    for panel, impl in (((4, 0), (8, 0)) if N > 168 else ((1, 0),)):
         prob.set_option("panel_tiles", panel)
         prob.set_option("gemm_impl", impl)
         prob.logl(cfg["hp"], cfg["modpar"])
@@ -25,6 +25,14 @@ for N, W in sizes:
             got, st = prob.logl(cfg["hp"], cfg["modpar"])
         dt = (time.perf_counter() - t0) / reps
         fl = workloads.flops_per_eval(N) * W
+        prob.set_option("profile", 1)
+        prob.logl(cfg["hp"], cfg["modpar"])
+        cats = ("gen", "potrf", "trsm", "update_panel", "update_trail", "mean", "final", "fused")
+        ns = {c: prob.info("prof_ns_" + c) for c in cats}
+        nl = {c: prob.info("prof_n_" + c) for c in cats}
+        prob.set_option("profile", 0)
+        tot = max(1, sum(ns.values()))
+        print("    kernel time shares: " + "  ".join("%s=%.1f%%(%d)" % (c, 100.0 * ns[c] / tot, nl[c]) for c in cats if nl[c]) + "  sum=%.3f ms" % (tot * 1e-6))
         print("N=%5d W=%4d panel=%d impl=%d path=%d wave=%d: %.3f ms/batch  %.1f evals/s  %.2f TF/s  status_ok=%s"
               % (N, W, panel, impl, prob.info("path"), prob.info("wave_walkers"), dt * 1e3, W / dt, fl / dt / 1e12, bool(np.all(st == 0))), flush=True)
     prob.close()
