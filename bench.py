@@ -41,9 +41,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=16384, help="data points N of the C5 sweep")
+    ap.add_argument("--npoints", dest="n", type=int, default=16384, help="data points N of the C5 sweep")
     ap.add_argument("--walkers-per-gpu", type=int, default=128)
-    ap.add_argument("--config", default="C5", help="workload generator (C1..C5)")
+    ap.add_argument("--workload", dest="config", default="C5", help="workload generator (C1..C5)")
     ap.add_argument("--panel", type=int, default=0)
     ap.add_argument("--wave", type=int, default=0)
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
@@ -63,12 +63,22 @@ def host_threads():
         return int(os.cpu_count() or 1)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=int(os.cpu_count() or 1))
+    except Exception:
+        pass
+
+
 def cpu_sample(cfg_name, N_target, budget_s):
     """Time the oracle's LogL on a bounded sample: the largest N_s <= N_target (halving from the
     target) whose predicted cost fits the budget; scale to N_target by the cubic law of the
     factorisations.  Returns (evals_per_s at N_target, description, seconds spent)."""
     import workloads
     from oracle import logl_port as port
+    use_all_host_threads()
     t_start = time.perf_counter()
     n = min(N_target, 1024)
     cfg = workloads.make_config(cfg_name, W=2, N=n)
