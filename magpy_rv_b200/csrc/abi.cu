@@ -132,6 +132,7 @@ struct mrv_problem {
   int64_t wave_opt = 0;
   int panel_opt = 0;
   int gemm_impl = 0;  // 0 = bulk-copy (TMA) + mbarrier pipeline, 1 = cp.async pipeline
+  int potrf_impl = 0;  // 0 = blocked rank-16 sweep with DMMA trailing updates, 1 = rank-1 sweep
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging
   DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor;
@@ -272,7 +273,9 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
 static int set_attrs(mrv_problem* p) {
   if (p->attrs_set) return 0;
   CU(cudaFuncSetAttribute(fused_small_logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(fused_small_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(potrf_tile_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_BLK_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TMA_SMEM_BYTES));
   p->attrs_set = true;
@@ -361,8 +364,12 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
         p->launches++;
       }
       p->prof.begin(CAT_POTRF, st, (T3 / 3.0 + 2.0 * TILE * TILE) * (double)B, 1.5 * T3 * (double)B);
-      potrf_tile_kernel<<<(unsigned)B, 256, POTRF_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad, zbuf,
-                                                                    logdet, quad, fstatus);
+      if (p->potrf_impl == 0)
+        potrf_tile_blk_kernel<<<(unsigned)B, 256, POTRF_BLK_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad,
+                                                                              zbuf, logdet, quad, fstatus);
+      else
+        potrf_tile_kernel<<<(unsigned)B, 256, POTRF_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad, zbuf,
+                                                                      logdet, quad, fstatus);
       p->prof.end(st);
       p->launches++;
       if (k + 1 < nt) {
@@ -406,12 +413,18 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   p->last_path = path;
   if (path == MRV_PATH_FUSED_SMEM) {
     if (D.N > SMALL_N_MAX) return fail(-1, "fused shared-memory path needs N <= %d (N=%d)", SMALL_N_MAX, D.N);
-    const size_t smem = small_smem_bytes(D.N);
+    const bool blk = p->potrf_impl == 0 && D.N <= MRV_SMALL_BLK_N_MAX;
+    const size_t smem = blk ? small_blk_smem_bytes(D.N) : small_smem_bytes(D.N);
     const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)W;
     p->prof.begin(CAT_FUSED, st, fl, fl);
-    fused_small_logl_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp,
-                                                                          d_modpar, d_model_given, to_ecc, d_logl,
-                                                                          d_status);
+    if (blk)
+      fused_small_blk_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp,
+                                                                           d_modpar, d_model_given, to_ecc, d_logl,
+                                                                           d_status);
+    else
+      fused_small_logl_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags,
+                                                                            d_hp, d_modpar, d_model_given, to_ecc,
+                                                                            d_logl, d_status);
     p->prof.end(st);
     p->launches++;
     CU(cudaGetLastError());
@@ -674,6 +687,9 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
   } else if (!strcmp(key, "gemm_impl")) {
     if (value < 0 || value > 1) return fail(-1, "gemm_impl must be 0 (bulk copy + mbarrier) or 1 (cp.async)");
     p->gemm_impl = (int)value;
+  } else if (!strcmp(key, "potrf_impl")) {
+    if (value < 0 || value > 1) return fail(-1, "potrf_impl must be 0 (blocked DMMA sweep) or 1 (rank-1 sweep)");
+    p->potrf_impl = (int)value;
   } else if (!strcmp(key, "profile")) {
     cudaSetDevice(p->device);
     p->prof.reset();

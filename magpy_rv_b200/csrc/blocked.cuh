@@ -195,6 +195,246 @@ potrf_tile_kernel(int k, int N, double* __restrict__ Abase, size_t walker_stride
 }
 
 // ------------------------------------------------------------------------------------------------
+// Blocked (rank-16) form of the same sweep, trailing updates on the FP64 tensor pipe.
+//
+// S is column-major with ld = 136 (== 8 mod 16: the transposed accumulator fragments below are
+// conflict-free 16-byte accesses; thread-per-row column walks are conflict-free for any ld).
+// Per block step kb (pivot columns K = [16 kb, 16 kb + 16)):
+//   1. the 16 x 16 pivot block D is swept by the scalar algorithm (256 threads, one element each);
+//   2. every other row rho (inverse rows < 16 kb, factor rows >= 16 kb + 16, residual row 128)
+//      finishes its 16 panel entries with a 120-FMA triangular recurrence (one thread per row);
+//      the panel is written back to S and staged as MMA operands
+//         PA[rho][j]  = panel value (pivot rows: unit upper triangle of the inverse block)
+//         PB[c][j]    = -S[c][j] / d_j
+//   3. S[rho][c] += sum_j PA[rho][j] PB[c][j] for all trailing columns c (pivot rows start from 0:
+//      assignment) as DMMA tiles, computed transposed (M = c, N = rho) so accumulators map to
+//      contiguous 16-byte smem accesses; tiles lying wholly in the not-yet-activated part of the
+//      upper triangle are skipped.
+// ------------------------------------------------------------------------------------------------
+#define PB_NB 16
+#define PB_LD 136
+#define PB_PA_LD 148   // == 4 mod 16: conflict-free B-fragment loads
+#define PB_PB_LD 132   // == 4 mod 16: conflict-free A-fragment loads
+#define PB_D_LD 17
+#define POTRF_BLK_SMEM_DOUBLES (PB_LD * TILE + PB_NB * PB_PA_LD + PB_NB * PB_PB_LD + PB_NB * PB_D_LD + PB_NB + 64 + TILE)
+#define POTRF_BLK_SMEM_BYTES ((size_t)POTRF_BLK_SMEM_DOUBLES * sizeof(double))
+
+__device__ __forceinline__ void dmma_1684_neg0(double (&d)[4], double a0, double a1, double b0) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k4.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};\n"
+      : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
+      : "d"(a0), "d"(a1), "d"(b0));
+}
+
+// Sweeps the n_cols x n_cols matrix held in S (column-major, ld = PB_LD, lower triangle valid, row
+// `n_cols` = residual) in place.  n_cols must be a multiple of 16; ld == 8 (mod 16), ld >= rows rounded up to 8, ld <= 256;
+// pa_ld, pb_ld == 4 (mod 16).  With WITH_INV the
+// strict upper triangle receives the unscaled inverse factor (see potrf_tile_kernel above);
+// without it only factor rows and the residual row are carried (fused small-N kernel).
+template <bool WITH_INV>
+__device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, double* PA, const int pa_ld, double* PB,
+                                       const int pb_ld, double* D, double* wv) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tig = lane & 3;
+  const int n_rows = n_cols + 1;                 // + residual row
+  const int n_rows8 = (n_rows + 7) & ~7;         // rows covered by n8 MMA tiles (padding rows are zero)
+  const int nblk = n_cols / PB_NB;
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int k0 = kb * PB_NB;
+    // ---- 1. pivot block -------------------------------------------------------------------
+    {
+      const int r = tid >> 4, c = tid & 15;
+      double v = S[(k0 + r) + (size_t)(k0 + c) * ld];
+      D[r * PB_D_LD + c] = v;
+      __syncthreads();
+      for (int j = 0; j < PB_NB - 1; ++j) {
+        if (c > j && (r >= c || r <= j)) {
+          const double w = 1.0 / D[j * PB_D_LD + j];
+          const double beta = D[c * PB_D_LD + j] * w;
+          if (r == j) v = -beta;
+          else v = fma(-D[r * PB_D_LD + j], beta, v);
+          D[r * PB_D_LD + c] = v;
+        }
+        __syncthreads();
+      }
+      if (r == c) wv[r] = 1.0 / v;
+      S[(k0 + r) + (size_t)(k0 + c) * ld] = v;     // final block (lower: factor, upper: inverse part)
+      __syncthreads();
+      // multipliers beta[j][jp] = D[j][jp] / d_jp (j > jp), in place, for the row recurrences below
+      if (c < r) D[r * PB_D_LD + c] = v * wv[c];
+      __syncthreads();
+    }
+    // ---- 2. panel rows ----------------------------------------------------------------------
+    if (tid < ld) {
+      const int rho = tid;
+      const bool pivot_row = rho >= k0 && rho < k0 + PB_NB;
+      const bool active = rho < n_rows && !pivot_row && (WITH_INV || rho >= k0 + PB_NB);
+      double x[PB_NB];
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < PB_NB; ++j) x[j] = S[rho + (size_t)(k0 + j) * ld];
+        // right-looking order: the inner updates are independent (ILP), only x[jp] is on the chain
+#pragma unroll
+        for (int jp = 0; jp < PB_NB - 1; ++jp) {
+#pragma unroll
+          for (int j = jp + 1; j < PB_NB; ++j) x[j] = fma(-x[jp], D[j * PB_D_LD + jp], x[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < PB_NB; ++j) S[rho + (size_t)(k0 + j) * ld] = x[j];
+      } else if (pivot_row) {
+        const int r = rho - k0;
+#pragma unroll
+        for (int j = 0; j < PB_NB; ++j) x[j] = (j == r) ? 1.0 : (j > r ? D[r * PB_D_LD + j] : 0.0);
+      } else {
+#pragma unroll
+        for (int j = 0; j < PB_NB; ++j) x[j] = 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < PB_NB; ++j) PA[j * pa_ld + rho] = x[j];
+      if (rho < n_cols) {
+#pragma unroll
+        for (int j = 0; j < PB_NB; ++j) PB[j * pb_ld + rho] = (rho >= k0 + PB_NB && rho < n_cols) ? -x[j] * wv[j] : 0.0;
+      }
+    }
+    __syncthreads();
+    // ---- 3. trailing update on the tensor pipe -------------------------------------------------
+    const int c_begin = k0 + PB_NB;
+    const int n_m16 = (n_cols - c_begin) / 16;
+    const int n_n8 = n_rows8 / 8;
+    // each warp owns row tiles tn = warp, warp + 8, warp + 16 (n_n8 <= 24); their three accumulator
+    // chains are interleaved so consecutive DMMAs are independent
+    int rho0s[3];
+    bool live[3], pivot[3];
+    double bfr[3][4];
+#pragma unroll
+    for (int sl = 0; sl < 3; ++sl) {
+      const int tn = warp + 8 * sl;
+      rho0s[sl] = tn * 8;
+      live[sl] = tn < n_n8 && (WITH_INV || rho0s[sl] + 7 >= c_begin);
+      pivot[sl] = rho0s[sl] >= k0 && rho0s[sl] < k0 + PB_NB;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) bfr[sl][kk] = live[sl] ? PA[(kk * 4 + tig) * pa_ld + rho0s[sl] + gq] : 0.0;
+    }
+    for (int tm = 0; tm < n_m16; ++tm) {
+      const int c0 = c_begin + tm * 16;
+      double a0[4], a1[4];
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        a0[kk] = PB[(kk * 4 + tig) * pb_ld + c0 + gq];
+        a1[kk] = PB[(kk * 4 + tig) * pb_ld + c0 + gq + 8];
+      }
+      double acc[3][4];
+      bool need[3];
+#pragma unroll
+      for (int sl = 0; sl < 3; ++sl) {
+        // needed if the rows are inverse/pivot rows (rho < c_begin) or contain factor rows (rho >= c)
+        need[sl] = live[sl] && (rho0s[sl] < c_begin || rho0s[sl] + 7 >= c0);
+        if (need[sl] && !pivot[sl]) {
+          const double2 u = *reinterpret_cast<const double2*>(S + (rho0s[sl] + 2 * tig) + (size_t)(c0 + gq) * ld);
+          const double2 v = *reinterpret_cast<const double2*>(S + (rho0s[sl] + 2 * tig) + (size_t)(c0 + gq + 8) * ld);
+          acc[sl][0] = u.x; acc[sl][1] = u.y; acc[sl][2] = v.x; acc[sl][3] = v.y;
+        } else {
+          acc[sl][0] = acc[sl][1] = acc[sl][2] = acc[sl][3] = 0.0;
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int sl = 0; sl < 3; ++sl)
+          if (need[sl]) dmma_1684_neg0(acc[sl], a0[kk], a1[kk], bfr[sl][kk]);   // warp-uniform predicate
+#pragma unroll
+      for (int sl = 0; sl < 3; ++sl) {
+        if (need[sl]) {
+          double2 u, v;
+          u.x = acc[sl][0]; u.y = acc[sl][1]; v.x = acc[sl][2]; v.y = acc[sl][3];
+          *reinterpret_cast<double2*>(S + (rho0s[sl] + 2 * tig) + (size_t)(c0 + gq) * ld) = u;
+          *reinterpret_cast<double2*>(S + (rho0s[sl] + 2 * tig) + (size_t)(c0 + gq + 8) * ld) = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+potrf_tile_blk_kernel(int k, int N, double* __restrict__ Abase, size_t walker_stride, double* __restrict__ resid,
+                      int ldr, double* __restrict__ zbuf, double* __restrict__ acc_logdet,
+                      double* __restrict__ acc_quad, int* __restrict__ status) {
+  extern __shared__ double smem[];
+  double* S = smem;
+  double* PA = S + (size_t)PB_LD * TILE;
+  double* PBm = PA + PB_NB * PB_PA_LD;
+  double* D = PBm + PB_NB * PB_PB_LD;
+  double* wv = D + PB_NB * PB_D_LD;
+  double* red = wv + PB_NB;
+  int* ired = (int*)(red + 32);
+  double* isd_s = red + 64;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double* tile = Abase + (size_t)b * walker_stride + tile_index(k, k) * TILE_ELEMS;
+  double* rk = resid + (size_t)b * ldr + (size_t)k * TILE;
+
+  // 16 independent 16-byte loads in flight per thread (the tile is 128 KiB of latency-bound traffic)
+#pragma unroll 1
+  for (int base = 0; base < TILE_ELEMS / 2; base += 256 * 16) {
+    double2 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldcs(reinterpret_cast<const double2*>(tile) + base + u * 256 + tid);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = 2 * (base + u * 256 + tid);
+      const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7, k3 = e & 3;
+      const int R = m8 * 8 + g, C = kg * 4 + k3;
+      S[R + (size_t)C * PB_LD] = v[u].x;
+      S[R + (size_t)(C + 1) * PB_LD] = v[u].y;
+    }
+  }
+  if (tid < TILE) {
+    S[TILE + (size_t)tid * PB_LD] = rk[tid];
+#pragma unroll
+    for (int r = TILE + 1; r < PB_LD; ++r) S[r + (size_t)tid * PB_LD] = 0.0;   // padding rows of the n8 tiles
+  }
+  __syncthreads();
+  cta_block_sweep<true>(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, D, wv);
+
+  double ld_part = 0.0, q_part = 0.0;
+  int first_bad = 0x7fffffff, nan_seen = 0;
+  double isd = 0.0;
+  if (tid < TILE) {
+    const double d = S[tid + (size_t)tid * PB_LD];
+    if (!(d > 0.0)) {
+      first_bad = k * TILE + tid + 1;
+      nan_seen = isnan(d) ? 1 : 0;
+    }
+    isd = 1.0 / sqrt(d);
+    ld_part = log(d);
+    const double z = S[TILE + (size_t)tid * PB_LD] * isd;
+    q_part = z * z;
+    zbuf[(size_t)b * TILE + tid] = z;
+  }
+  const double logdet = block_sum(ld_part, red);
+  const double quad = block_sum(q_part, red);
+  const int fb = -block_max_int(-first_bad, ired);
+  const int anynan = block_max_int(nan_seen, ired);
+  if (tid == 0) {
+    acc_logdet[b] += logdet;
+    acc_quad[b] += quad;
+    if (status[b] == 0 && fb != 0x7fffffff) status[b] = anynan ? -1 : fb;
+  }
+  if (tid < TILE) isd_s[tid] = isd;
+  __syncthreads();
+  for (int e2 = tid; e2 < TILE_ELEMS / 2; e2 += 256) {
+    const int e = 2 * e2;
+    const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7, k3 = e & 3;
+    const int R = m8 * 8 + g, C = kg * 4 + k3;
+    const double s = isd_s[R];
+    double2 o;
+    o.x = (C < R) ? S[C + (size_t)R * PB_LD] * s : (C == R ? s : 0.0);
+    o.y = (C + 1 < R) ? S[C + 1 + (size_t)R * PB_LD] * s : (C + 1 == R ? s : 0.0);
+    reinterpret_cast<double2*>(tile)[e2] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // DMMA tile GEMM: acc(128x128) = sum over operand tile pairs of A_p * B_p^T, K = 128 per pair.
 // 8 warps as 2 (m) x 4 (n): warp tile 64 x 32 = 4 m16-fragments x 4 n8-fragments.
 // 3-stage cp.async pipeline over k16 slices (16 KiB of A + 16 KiB of B per stage).
@@ -293,7 +533,13 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
   unsigned long long* empty_bar = full_bar + GEMM_TMA_STAGES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = (warp >> 2) & 1, wn = warp & 3;  // 2 x 4 consumer warp grid
+  // 2 x 4 warp grid.  In TRSM the B operand inv(L_kk) is lower triangular, so the warp owning output
+  // columns [32 wn, 32 wn + 32) only needs k16 slices 0 .. 2 wn + 1; the two warps that share an SM
+  // sub-partition (warp, warp + 4) are given wn and 3 - wn so every sub-partition issues 10 of the
+  // 16 warp-slices (balanced 37.5 % saving instead of an idle/busy split).
+  const int wm = (warp >> 2) & 1;
+  const int wn = (g.mode == GEMM_TRSM && wm) ? 3 - (warp & 3) : (warp & 3);
+  const int q_last = (g.mode == GEMM_TRSM) ? 2 * wn + 1 : 0x7fffffff;
   const int gq = lane >> 2, tig = lane & 3;
   const int b = blockIdx.y;
   double* Aw = g.Abase + (size_t)b * g.walker_stride;
@@ -473,10 +719,12 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
 #pragma unroll
         for (int v = 0; v < 4; ++v) bf[nxt][v] = Bn[v << 5];
       }
+      if (q <= q_last) {   // warp-uniform
 #pragma unroll
-      for (int mi = 0; mi < 4; ++mi)
+        for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
+          for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
+      }
     }
     if (TMA) {
       // this warp has read everything it needs from stage `st`: hand it back to the producer

@@ -14,6 +14,7 @@
 // smem: column-major (N+1) x N with an odd leading dimension (bank-conflict-free rows and
 // columns) + t + r + small vectors.  N <= 168 fits the 227 KB opt-in limit.
 #pragma once
+#include "blocked.cuh"
 #include "mean_model.cuh"
 
 #define MRV_SMALL_THREADS 256
@@ -106,6 +107,115 @@ fused_small_logl_kernel(ProblemDesc D, const double* __restrict__ t, const doubl
   const int anybad = block_max_int(bad, ired);
 
   // 5. closed form + priors
+  if (tid == 0) {
+    double v = -((double)N / 2.0) * log(2.0 * MRV_PI) - 0.5 * logdet - 0.5 * quad;
+    v = add_priors(D, hpv, phys, v);
+    int st = 0;
+    if (anybad) st = -1;
+    else if (fb != 0x7fffffff) st = fb;
+    logl_out[w] = v;
+    status_out[w] = st;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Same fused pipeline with the rank-16 blocked sweep (blocked.cuh, cta_block_sweep<false>): the
+// trailing updates run on the FP64 tensor pipe (DMMA) straight out of shared memory.  N is padded
+// to a multiple of 16 with an identity block; the residual row sits at row n_cols.  Fits N <= 144.
+// ------------------------------------------------------------------------------------------------
+#define MRV_SMALL_BLK_N_MAX 144
+__host__ __device__ inline int sblk_cols(int N) { return (N + 15) & ~15; }
+__host__ __device__ inline int sblk_ld(int N) {
+  int ld = (sblk_cols(N) + 1 + 7) & ~7;
+  if ((ld & 15) != 8) ld += 8;
+  return ld;
+}
+__host__ inline size_t small_blk_smem_bytes(int N) {
+  const int nc = sblk_cols(N), ld = sblk_ld(N);
+  return ((size_t)ld * nc + PB_NB * (size_t)(ld + 12) + PB_NB * (size_t)(nc + 4) + PB_NB * PB_D_LD + PB_NB + 2 * (size_t)N +
+          MRV_MAX_MODPAR + MRV_MAX_HP + 40) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(MRV_SMALL_THREADS)
+fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double* __restrict__ y,
+                       const double* __restrict__ yerr, const double* __restrict__ flags,
+                       const double* __restrict__ hp_all, const double* __restrict__ modpar_all,
+                       const double* __restrict__ model_given, int to_ecc, double* __restrict__ logl_out,
+                       int* __restrict__ status_out) {
+  extern __shared__ double smem[];
+  const int N = D.N, nc = sblk_cols(N), ld = sblk_ld(N), pa_ld = ld + 12, pb_ld = nc + 4;
+  double* S = smem;                          // ld x nc column major; row nc = residual row
+  double* PA = S + (size_t)ld * nc;
+  double* PBm = PA + PB_NB * pa_ld;
+  double* Dblk = PBm + PB_NB * pb_ld;
+  double* wv = Dblk + PB_NB * PB_D_LD;
+  double* ts = wv + PB_NB;                   // N
+  double* r = ts + N;                        // N
+  double* phys = r + N;                      // MRV_MAX_MODPAR
+  double* hpv = phys + MRV_MAX_MODPAR;       // MRV_MAX_HP
+  double* red = hpv + MRV_MAX_HP;            // 32
+  int* ired = (int*)(red + 32);              // 32 ints
+  const int w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+
+  if (tid == 0) {
+    for (int i = 0; i < D.nh; ++i) hpv[i] = hp_all[(size_t)w * D.nh + i];
+    for (int i = 0; i < D.nm; ++i) phys[i] = modpar_all[(size_t)w * D.nm + i];
+    if (model_given == nullptr) convert_to_ecc(D, phys, to_ecc);
+  }
+  for (int i = tid; i < N; i += nt) ts[i] = t[i];
+  __syncthreads();
+
+  if (model_given != nullptr) {
+    for (int i = tid; i < N; i += nt) r[i] = model_given[(size_t)w * N + i];
+    __syncthreads();
+  } else {
+    cta_mean_model(D, ts, flags, phys, r, /*E scratch=*/S, red);
+  }
+  int bad = 0;
+  for (int i = tid; i < N; i += nt) {
+    const double v = __dsub_rn(y[i], r[i]);
+    r[i] = v;
+    bad |= !isfinite(v);
+  }
+  __syncthreads();
+
+  // K (lower triangle), identity padding, residual row, zero elsewhere
+  const CovParams cp = make_cov_params(D.kernel_id, D.variant, hpv);
+  for (int c = warp; c < nc; c += nwarps) {
+    double* col = S + (size_t)c * ld;
+    const double tc = c < N ? ts[c] : 0.0;
+    for (int i = lane; i < ld; i += 32) {
+      double v = 0.0;
+      if (i < N && c < N) {
+        if (i == c) v = cov_diag(cp, yerr[i]);
+        else if (i > c) v = cov_eval(cp, ts[i], tc);
+      } else if (i == c) {
+        v = 1.0;
+      } else if (i == nc && c < N) {
+        v = r[c];
+      }
+      bad |= !isfinite(v);
+      col[i] = v;
+    }
+  }
+  __syncthreads();
+  cta_block_sweep<false>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
+
+  double ld_part = 0.0, q_part = 0.0;
+  int first_bad = 0x7fffffff;
+  for (int j = tid; j < N; j += nt) {
+    const double d = S[(size_t)j * ld + j];
+    const double zr = S[(size_t)j * ld + nc];
+    if (!(d > 0.0)) first_bad = min(first_bad, j + 1);
+    ld_part += log(d);
+    q_part += (zr * zr) / d;
+  }
+  const double logdet = block_sum(ld_part, red);
+  const double quad = block_sum(q_part, red);
+  const int fb = -block_max_int(-first_bad, ired);
+  const int anybad = block_max_int(bad, ired);
   if (tid == 0) {
     double v = -((double)N / 2.0) * log(2.0 * MRV_PI) - 0.5 * logdet - 0.5 * quad;
     v = add_priors(D, hpv, phys, v);
