@@ -97,6 +97,20 @@ int mrv_logl_batch_device(mrv_problem* p, const double* d_hp, const double* d_mo
 int mrv_logl_given_model(mrv_problem* p, const double* hp, const double* modpar,
                          const double* model_y, int64_t W, double* logL_out, int32_t* status_out);
 
+/* Forward half of cho_solve for W (hyper-parameter set, right-hand side) pairs: z_b = L_b^-1 rhs_b
+ * with K_b = L_b L_b^T built from hp_b and the problem's t / yerr, plus ln det K_b.  The building
+ * block of GPLikelihood.predict (gp_likelihood.py:406-481: mean = Ks K^-1 y = (L^-1 Ks^T)^T (L^-1 y),
+ * cov = Kss - (L^-1 Ks^T)^T (L^-1 Ks^T)); the reference factorises K twice there (:434, :439).
+ * hp [W, nh], rhs [W, N]; z_out [W, N], logdet_out [W] (may be NULL), status_out [W]. */
+int mrv_solve_batch(mrv_problem* p, const double* hp, const double* rhs, int64_t W, double* z_out,
+                    double* logdet_out, int32_t* status_out);
+
+/* Prediction reductions on the device: V [Np, N] (rows L^-1 Ks_p^T), z [N] (= L^-1 y), Kss [Np, Np]:
+ * mean_out[p] = V_p . z;  cov_out = Kss - V V^T ([Np, Np]) when full_cov, else the Np variances
+ * Kss_pp - |V_p|^2 (gp_likelihood.py:435-441, 476-481). */
+int mrv_predict_reduce(int device, const double* V, const double* z, const double* Kss, int64_t Np,
+                       int64_t N, int full_cov, double* mean_out, double* cov_out);
+
 /* Mean-model curves for W parameter vectors over an arbitrary time vector (no handle): get_model
  * (mcmc_aux.py:52-97) and the Model.model() methods (models.py:266, 370, 467-479, 674-697).
  * flags may be NULL when no OFFSET op is present.  model_out [W, N]; modpar_phys_out (may be NULL)

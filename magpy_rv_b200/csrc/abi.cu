@@ -15,6 +15,7 @@
 #include "blocked.cuh"
 #include "common.cuh"
 #include "dense_ops.cuh"
+#include "gemm_persist.cuh"
 #include "mean_model.cuh"
 #include "small_logl.cuh"
 
@@ -131,7 +132,8 @@ struct mrv_problem {
   int path_opt = MRV_PATH_AUTO;
   int64_t wave_opt = 0;
   int panel_opt = 0;
-  int gemm_impl = 0;  // 0 = bulk-copy (TMA) + mbarrier pipeline, 1 = cp.async pipeline
+  int gemm_impl = 0;  // 0 = one tile per CTA, bulk-copy/mbarrier ring (default); 1 = persistent variant; 2 = cp.async
+  int num_sms = 148;
   int potrf_impl = 0;  // 0 = blocked rank-16 sweep with DMMA trailing updates, 1 = rank-1 sweep
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging
@@ -278,6 +280,8 @@ static int set_attrs(mrv_problem* p) {
   CU(cudaFuncSetAttribute(potrf_tile_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_BLK_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TMA_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TMA_SMEM_BYTES));
+  CU(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
   p->attrs_set = true;
   return 0;
 }
@@ -289,7 +293,7 @@ static int choose_path(const mrv_problem* p) {
 }
 
 // Blocked path for one wave of `B` walkers starting at walker w0.
-static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st) {
+static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so) {
   const ProblemDesc& D = p->desc;
   const int nt = p->nt, N = D.N;
   const size_t walker_stride = tile_index(nt - 1, nt - 1) * TILE_ELEMS + TILE_ELEMS;
@@ -300,6 +304,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   double* quad = p->quad.as<double>() + w0;
   int* fstatus = p->fstatus.as<int>() + w0;
   const double* hp_wave = d_hp + (size_t)w0 * D.nh;
+  double* zout = so.z ? so.z + (size_t)w0 * so.ldz : nullptr;
   const int PW = std::max(1, p->panel_opt > 0 ? p->panel_opt : 8);
 
   GemmArgs g;
@@ -324,10 +329,16 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
     return (unsigned)n;
   };
 
-  const bool use_tma = p->gemm_impl == 0;
   auto launch_gemm = [&](dim3 grid) {
-    if (use_tma) gemm_tile_kernel<true><<<grid, GEMM_TMA_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g);
-    else gemm_tile_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+    if (p->gemm_impl == 1) {
+      const long long total = (long long)grid.x * grid.y;
+      const unsigned ctas = (unsigned)std::min<long long>(total, p->num_sms);
+      gemm_persist_kernel<<<ctas, GEMM_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g, (int)grid.x, (int)total);
+    } else if (p->gemm_impl == 0) {
+      gemm_tile_kernel<true><<<grid, GEMM_TMA_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g);
+    } else {
+      gemm_tile_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
+    }
   };
   const double T3 = (double)TILE * TILE * TILE;
   // algorithmic / executed FLOPs of an UPDATE launch over target columns [c0, c1) with np operand columns
@@ -366,10 +377,10 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
       p->prof.begin(CAT_POTRF, st, (T3 / 3.0 + 2.0 * TILE * TILE) * (double)B, 1.5 * T3 * (double)B);
       if (p->potrf_impl == 0)
         potrf_tile_blk_kernel<<<(unsigned)B, 256, POTRF_BLK_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad,
-                                                                              zbuf, logdet, quad, fstatus);
+                                                                              zbuf, logdet, quad, fstatus, zout, so.ldz);
       else
         potrf_tile_kernel<<<(unsigned)B, 256, POTRF_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad, zbuf,
-                                                                      logdet, quad, fstatus);
+                                                                      logdet, quad, fstatus, zout, so.ldz);
       p->prof.end(st);
       p->launches++;
       if (k + 1 < nt) {
@@ -403,7 +414,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
 
 // Core: everything on device, asynchronous on `st`.
 static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, const double* d_model_given, int64_t W,
-                    int to_ecc, double* d_logl, int* d_status, cudaStream_t st) {
+                    int to_ecc, double* d_logl, int* d_status, cudaStream_t st, SolveOut so = SolveOut{nullptr, 0, nullptr, 0}) {
   if (W <= 0) return 0;
   if (W > 65535 * 64) return fail(-1, "W=%lld too large", (long long)W);
   CU(cudaSetDevice(p->device));
@@ -420,11 +431,11 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
     if (blk)
       fused_small_blk_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp,
                                                                            d_modpar, d_model_given, to_ecc, d_logl,
-                                                                           d_status);
+                                                                           d_status, so);
     else
       fused_small_logl_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags,
                                                                             d_hp, d_modpar, d_model_given, to_ecc,
-                                                                            d_logl, d_status);
+                                                                            d_logl, d_status, so);
     p->prof.end(st);
     p->launches++;
     CU(cudaGetLastError());
@@ -464,20 +475,21 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   CU(cudaMemsetAsync(p->quad.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->fstatus.p, 0, (size_t)W * sizeof(int), st));
   p->prof.begin(CAT_MEAN, st, 0.0, 0.0);
-  mean_residual_kernel<<<(unsigned)W, 256, 0, st>>>(D, p->d_t, p->d_y, p->d_flags, d_modpar, d_model_given, to_ecc,
+  mean_residual_kernel<<<(unsigned)W, 256, 0, st>>>(D, p->d_t, so.given_is_resid ? nullptr : p->d_y, p->d_flags, d_modpar,
+                                                    d_model_given, to_ecc,
                                                     p->resid.as<double>(), p->n_pad, p->escratch.as<double>(),
                                                     p->phys.as<double>(), p->nonfinite.as<int>());
   p->prof.end(st);
   p->launches++;
   CU(cudaGetLastError());
   for (int64_t w0 = 0; w0 < W; w0 += B) {
-    if ((rc = run_wave(p, d_hp, w0, std::min<int64_t>(B, W - w0), st))) return rc;
+    if ((rc = run_wave(p, d_hp, w0, std::min<int64_t>(B, W - w0), st, so))) return rc;
   }
   p->prof.begin(CAT_FINAL, st, 0.0, 0.0);
   finalize_logl_kernel<<<(unsigned)((W + 127) / 128), 128, 0, st>>>(D, (int)W, d_hp, p->phys.as<double>(),
                                                                     p->logdet.as<double>(), p->quad.as<double>(),
                                                                     p->nonfinite.as<int>(), p->fstatus.as<int>(), d_logl,
-                                                                    d_status);
+                                                                    d_status, so.logdet);
   p->prof.end(st);
   p->launches++;
   CU(cudaGetLastError());
@@ -528,6 +540,112 @@ extern "C" int mrv_logl_given_model(mrv_problem* p, const double* hp, const doub
                                     int64_t W, double* logL_out, int32_t* status_out) {
   if (!model_y) return fail(-1, "null model_y");
   return host_logl(p, hp, modpar, model_y, W, 0, logL_out, status_out);
+}
+
+// z_b = L_b^-1 rhs_b and ln det K_b for W (hyper-parameter, right-hand side) pairs: the forward half
+// of cho_solve, exposed for GPLikelihood.predict (gp_likelihood.py:434-440).
+extern "C" int mrv_solve_batch(mrv_problem* p, const double* hp, const double* rhs, int64_t W, double* z_out,
+                               double* logdet_out, int32_t* status_out) {
+  if (!p || !hp || !rhs || !z_out || !status_out) return fail(-1, "null argument");
+  if (W <= 0) return 0;
+  CU(cudaSetDevice(p->device));
+  const ProblemDesc& D = p->desc;
+  int rc = 0;
+  DevBuf zbuf, ldbuf, mpbuf;
+  auto done = [&](int code) {
+    zbuf.release();
+    ldbuf.release();
+    mpbuf.release();
+    return code;
+  };
+  if ((rc = p->hp.ensure((size_t)W * D.nh * sizeof(double)))) return rc;
+  if ((rc = p->model.ensure((size_t)W * D.N * sizeof(double)))) return rc;
+  if ((rc = p->logl.ensure((size_t)W * sizeof(double)))) return rc;
+  if ((rc = p->status.ensure((size_t)W * sizeof(int)))) return rc;
+  if ((rc = zbuf.ensure((size_t)W * D.N * sizeof(double)))) return done(rc);
+  if ((rc = ldbuf.ensure((size_t)W * sizeof(double)))) return done(rc);
+  if ((rc = mpbuf.ensure(std::max<size_t>(1, (size_t)W * D.nm) * sizeof(double)))) return done(rc);
+  cudaStream_t st = p->stream;
+  cudaError_t e = cudaMemcpyAsync(p->hp.p, hp, (size_t)W * D.nh * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->model.p, rhs, (size_t)W * D.N * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(mpbuf.p, 0, mpbuf.bytes, st);
+  if (e != cudaSuccess) return done(fail(-2, "mrv_solve_batch copy-in: %s", cudaGetErrorString(e)));
+  // priors are part of LogL, not of the solve: evaluate with an empty prior list
+  const int n_priors_saved = p->desc.n_priors;
+  p->desc.n_priors = 0;
+  SolveOut so{zbuf.as<double>(), (long long)D.N, ldbuf.as<double>(), 1};
+  rc = run_logl(p, p->hp.as<double>(), mpbuf.as<double>(), p->model.as<double>(), W, 0, p->logl.as<double>(),
+                p->status.as<int>(), st, so);
+  p->desc.n_priors = n_priors_saved;
+  if (rc) return done(rc);
+  e = cudaMemcpyAsync(z_out, zbuf.p, (size_t)W * D.N * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && logdet_out)
+    e = cudaMemcpyAsync(logdet_out, ldbuf.p, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(status_out, p->status.p, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return done(fail(-2, "mrv_solve_batch copy-out: %s", cudaGetErrorString(e)));
+  return done(0);
+}
+
+// mean_p = V_p . z ;  cov_pq = Kss_pq - V_p . V_q  (full) or  var_p = Kss_pp - |V_p|^2.
+// One warp per output entry, fixed-order reduction.
+__global__ void predict_reduce_kernel(const double* __restrict__ V, const double* __restrict__ z,
+                                      const double* __restrict__ Kss, long long Np, long long N, int full,
+                                      double* __restrict__ mean_out, double* __restrict__ cov_out) {
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long n_cov = full ? Np * Np : Np;
+  if (warp_global < Np) {  // means
+    const double* vp = V + warp_global * N;
+    double s = 0.0;
+    for (long long i = lane; i < N; i += 32) s = fma(vp[i], z[i], s);
+    s = warp_sum(s);
+    if (lane == 0) mean_out[warp_global] = s;
+  } else if (warp_global < Np + n_cov) {
+    const long long e = warp_global - Np;
+    const long long pi = full ? e / Np : e, qi = full ? e % Np : e;
+    const double *vp = V + pi * N, *vq = V + qi * N;
+    double s = 0.0;
+    for (long long i = lane; i < N; i += 32) s = fma(vp[i], vq[i], s);
+    s = warp_sum(s);
+    if (lane == 0) cov_out[e] = Kss[pi * Np + qi] - s;
+  }
+}
+
+extern "C" int mrv_predict_reduce(int device, const double* V, const double* z, const double* Kss, int64_t Np, int64_t N,
+                                  int full_cov, double* mean_out, double* cov_out) {
+  if (!V || !z || !Kss || !mean_out || !cov_out) return fail(-1, "null argument");
+  if (int rc = require_device(device)) return rc;
+  if (Np <= 0 || N <= 0) return 0;
+  double *d_V = nullptr, *d_z = nullptr, *d_K = nullptr, *d_m = nullptr, *d_c = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_V);
+    cudaFree(d_z);
+    cudaFree(d_K);
+    cudaFree(d_m);
+    cudaFree(d_c);
+  };
+  int rc = 0;
+  const size_t n_cov = full_cov ? (size_t)Np * Np : (size_t)Np;
+  if ((rc = upload(&d_V, V, (size_t)Np * N)) || (rc = upload(&d_z, z, N)) || (rc = upload(&d_K, Kss, (size_t)Np * Np))) {
+    cleanup();
+    return rc;
+  }
+  cudaError_t e = cudaMalloc((void**)&d_m, Np * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_c, n_cov * sizeof(double));
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(-3, "cudaMalloc failed: %s", cudaGetErrorString(e));
+  }
+  const long long warps = Np + (long long)n_cov;
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  predict_reduce_kernel<<<blocks, 256>>>(d_V, d_z, d_K, Np, N, full_cov, d_m, d_c);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(mean_out, d_m, Np * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(cov_out, d_c, n_cov * sizeof(double), cudaMemcpyDeviceToHost);
+  cleanup();
+  if (e != cudaSuccess) return fail(-2, "mrv_predict_reduce: %s", cudaGetErrorString(e));
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -685,7 +803,7 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
   } else if (!strcmp(key, "panel_tiles")) {
     p->panel_opt = (int)value;
   } else if (!strcmp(key, "gemm_impl")) {
-    if (value < 0 || value > 1) return fail(-1, "gemm_impl must be 0 (bulk copy + mbarrier) or 1 (cp.async)");
+    if (value < 0 || value > 2) return fail(-1, "gemm_impl must be 0 (bulk copy per tile), 1 (persistent) or 2 (cp.async)");
     p->gemm_impl = (int)value;
   } else if (!strcmp(key, "potrf_impl")) {
     if (value < 0 || value > 1) return fail(-1, "potrf_impl must be 0 (blocked DMMA sweep) or 1 (rank-1 sweep)");

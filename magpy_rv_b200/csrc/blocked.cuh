@@ -116,7 +116,8 @@ gen_column_kernel(int N, int nt, int col, int kernel_id, int variant, int nh, co
 __global__ void __launch_bounds__(256)
 potrf_tile_kernel(int k, int N, double* __restrict__ Abase, size_t walker_stride, double* __restrict__ resid,
                   int ldr, double* __restrict__ zbuf, double* __restrict__ acc_logdet,
-                  double* __restrict__ acc_quad, int* __restrict__ status) {
+                  double* __restrict__ acc_quad, int* __restrict__ status, double* __restrict__ zout,
+                  long long ldz) {
   extern __shared__ double smem[];
   double* S = smem;
   double* red = smem + (size_t)POTRF_LD * TILE;
@@ -168,6 +169,7 @@ potrf_tile_kernel(int k, int N, double* __restrict__ Abase, size_t walker_stride
     const double z = S[TILE + tid * POTRF_LD] * isd;
     q_part = z * z;
     zbuf[(size_t)b * TILE + tid] = z;
+    if (zout != nullptr && k * TILE + tid < N) zout[(size_t)b * ldz + (size_t)k * TILE + tid] = z;
   }
   const double logdet = block_sum(ld_part, red);
   const double quad = block_sum(q_part, red);
@@ -359,7 +361,8 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
 __global__ void __launch_bounds__(256)
 potrf_tile_blk_kernel(int k, int N, double* __restrict__ Abase, size_t walker_stride, double* __restrict__ resid,
                       int ldr, double* __restrict__ zbuf, double* __restrict__ acc_logdet,
-                      double* __restrict__ acc_quad, int* __restrict__ status) {
+                      double* __restrict__ acc_quad, int* __restrict__ status, double* __restrict__ zout,
+                  long long ldz) {
   extern __shared__ double smem[];
   double* S = smem;
   double* PA = S + (size_t)PB_LD * TILE;
@@ -410,6 +413,7 @@ potrf_tile_blk_kernel(int k, int N, double* __restrict__ Abase, size_t walker_st
     const double z = S[TILE + (size_t)tid * PB_LD] * isd;
     q_part = z * z;
     zbuf[(size_t)b * TILE + tid] = z;
+    if (zout != nullptr && k * TILE + tid < N) zout[(size_t)b * ldz + (size_t)k * TILE + tid] = z;
   }
   const double logdet = block_sum(ld_part, red);
   const double quad = block_sum(q_part, red);
@@ -795,7 +799,7 @@ __global__ void finalize_logl_kernel(ProblemDesc D, int W, const double* __restr
                                      const double* __restrict__ phys, const double* __restrict__ acc_logdet,
                                      const double* __restrict__ acc_quad, const int* __restrict__ nonfinite,
                                      const int* __restrict__ fact_status, double* __restrict__ logl_out,
-                                     int* __restrict__ status_out) {
+                                     int* __restrict__ status_out, double* __restrict__ logdet_out) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   double v = -((double)D.N / 2.0) * log(2.0 * MRV_PI) - 0.5 * acc_logdet[w] - 0.5 * acc_quad[w];
@@ -804,4 +808,5 @@ __global__ void finalize_logl_kernel(ProblemDesc D, int W, const double* __restr
   if (nonfinite[w]) st = -1;
   logl_out[w] = v;
   status_out[w] = st;
+  if (logdet_out != nullptr) logdet_out[w] = acc_logdet[w];
 }

@@ -21,6 +21,14 @@ struct PriorSpec {
   double p0, p1, p2;
 };
 
+// Optional extra outputs / input mode of a batched evaluation (mrv_solve_batch).
+struct SolveOut {
+  double* z;           // [W, ldz]  L^-1 r per walker (nullable)
+  long long ldz;
+  double* logdet;      // [W] ln det K (nullable)
+  int given_is_resid;  // the caller-supplied [W, N] array is the right-hand side itself, not a model curve
+};
+
 // Everything a kernel needs to know about the problem besides the per-walker parameters.
 struct ProblemDesc {
   int N;             // data points

@@ -140,6 +140,8 @@ __global__ void mean_residual_kernel(ProblemDesc D, const double* __restrict__ t
       r[i] = v;
       bad |= !isfinite(v);
     }
+  } else {
+    for (int i = tid; i < N; i += nt) bad |= !isfinite(r[i]);
   }
   for (int i = N + tid; i < ldr; i += nt) r[i] = 0.0;
   if (nonfinite != nullptr) {

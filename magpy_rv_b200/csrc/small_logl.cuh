@@ -29,7 +29,7 @@ fused_small_logl_kernel(ProblemDesc D, const double* __restrict__ t, const doubl
                         const double* __restrict__ yerr, const double* __restrict__ flags,
                         const double* __restrict__ hp_all, const double* __restrict__ modpar_all,
                         const double* __restrict__ model_given, int to_ecc, double* __restrict__ logl_out,
-                        int* __restrict__ status_out) {
+                        int* __restrict__ status_out, SolveOut so) {
   extern __shared__ double smem[];
   const int N = D.N, ld = small_ld(N);
   double* S = smem;                         // ld x N, column major; row N = residual row
@@ -59,7 +59,7 @@ fused_small_logl_kernel(ProblemDesc D, const double* __restrict__ t, const doubl
   }
   int bad = 0;
   for (int i = tid; i < N; i += nt) {
-    const double v = __dsub_rn(y[i], r[i]);
+    const double v = so.given_is_resid ? r[i] : __dsub_rn(y[i], r[i]);
     r[i] = v;
     bad |= !isfinite(v);
   }
@@ -105,6 +105,9 @@ fused_small_logl_kernel(ProblemDesc D, const double* __restrict__ t, const doubl
   const double quad = block_sum(q_part, red);
   const int fb = -block_max_int(-first_bad, ired);
   const int anybad = block_max_int(bad, ired);
+  if (so.z != nullptr)
+    for (int j = tid; j < N; j += nt) so.z[(size_t)w * so.ldz + j] = S[(size_t)j * ld + N] / sqrt(S[(size_t)j * ld + j]);
+  if (so.logdet != nullptr && tid == 0) so.logdet[w] = logdet;
 
   // 5. closed form + priors
   if (tid == 0) {
@@ -142,7 +145,7 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
                        const double* __restrict__ yerr, const double* __restrict__ flags,
                        const double* __restrict__ hp_all, const double* __restrict__ modpar_all,
                        const double* __restrict__ model_given, int to_ecc, double* __restrict__ logl_out,
-                       int* __restrict__ status_out) {
+                       int* __restrict__ status_out, SolveOut so) {
   extern __shared__ double smem[];
   const int N = D.N, nc = sblk_cols(N), ld = sblk_ld(N), pa_ld = ld + 12, pb_ld = nc + 4;
   double* S = smem;                          // ld x nc column major; row nc = residual row
@@ -175,29 +178,46 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   }
   int bad = 0;
   for (int i = tid; i < N; i += nt) {
-    const double v = __dsub_rn(y[i], r[i]);
+    const double v = so.given_is_resid ? r[i] : __dsub_rn(y[i], r[i]);
     r[i] = v;
     bad |= !isfinite(v);
   }
   __syncthreads();
 
-  // K (lower triangle), identity padding, residual row, zero elsewhere
-  const CovParams cp = make_cov_params(D.kernel_id, D.variant, hpv);
+  // (a) everything that is not a real lower-triangle entry: zeros, identity padding, residual row
   for (int c = warp; c < nc; c += nwarps) {
     double* col = S + (size_t)c * ld;
-    const double tc = c < N ? ts[c] : 0.0;
     for (int i = lane; i < ld; i += 32) {
+      if (i < N && c < N && i >= c) continue;   // written by (b)
       double v = 0.0;
-      if (i < N && c < N) {
-        if (i == c) v = cov_diag(cp, yerr[i]);
-        else if (i > c) v = cov_eval(cp, ts[i], tc);
-      } else if (i == c) {
-        v = 1.0;
-      } else if (i == nc && c < N) {
-        v = r[c];
-      }
-      bad |= !isfinite(v);
+      if (i == c) v = 1.0;                      // identity padding (c >= N)
+      else if (i == nc && c < N) v = r[c];      // residual row
       col[i] = v;
+    }
+  }
+  // (b) the N(N+1)/2 covariance evaluations, perfectly balanced: a warp takes the column pair
+  //     (c, N-1-c), whose lower-triangle lengths add up to N+1, and every lane evaluates two
+  //     independent entries per trip (ILP across the fp64 exp/sin dependency chains).
+  const CovParams cp = make_cov_params(D.kernel_id, D.variant, hpv);
+  const int npairs = (N + 1) / 2;
+  for (int pc = warp; pc < npairs; pc += nwarps) {
+    const int cA = pc, cB = N - 1 - pc;
+    const int lenA = N - cA;
+    const int total = (cA == cB) ? lenA : (N + 1);
+    for (int v0 = lane; v0 < total; v0 += 64) {
+      const int v1 = v0 + 32;
+      const bool ok1 = v1 < total;
+      const int c0 = (v0 < lenA) ? cA : cB, i0 = (v0 < lenA) ? cA + v0 : cB + (v0 - lenA);
+      const int c1 = (!ok1 || v1 < lenA) ? cA : cB;
+      const int i1 = !ok1 ? cA : ((v1 < lenA) ? cA + v1 : cB + (v1 - lenA));
+      const double e0 = (i0 == c0) ? cov_diag(cp, yerr[i0]) : cov_eval(cp, ts[i0], ts[c0]);
+      const double e1 = (i1 == c1) ? cov_diag(cp, yerr[i1]) : cov_eval(cp, ts[i1], ts[c1]);
+      bad |= !isfinite(e0);
+      S[(size_t)c0 * ld + i0] = e0;
+      if (ok1) {
+        bad |= !isfinite(e1);
+        S[(size_t)c1 * ld + i1] = e1;
+      }
     }
   }
   __syncthreads();
@@ -216,6 +236,9 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   const double quad = block_sum(q_part, red);
   const int fb = -block_max_int(-first_bad, ired);
   const int anybad = block_max_int(bad, ired);
+  if (so.z != nullptr)
+    for (int j = tid; j < N; j += nt) so.z[(size_t)w * so.ldz + j] = S[(size_t)j * ld + nc] / sqrt(S[(size_t)j * ld + j]);
+  if (so.logdet != nullptr && tid == 0) so.logdet[w] = logdet;
   if (tid == 0) {
     double v = -((double)N / 2.0) * log(2.0 * MRV_PI) - 0.5 * logdet - 0.5 * quad;
     v = add_priors(D, hpv, phys, v);

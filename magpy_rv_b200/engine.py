@@ -180,6 +180,24 @@ class LikelihoodProblem:
         nat.check(rc, "mrv_logl_given_model")
         return out, status
 
+    def solve(self, hp, rhs):
+        """(z [W, N] = L^-1 rhs, logdet [W], status [W]) -- see mrv_solve_batch."""
+        hp = nat.as_f64(hp)
+        if hp.ndim == 1:
+            hp = hp[None, :]
+        rhs = nat.as_f64(rhs).reshape(-1, self.N)
+        W = rhs.shape[0]
+        if hp.shape[0] == 1 and W > 1:
+            hp = np.ascontiguousarray(np.broadcast_to(hp, (W, self.nh)))
+        assert hp.shape == (W, self.nh)
+        z = np.empty((W, self.N), dtype=np.float64)
+        logdet = np.empty(W, dtype=np.float64)
+        status = np.empty(W, dtype=np.int32)
+        rc = nat.lib().mrv_solve_batch(self._handle, nat.dptr(hp), nat.dptr(rhs), W, nat.dptr(z), nat.dptr(logdet),
+                                       status.ctypes.data_as(nat.c_int32_p))
+        nat.check(rc, "mrv_solve_batch")
+        return z, logdet, status
+
     def set_option(self, key, value):
         nat.check(nat.lib().mrv_set_option(self._handle, key.encode(), int(value)), "mrv_set_option(%s)" % key)
 
@@ -250,6 +268,22 @@ def model_eval_ops(ops, nm, t, modpar, to_ecc=False, flags=None, device=None):
                                   nat.dptr(modpar), W, int(bool(to_ecc)), nat.dptr(out), nat.dptr(phys))
     nat.check(rc, "mrv_model_eval")
     return out, phys
+
+
+def predict_reduce(V, z, Kss, full_cov=False, device=None):
+    """(mean [Np], cov [Np, Np] or var [Np]) -- see mrv_predict_reduce."""
+    V = nat.as_f64(V)
+    z = nat.as_f64(z).ravel()
+    Kss = nat.as_f64(Kss)
+    Np, N = V.shape
+    assert z.shape[0] == N and Kss.shape == (Np, Np)
+    mean = np.empty(Np, dtype=np.float64)
+    cov = np.empty((Np, Np) if full_cov else (Np,), dtype=np.float64)
+    device = nat.default_device() if device is None else device
+    rc = nat.lib().mrv_predict_reduce(device, nat.dptr(V), nat.dptr(z), nat.dptr(Kss), Np, N, int(bool(full_cov)),
+                                      nat.dptr(mean), nat.dptr(cov))
+    nat.check(rc, "mrv_predict_reduce")
+    return mean, cov
 
 
 def _diag_args(diag_mode, diag_add, n2):

@@ -33,6 +33,34 @@ def _default_backend(t, rv, rv_err, kernel_name, model_name, prior_list, hparam_
     return ShardedEvaluator(t, rv, rv_err, kernel_name, model_name, prior_list, hparam_names, modpar_names, flags)
 
 
+def _randint0(n):
+    """random.randint(0, n - 1): randint -> randrange -> _randbelow(n) on the module's hidden
+    instance; calling the last step directly consumes the Python RNG stream identically."""
+    if n <= 0:
+        return random.randint(0, n - 1)     # raises exactly as the reference's call does
+    return _randbelow(n)
+
+
+_randbelow = getattr(getattr(random, "_inst", None), "_randbelow", None) or (lambda n: random.randint(0, n - 1))
+
+
+def _parameter_check_rows(rows, names, check_args=()):
+    """Row-wise ``mcmc_aux.parameter_check`` (reference mcmc_aux.py:187-231) for a [n, nm] array."""
+    ok = np.ones(rows.shape[0], dtype=bool)
+    if check_args:      # Rstar and Mstar given: the reference's orbit_check path (AttributeError, F10)
+        for i in range(rows.shape[0]):
+            ok[i] = parameter_check(rows[i], names, *check_args)
+        return ok
+    o = 0
+    for name in names:
+        if name.startswith(('kepl', 'Kepl')):
+            bad = (rows[:, o] < 0.) | (rows[:, o + 1] < 0.) | (rows[:, o + 4] < 0.)
+            bad |= (rows[:, o + 2] ** 2 + rows[:, o + 3] ** 2) > 1.
+            ok &= ~bad
+        o += numb_param_per_model(name)
+    return ok
+
+
 # test hook: tests replace this factory to check the host logic without a GPU
 _BACKEND_FACTORY = _default_backend
 
@@ -210,8 +238,11 @@ class MCMC:
         of each split one random.randint followed by np.random.rand draws (redrawn while a
         hyper-parameter is negative or parameter_check fails)."""
         W = self.numb_chains
-        inds = np.arange(W) % n_splits
+        # same RNG consumption and result as random.shuffle on the NumPy array, without the slow
+        # element-wise array swaps
+        inds = (np.arange(W) % n_splits).tolist()
         random.shuffle(inds)
+        inds = np.array(inds)
 
         self.hp = np.zeros_like(self.hp0)
         self.modpar = np.zeros_like(self.modpar0)
@@ -221,12 +252,17 @@ class MCMC:
         mod0 = self.modpar0[0]
         # the reference locates each walker again by matching the first hyper-parameter and first
         # model parameter, keeping the LAST match (mcmc.py:378-381); same rule, O(W) instead of O(W^2)
-        last_match = {}
-        for o in range(W):
-            last_match[(hp0[o, 0], mod0[o, 0])] = o
+        keys = list(zip(hp0[:, 0].tolist(), mod0[:, 0].tolist()))
+        last_match = {k: o for o, k in enumerate(keys)}
         hp_vary = np.array(self.hp_vary, dtype=bool)
         mod_vary = np.array(self.modpar_vary, dtype=bool)
         check_args = (Rstar, Mstar) if (Rstar is not None and Mstar is not None) else ()
+        a = float(a)
+
+        def stretch(u):
+            # pure Python-float arithmetic, exactly the reference's expression (np.random.rand()
+            # returns a Python float there, so `**2` is libm pow(x, 2.0), not x*x)
+            return (u * (a - 1) + 1) ** 2 / a
 
         for split in range(n_splits):
             in_s1 = inds == split
@@ -234,19 +270,58 @@ class MCMC:
             S1_mod, S2_mod = mod0[in_s1], mod0[~in_s1]
             N_chains1, N_chains2 = len(S1_hp), len(S2_hp)
             S1_hp[0]                      # an empty first set is an IndexError in the reference too
-            for chain in range(N_chains1):
-                rint = random.randint(0, N_chains2 - 1)
-                Xj, Xj_mod = S2_hp[rint], S2_mod[rint]
+            # Python `random` stream: one randint per chain, in chain order (independent of np.random)
+            rints = np.array([_randint0(N_chains2) for _ in range(N_chains1)], dtype=np.intp)
+            Xj, Xj_mod = S2_hp[rints], S2_mod[rints]
+            dX, dX_mod = S1_hp - Xj, S1_mod - Xj_mod
+
+            # np.random stream: chain i consumes the next uniform and keeps consuming while its proposal
+            # is invalid.  Evaluate speculatively in bulk (chain first+i <-> i-th number of the batch);
+            # at the first invalid chain rewind the stream to just after that chain's first draw,
+            # redraw for that chain with the scalar rule, and resume in bulk.  The sequence of numbers
+            # each chain sees is exactly the reference's.
+            z = np.empty(N_chains1)
+            new_hp = np.empty_like(S1_hp)
+            new_mod = np.empty_like(S1_mod)
+            first = 0
+            while first < N_chains1:
+                n = min(N_chains1 - first, 128)      # bounded speculation: a redraw costs <= one chunk
+                state = np.random.get_state()
+                u = np.random.rand(n).tolist()
+                zz = np.array([stretch(x) for x in u])
+                cand_hp = Xj[first:first + n] + dX[first:first + n] * zz[:, None]
+                cand_mod = Xj_mod[first:first + n] + dX_mod[first:first + n] * zz[:, None]
+                ok = ~(np.min(cand_hp, axis=1) < 0)
+                ok &= _parameter_check_rows(cand_mod, self.model_name, check_args)
+                nok = n if ok.all() else int(np.argmin(ok))
+                z[first:first + nok] = zz[:nok]
+                new_hp[first:first + nok] = cand_hp[:nok]
+                new_mod[first:first + nok] = cand_mod[:nok]
+                first += nok
+                if nok == n:
+                    continue
+                np.random.set_state(state)
+                np.random.rand(nok + 1)          # replay: the accepted chains' draws + this chain's first
                 while True:
-                    z = (np.random.rand() * (a - 1) + 1) ** 2 / a
-                    Xk_new = Xj + (S1_hp[chain] - Xj) * z
-                    Xk_new_mod = Xj_mod + (S1_mod[chain] - Xj_mod) * z
+                    zc = stretch(np.random.rand())
+                    Xk_new = Xj[first] + dX[first] * zc
+                    Xk_new_mod = Xj_mod[first] + dX_mod[first] * zc
                     if not (np.min(Xk_new) < 0) and parameter_check(Xk_new_mod, self.model_name, *check_args):
                         break
-                position = last_match[(S1_hp[chain, 0], S1_mod[chain, 0])]
-                self.hp[0, position] = np.where(hp_vary, Xk_new, S1_hp[chain])
-                self.modpar[0, position] = np.where(mod_vary, Xk_new_mod, S1_mod[chain])
-                self.logz[position] = np.log(z)
+                z[first], new_hp[first], new_mod[first] = zc, Xk_new, Xk_new_mod
+                first += 1
+
+            positions = [last_match[keys[i]] for i in np.nonzero(in_s1)[0].tolist()]
+            out_hp = np.where(hp_vary, new_hp, S1_hp)
+            out_mod = np.where(mod_vary, new_mod, S1_mod)
+            logz = np.array([np.log(v) for v in z.tolist()])
+            if len(set(positions)) == N_chains1:
+                self.hp[0, positions] = out_hp
+                self.modpar[0, positions] = out_mod
+                self.logz[positions] = logz
+            else:   # duplicated keys: later chains overwrite earlier ones, as in the reference's loop
+                for c, pos in enumerate(positions):
+                    self.hp[0, pos], self.modpar[0, pos], self.logz[pos] = out_hp[c], out_mod[c], logz[c]
 
     # -- likelihood ----------------------------------------------------------------------------------
     def compute(self):

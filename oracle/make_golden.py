@@ -11,6 +11,7 @@ Outputs (all small):
     tests/golden/logl_cases.npz      per-walker LogL / model curves for kernel x model x prior cases
     tests/golden/cov_cases.npz       compute_covmatrix outputs (square, rectangular, as-coded Matern5)
     tests/golden/chain_C*.npz        seeded run_MCMC chains (random.seed(s); np.random.seed(s))
+    tests/golden/predict_cases.npz   GPLikelihood.predict means / std / full covariances
 """
 import contextlib
 import io
@@ -229,8 +230,43 @@ def make_chains(ref, which=("C1", "C2", "C3")):
                             W=W, N=cfg["N"], seed=seed)
 
 
+def make_predict(ref):
+    """GPLikelihood.predict outputs (gp_likelihood.py:406-481) incl. the Kss diagonal quirks."""
+    rng = np.random.default_rng(1357911)
+    N = 60
+    x = np.sort(rng.uniform(0, 80, N))
+    y = 4.0 * np.sin(2 * np.pi * x / 19.0) + rng.normal(0, 0.8, N)
+    err = rng.uniform(0.4, 1.0, N)
+    model_y = 0.3 + 0.01 * x
+    out = dict(x=x, y=y, err=err, model_y=model_y)
+    grids = {"dense": np.linspace(-5, 90, 157), "samelen": np.sort(rng.uniform(0, 80, N)), "same": x.copy(),
+             "single": np.array([33.3])}
+    for key in grids:
+        out["xpred_" + key] = grids[key]
+    for kern in ("QuasiPer", "JitterQuasiPer", "Matern3/2", "ExpSquared"):
+        hp = ref.par.par_create(kern)
+        vals = [v for v, _ in KERNEL_GUESS[kern]]
+        for i, k in enumerate(hp):
+            hp[k] = ref.par.parameter(value=vals[i], error=1., vary=True)
+        mp = ref.mod.mod_create(["Polynomial"])
+        for k, v in zip(mp, (0.3, 0.01, 0.0, 0.0)):
+            mp[k] = ref.par.parameter(value=v, error=1., vary=True)
+        kk = kern.replace("/", "")
+        out[kk + "__hp"] = np.array(vals)
+        for gname, xp in grids.items():
+            like = ref.gp.GPLikelihood(x, y, err, hp, kern, model_y, mp)
+            mean, std = like.predict(xp)
+            like = ref.gp.GPLikelihood(x, y, err, hp, kern, model_y, mp)
+            mean2, cov = like.predict(xp, FullCov=True)
+            out["%s__%s__mean" % (kk, gname)] = mean
+            out["%s__%s__std" % (kk, gname)] = std
+            out["%s__%s__cov" % (kk, gname)] = cov
+        print("predict %-14s mean[0]=%.10g std[0]=%.10g" % (kern, out[kk + "__dense__mean"][0], out[kk + "__dense__std"][0]))
+    np.savez_compressed(os.path.join(GOLD, "predict_cases.npz"), **out)
+
+
 def main(argv):
-    groups = set(argv) or {"kat", "cases", "cov", "chains"}
+    groups = set(argv) or {"kat", "cases", "cov", "chains", "predict"}
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
     if "kat" in groups:
@@ -241,6 +277,8 @@ def main(argv):
         make_cov(ref)
     if "chains" in groups:
         make_chains(ref)
+    if "predict" in groups:
+        make_predict(ref)
 
 
 if __name__ == "__main__":

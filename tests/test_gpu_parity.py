@@ -282,3 +282,56 @@ def test_device_pointer_entry_and_shard_invariance():
             assert int(d_s.abs().sum()) == 0
         np.testing.assert_array_equal(out, full)
     prob.close()
+
+
+def test_predict_matches_reference():
+    """GPLikelihood.predict against the reference's outputs, including the
+    Kss diagonal rules for len(xpred) == len(x), xpred == x and a single prediction point."""
+    g = np.load(os.path.join(GOLD, "predict_cases.npz"))
+    x, y, err, model_y = g["x"], g["y"], g["err"], g["model_y"]
+    for kern in ("QuasiPer", "JitterQuasiPer", "Matern3/2", "ExpSquared"):
+        kk = kern.replace("/", "")
+        hp = par.par_create(kern)
+        for k, v in zip(hp, g[kk + "__hp"]):
+            hp[k] = par.parameter(value=float(v), error=1., vary=True)
+        mp = mod.mod_create(["Polynomial"])
+        for k, v in zip(mp, (0.3, 0.01, 0.0, 0.0)):
+            mp[k] = par.parameter(value=v, error=1., vary=True)
+        for gname in ("dense", "samelen", "same", "single"):
+            xp = g["xpred_" + gname]
+            want_mean, want_std, want_cov = g["%s__%s__mean" % (kk, gname)], g["%s__%s__std" % (kk, gname)], g["%s__%s__cov" % (kk, gname)]
+            scale = max(1.0, float(np.max(np.abs(want_cov))))
+            mean, std = gp.GPLikelihood(x, y, err, hp, kern, model_y, mp).predict(xp)
+            mean2, cov = gp.GPLikelihood(x, y, err, hp, kern, model_y, mp).predict(xp, FullCov=True)
+            np.testing.assert_allclose(mean, want_mean, rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(mean2, want_mean, rtol=1e-9, atol=1e-9)
+            np.testing.assert_allclose(cov, want_cov, rtol=1e-8, atol=1e-9 * scale)
+            safe = np.diag(want_cov) > 1e-6 * scale          # sqrt of a round-off-level variance is noise
+            np.testing.assert_allclose(std[safe], want_std[safe], rtol=1e-6)
+            assert mean.shape == want_mean.shape and std.shape == want_std.shape and cov.shape == want_cov.shape
+
+
+def test_solve_batch_blocked_and_fused_agree():
+    """mrv_solve_batch: z = L^-1 rhs and ln det K from both paths against SciPy's triangular solve
+    of the oracle's covariance."""
+    from scipy.linalg import cholesky, solve_triangular
+    rng = np.random.default_rng(11)
+    for N in (50, 200):
+        t = np.sort(rng.uniform(0, 90, N))
+        yerr = rng.uniform(0.5, 1.0, N)
+        hp = np.array([20., .5, 30., 4.])
+        rhs = rng.normal(0, 1, (3, N))
+        K = port.compute_kernel("QuasiPer", hp, t, t, t, yerr)
+        L = cholesky(K, lower=True)
+        want = solve_triangular(L, rhs.T, lower=True).T
+        for path in (1, 2):
+            prob = engine.LikelihoodProblem(t, np.zeros(N), yerr, "QuasiPer")
+            if path == 1 and N > prob.info("small_n_max"):
+                prob.close()
+                continue
+            prob.set_option("path", path)
+            z, logdet, st = prob.solve(hp, rhs)
+            assert np.all(st == 0)
+            np.testing.assert_allclose(z, want, rtol=1e-9, atol=1e-10)
+            np.testing.assert_allclose(logdet, 2 * np.sum(np.log(np.diag(L))), rtol=1e-12)
+            prob.close()

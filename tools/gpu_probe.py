@@ -14,7 +14,7 @@ if len(sys.argv) > 1:
 for N, W in sizes:
     cfg = workloads.make_config("C5", W=W, N=N)
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"])
-    for panel, impl in (((4, 0), (8, 0)) if N > 168 else ((1, 0),)):
+    for panel, impl in (((8, 0),) if N > 168 else ((1, 0),)):
         prob.set_option("panel_tiles", panel)
         prob.set_option("gemm_impl", impl)
         prob.logl(cfg["hp"], cfg["modpar"])
