@@ -60,6 +60,14 @@ def host_threads():
         n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
         return int(n)
     except Exception:
+        return usable_cores()
+
+
+def usable_cores():
+    """Cores this process may run on (cgroup / affinity aware), not the machine's core count."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
         return int(os.cpu_count() or 1)
 
 
@@ -67,7 +75,7 @@ def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU baseline is meant to use every host core."""
     try:
         from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=int(os.cpu_count() or 1))
+        threadpool_limits(limits=usable_cores())
     except Exception:
         pass
 
@@ -143,6 +151,17 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+def measured_traffic(args, prob):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture of this
+    very configuration (profiles/traffic.json); None when no capture matches."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        key = "%s_N%d_wave%d_panel%d" % (args.config, args.n, prob.info("wave_walkers"), args.panel or 8)
+        return table[key]["dram_bytes_per_launch"] if key in table else None
+    except Exception:
+        return None
 
 
 def workload_config(args):
@@ -315,7 +334,7 @@ def run_ours(args):
         roofline = {
             "bound": "tensor", "kernel": "gemm_tile_kernel (trailing SYRK/GEMM update, DMMA)" if dom != "fused" else "fused_small_logl_kernel",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": None,
+            "traffic": measured_traffic(args, prob),
             "peak_source": "FP64 DMMA issue microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); "
                            "DFMA vector pipe measured %.1f TFLOP/s" % (dfma_peak / 1e12),
             "launches": d["n"] // args.steps, "avg_launch_ms": d["ns"] / max(1, d["n"]) * 1e-6,
@@ -333,14 +352,16 @@ def run_ours(args):
             "status_ok": status_ok, "path": prob.info("path"), "wave_walkers": prob.info("wave_walkers"),
             "tflops_per_gpu": (value / n_gpus) * flops_eval / 1e12,
         }
-        if not args.no_cpu_baseline:
-            v, desc, _ = cpu_sample(args.config, args.n, args.cpu_budget_s)
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc}
-        print(json.dumps(out), flush=True)
     prob.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        # CPU baseline last: the other ranks have exited, so the host cores are free for the oracle
+        if not args.no_cpu_baseline:
+            v, desc, _ = cpu_sample(args.config, args.n, args.cpu_budget_s)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc}
+        print(json.dumps(out), flush=True)
 
 
 def main():

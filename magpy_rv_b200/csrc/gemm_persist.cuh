@@ -24,13 +24,7 @@ __device__ __forceinline__ TileWork decode_work(const GemmArgs& g, int w, int ti
     t.tj = g.k;
     t.nslices = SLICES_PER_TILE;
   } else {
-    int tj = g.col_begin;
-    while (rem >= g.nt - tj) {
-      rem -= g.nt - tj;
-      ++tj;
-    }
-    t.tj = tj;
-    t.ti = tj + rem;
+    decode_update_tile(g, rem, t.ti, t.tj);
     t.nslices = (g.p_end - g.p_begin) * SLICES_PER_TILE;
   }
   t.Aw = g.Abase + (size_t)t.b * g.walker_stride;
