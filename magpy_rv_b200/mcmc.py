@@ -228,7 +228,10 @@ class MCMC:
             sfx = "" if "P" in names else "_" + str(i)
             iP, iK = names.index("P" + sfx), names.index("K" + sfx)
             iO, iE = names.index("omega" + sfx), names.index("ecc" + sfx)
-            out[0, :, i] = aux.mass_calc([modpar[:, iP], modpar[:, iK], modpar[:, iO], modpar[:, iE]], self.Mstar)
+            # element by element on NumPy scalars, as the reference does: the array (SIMD) pow differs
+            # from the scalar libm pow in the last bit
+            for w in range(W):
+                out[0, w, i] = aux.mass_calc([modpar[w, iP], modpar[w, iK], modpar[w, iO], modpar[w, iE]], self.Mstar)
         return out
 
     # -- proposal ----------------------------------------------------------------------------------

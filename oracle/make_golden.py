@@ -230,6 +230,38 @@ def make_chains(ref, which=("C1", "C2", "C3")):
                             W=W, N=cfg["N"], seed=seed)
 
 
+def make_chain_options(ref):
+    """A chain exercising the remaining run_MCMC options: flags + Offset models + Keplerian, Mstar
+    (mass output with the argument-order quirk), n_splits=3, a=2.5, a non-varying
+    parameter."""
+    import workloads
+    cfg = workloads.make_config("C4", W=40, N=96)
+    seed = 424242
+    model_list = ["Keplerian", "Offset", "Offset"]
+    vals = {"P_0": (11.0, 0.5, True), "K_0": (2.0, 0.4, True), "ecc_0": (0.2, 0.05, True), "omega_0": (1.0, 0.2, True),
+            "t0_0": (5.0, 1.0, False), "offset_0": (2.0, 0.5, True), "offset_1": (1.5, 0.5, True)}
+    pri = [("gp_per", "Uniform", [0., 100.]), ("gp_amp", "Jeffrey", [0.01, 100.]), ("ecc_0", "Uniform", [0., 1.]),
+           ("offset_0", "Gaussian", [2., 1.]), ("K_0", "Modified_Jeffrey", [0.01, 50., 1.0])]
+    hp0 = ref.par.par_create(cfg["kernel"])
+    for k in hp0:
+        src = cfg["hparam0"][k]
+        hp0[k] = ref.par.parameter(value=src.value, error=src.error, vary=src.vary)
+    mp0 = ref.mod.mod_create(model_list)
+    for k in mp0:
+        v, e, vary = vals[k]
+        mp0[k] = ref.par.parameter(value=v, error=e, vary=vary)
+    prior_list = [ref.par.pri_create(a, b, c) for a, b, c in pri]
+    random.seed(seed)
+    np.random.seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        logL, hps, mps, done, mass = ref.mcmc.run_MCMC(15, cfg["t"], cfg["y"], cfg["yerr"], hp0, cfg["kernel"], mp0, model_list,
+                                                       prior_list, numb_chains=40, n_splits=3, a=2.5, Mstar=1.1,
+                                                       flags=cfg["flags"])
+    print("chain options: final mean logL %.6f, mass[-1,0]=%s" % (logL[-1].mean(), mass[-1, 0]))
+    np.savez_compressed(os.path.join(GOLD, "chain_options.npz"), logL=logL, hp=hps, modpar=mps, mass=mass, seed=seed,
+                        vals=json.dumps(vals), priors=json.dumps(pri), model_list=json.dumps(model_list))
+
+
 def make_predict(ref):
     """GPLikelihood.predict outputs (gp_likelihood.py:406-481) incl. the Kss diagonal quirks."""
     rng = np.random.default_rng(1357911)
@@ -266,7 +298,7 @@ def make_predict(ref):
 
 
 def main(argv):
-    groups = set(argv) or {"kat", "cases", "cov", "chains", "predict"}
+    groups = set(argv) or {"kat", "cases", "cov", "chains", "predict", "options"}
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_loader.load()
     if "kat" in groups:
@@ -279,6 +311,8 @@ def main(argv):
         make_chains(ref)
     if "predict" in groups:
         make_predict(ref)
+    if "options" in groups:
+        make_chain_options(ref)
 
 
 if __name__ == "__main__":

@@ -335,3 +335,42 @@ def test_solve_batch_blocked_and_fused_agree():
             np.testing.assert_allclose(z, want, rtol=1e-9, atol=1e-10)
             np.testing.assert_allclose(logdet, 2 * np.sum(np.log(np.diag(L))), rtol=1e-12)
             prob.close()
+
+
+def test_chain_parity_with_options_gpu():
+    """flags + Offset + Keplerian, Mstar, n_splits=3, a=2.5 through the CUDA path vs the reference chain."""
+    from test_host_logic import run_options_chain
+    g, (logL, hp, mp, done, mass) = run_options_chain()
+    assert np.array_equal(hp, g["hp"]) and np.array_equal(mp, g["modpar"]), "chain diverged from the reference"
+    np.testing.assert_array_equal(mass, g["mass"])
+    assert relerr(logL[g["logL"] != 0], g["logL"][g["logL"] != 0]) < RTOL
+    assert np.array_equal(logL == 0, g["logL"] == 0)
+
+
+def test_full_size_properties_n16384():
+    """BASELINE's largest size (N = 16384) through size-independent properties (the oracle needs
+    minutes and ~15 GiB per evaluation there):
+      * scaling y, amp and yerr by c multiplies K by c^2:  logL' = logL - N ln c   (tests log det)
+      * the quadratic form is homogeneous of degree 2 in y: logL(2y) - logL(0) = 4 (logL(y) - logL(0))
+      * status is clean and the value is finite."""
+    cfg = workloads.make_config("C5", W=2, N=16384)
+    t, y, e, hp, mp = cfg["t"], cfg["y"], cfg["yerr"], cfg["hp"][:1], cfg["modpar"][:1]
+    N = cfg["N"]
+
+    def logl(yv, ev, hpv):
+        prob = engine.LikelihoodProblem(t, yv, ev, cfg["kernel"])
+        v, st = prob.logl(hpv, mp)
+        prob.close()
+        assert st[0] == 0 and np.isfinite(v[0])
+        return float(v[0])
+
+    base = logl(y, e, hp)
+    c = 1.75
+    hp_c = hp.copy()
+    hp_c[0, 3] *= c                                   # gp_amp
+    scaled = logl(c * y, c * e, hp_c)
+    assert abs(scaled - (base - N * np.log(c))) <= 1e-10 * abs(base), (scaled, base - N * np.log(c))
+    zero = logl(np.zeros(N), e, hp)
+    twice = logl(2.0 * y, e, hp)
+    q1, q2 = base - zero, twice - zero
+    assert abs(q2 - 4.0 * q1) <= 1e-9 * abs(q2), (q1, q2)
