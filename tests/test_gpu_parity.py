@@ -374,3 +374,29 @@ def test_full_size_properties_n16384():
     twice = logl(2.0 * y, e, hp)
     q1, q2 = base - zero, twice - zero
     assert abs(q2 - 4.0 * q1) <= 1e-9 * abs(q2), (q1, q2)
+
+
+def test_status_words_on_both_paths():
+    """Non-PD covariance -> LAPACK-style status > 0 (first non-positive pivot), non-finite input ->
+    status -1, on the fused and on the blocked path; healthy walkers in the same batch unaffected."""
+    rng = np.random.default_rng(5)
+    for N in (60, 300):
+        t = np.sort(rng.uniform(0, 100, N))
+        y = rng.normal(0, 1, N)
+        e = rng.uniform(0.5, 1.0, N)
+        # as-coded Matern 5/2 is indefinite (SURVEY.md F1)
+        prob = engine.LikelihoodProblem(t, y, e, "Matern5/2")
+        _, st = prob.logl([[5.0, 12.0], [4.0, 9.0]], np.zeros((2, 1)))
+        K = port.compute_kernel("Matern5/2", [5.0, 12.0], t, t, t, e)
+        with pytest.raises(np.linalg.LinAlgError):
+            np.linalg.cholesky(K)
+        assert np.all(st > 0) and np.all(st <= N), st
+        prob.close()
+        # NaN hyper-parameter in one walker only
+        prob = engine.LikelihoodProblem(t, y, e, "QuasiPer")
+        hp = np.array([[20., .5, 30., 4.], [np.nan, .5, 30., 4.], [21., .6, 28., 3.]])
+        got, st = prob.logl(hp, np.zeros((3, 1)))
+        want = port.logL_batch(t, y, e, "QuasiPer", hp[[0, 2]], ["no"], np.zeros((2, 1)))
+        assert st[0] == 0 and st[2] == 0 and st[1] == -1, st
+        assert relerr(got[[0, 2]], want) < RTOL
+        prob.close()
