@@ -376,7 +376,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
       }
       p->prof.begin(CAT_POTRF, st, (T3 / 3.0 + 2.0 * TILE * TILE) * (double)B, 1.5 * T3 * (double)B);
       if (p->potrf_impl == 0)
-        potrf_tile_blk_kernel<<<(unsigned)B, 256, POTRF_BLK_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad,
+        potrf_tile_blk_kernel<<<(unsigned)B, POTRF_BLK_THREADS, POTRF_BLK_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad,
                                                                               zbuf, logdet, quad, fstatus, zout, so.ldz);
       else
         potrf_tile_kernel<<<(unsigned)B, 256, POTRF_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad, zbuf,
@@ -424,7 +424,9 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   p->last_path = path;
   if (path == MRV_PATH_FUSED_SMEM) {
     if (D.N > SMALL_N_MAX) return fail(-1, "fused shared-memory path needs N <= %d (N=%d)", SMALL_N_MAX, D.N);
-    const bool blk = p->potrf_impl == 0 && D.N <= MRV_SMALL_BLK_N_MAX;
+    // measured crossover (profiles/README.md): below ~80 points the rank-1 kernel's smaller footprint
+    // (several CTAs per SM) wins over the blocked DMMA sweep
+    const bool blk = p->potrf_impl == 0 && D.N >= 80 && D.N <= MRV_SMALL_BLK_N_MAX;
     const size_t smem = blk ? small_blk_smem_bytes(D.N) : small_smem_bytes(D.N);
     const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)W;
     p->prof.begin(CAT_FUSED, st, fl, fl);

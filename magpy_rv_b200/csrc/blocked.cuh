@@ -233,7 +233,7 @@ __device__ __forceinline__ void dmma_1684_neg0(double (&d)[4], double a0, double
 // pa_ld, pb_ld == 4 (mod 16).  With WITH_INV the
 // strict upper triangle receives the unscaled inverse factor (see potrf_tile_kernel above);
 // without it only factor rows and the residual row are carried (fused small-N kernel).
-template <bool WITH_INV>
+template <bool WITH_INV, int NWARPS>
 __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, double* PA, const int pa_ld, double* PB,
                                        const int pb_ld, double* D, double* wv) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -245,12 +245,16 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
     const int k0 = kb * PB_NB;
     // ---- 1. pivot block -------------------------------------------------------------------
     {
-      const int r = tid >> 4, c = tid & 15;
-      double v = S[(k0 + r) + (size_t)(k0 + c) * ld];
-      D[r * PB_D_LD + c] = v;
+      const bool in_blk = tid < PB_NB * PB_NB;           // one thread per pivot-block element
+      const int r = (tid >> 4) & 15, c = tid & 15;
+      double v = 0.0;
+      if (in_blk) {
+        v = S[(k0 + r) + (size_t)(k0 + c) * ld];
+        D[r * PB_D_LD + c] = v;
+      }
       __syncthreads();
       for (int j = 0; j < PB_NB - 1; ++j) {
-        if (c > j && (r >= c || r <= j)) {
+        if (in_blk && c > j && (r >= c || r <= j)) {
           const double w = 1.0 / D[j * PB_D_LD + j];
           const double beta = D[c * PB_D_LD + j] * w;
           if (r == j) v = -beta;
@@ -259,11 +263,13 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
         }
         __syncthreads();
       }
-      if (r == c) wv[r] = 1.0 / v;
-      S[(k0 + r) + (size_t)(k0 + c) * ld] = v;     // final block (lower: factor, upper: inverse part)
+      if (in_blk) {
+        if (r == c) wv[r] = 1.0 / v;
+        S[(k0 + r) + (size_t)(k0 + c) * ld] = v;     // final block (lower: factor, upper: inverse part)
+      }
       __syncthreads();
       // multipliers beta[j][jp] = D[j][jp] / d_jp (j > jp), in place, for the row recurrences below
-      if (c < r) D[r * PB_D_LD + c] = v * wv[c];
+      if (in_blk && c < r) D[r * PB_D_LD + c] = v * wv[c];
       __syncthreads();
     }
     // ---- 2. panel rows ----------------------------------------------------------------------
@@ -303,14 +309,15 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
     const int c_begin = k0 + PB_NB;
     const int n_m16 = (n_cols - c_begin) / 16;
     const int n_n8 = n_rows8 / 8;
-    // each warp owns row tiles tn = warp, warp + 8, warp + 16 (n_n8 <= 24); their three accumulator
+    // each warp owns row tiles tn = warp, warp + NWARPS, ... (n_n8 <= 24); their accumulator
     // chains are interleaved so consecutive DMMAs are independent
-    int rho0s[3];
-    bool live[3], pivot[3];
-    double bfr[3][4];
+    constexpr int SLOTS = (24 + NWARPS - 1) / NWARPS;     // n_n8 <= 24 row tiles
+    int rho0s[SLOTS];
+    bool live[SLOTS], pivot[SLOTS];
+    double bfr[SLOTS][4];
 #pragma unroll
-    for (int sl = 0; sl < 3; ++sl) {
-      const int tn = warp + 8 * sl;
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      const int tn = warp + NWARPS * sl;
       rho0s[sl] = tn * 8;
       live[sl] = tn < n_n8 && (WITH_INV || rho0s[sl] + 7 >= c_begin);
       pivot[sl] = rho0s[sl] >= k0 && rho0s[sl] < k0 + PB_NB;
@@ -325,10 +332,10 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
         a0[kk] = PB[(kk * 4 + tig) * pb_ld + c0 + gq];
         a1[kk] = PB[(kk * 4 + tig) * pb_ld + c0 + gq + 8];
       }
-      double acc[3][4];
-      bool need[3];
+      double acc[SLOTS][4];
+      bool need[SLOTS];
 #pragma unroll
-      for (int sl = 0; sl < 3; ++sl) {
+      for (int sl = 0; sl < SLOTS; ++sl) {
         // needed if the rows are inverse/pivot rows (rho < c_begin) or contain factor rows (rho >= c)
         need[sl] = live[sl] && (rho0s[sl] < c_begin || rho0s[sl] + 7 >= c0);
         if (need[sl] && !pivot[sl]) {
@@ -342,10 +349,10 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-        for (int sl = 0; sl < 3; ++sl)
+        for (int sl = 0; sl < SLOTS; ++sl)
           if (need[sl]) dmma_1684_neg0(acc[sl], a0[kk], a1[kk], bfr[sl][kk]);   // warp-uniform predicate
 #pragma unroll
-      for (int sl = 0; sl < 3; ++sl) {
+      for (int sl = 0; sl < SLOTS; ++sl) {
         if (need[sl]) {
           double2 u, v;
           u.x = acc[sl][0]; u.y = acc[sl][1]; v.x = acc[sl][2]; v.y = acc[sl][3];
@@ -358,7 +365,8 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
   }
 }
 
-__global__ void __launch_bounds__(256)
+#define POTRF_BLK_THREADS 512
+__global__ void __launch_bounds__(POTRF_BLK_THREADS)
 potrf_tile_blk_kernel(int k, int N, double* __restrict__ Abase, size_t walker_stride, double* __restrict__ resid,
                       int ldr, double* __restrict__ zbuf, double* __restrict__ acc_logdet,
                       double* __restrict__ acc_quad, int* __restrict__ status, double* __restrict__ zout,
@@ -378,13 +386,13 @@ potrf_tile_blk_kernel(int k, int N, double* __restrict__ Abase, size_t walker_st
 
   // 16 independent 16-byte loads in flight per thread (the tile is 128 KiB of latency-bound traffic)
 #pragma unroll 1
-  for (int base = 0; base < TILE_ELEMS / 2; base += 256 * 16) {
+  for (int base = 0; base < TILE_ELEMS / 2; base += POTRF_BLK_THREADS * 16) {
     double2 v[16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldcs(reinterpret_cast<const double2*>(tile) + base + u * 256 + tid);
+    for (int u = 0; u < 16; ++u) v[u] = __ldcs(reinterpret_cast<const double2*>(tile) + base + u * POTRF_BLK_THREADS + tid);
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      const int e = 2 * (base + u * 256 + tid);
+      const int e = 2 * (base + u * POTRF_BLK_THREADS + tid);
       const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7, k3 = e & 3;
       const int R = m8 * 8 + g, C = kg * 4 + k3;
       S[R + (size_t)C * PB_LD] = v[u].x;
@@ -397,7 +405,7 @@ potrf_tile_blk_kernel(int k, int N, double* __restrict__ Abase, size_t walker_st
     for (int r = TILE + 1; r < PB_LD; ++r) S[r + (size_t)tid * PB_LD] = 0.0;   // padding rows of the n8 tiles
   }
   __syncthreads();
-  cta_block_sweep<true>(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, D, wv);
+  cta_block_sweep<true, POTRF_BLK_THREADS / 32>(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, D, wv);
 
   double ld_part = 0.0, q_part = 0.0;
   int first_bad = 0x7fffffff, nan_seen = 0;
@@ -426,7 +434,7 @@ potrf_tile_blk_kernel(int k, int N, double* __restrict__ Abase, size_t walker_st
   }
   if (tid < TILE) isd_s[tid] = isd;
   __syncthreads();
-  for (int e2 = tid; e2 < TILE_ELEMS / 2; e2 += 256) {
+  for (int e2 = tid; e2 < TILE_ELEMS / 2; e2 += POTRF_BLK_THREADS) {
     const int e = 2 * e2;
     const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7, k3 = e & 3;
     const int R = m8 * 8 + g, C = kg * 4 + k3;

@@ -221,7 +221,7 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
     }
   }
   __syncthreads();
-  cta_block_sweep<false>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
+  cta_block_sweep<false, MRV_SMALL_THREADS / 32>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
 
   double ld_part = 0.0, q_part = 0.0;
   int first_bad = 0x7fffffff;
