@@ -135,6 +135,8 @@ struct mrv_problem {
   int gemm_impl = 0;  // 0 = one tile per CTA, bulk-copy/mbarrier ring (default); 1 = persistent variant; 2 = cp.async
   int num_sms = 148;
   int potrf_impl = 0;  // 0 = blocked rank-16 sweep with DMMA trailing updates, 1 = rank-1 sweep
+  int band_opt = 0;    // UPDATE rasterisation band (tile rows), 0 = default
+  int cs_store = 1;    // streaming stores for updated C tiles
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging
   DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor;
@@ -322,6 +324,8 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   g.resid = resid;
   g.ldr = p->n_pad;
   g.zbuf = zbuf;
+  g.band = p->band_opt;
+  g.cs_store = p->cs_store;
 
   auto tiles_in_cols = [&](int c0, int c1) {
     long long n = 0;
@@ -807,6 +811,10 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
   } else if (!strcmp(key, "gemm_impl")) {
     if (value < 0 || value > 2) return fail(-1, "gemm_impl must be 0 (bulk copy per tile), 1 (persistent) or 2 (cp.async)");
     p->gemm_impl = (int)value;
+  } else if (!strcmp(key, "update_band")) {
+    p->band_opt = (int)value;
+  } else if (!strcmp(key, "cs_store")) {
+    p->cs_store = value != 0;
   } else if (!strcmp(key, "potrf_impl")) {
     if (value < 0 || value > 1) return fail(-1, "potrf_impl must be 0 (blocked DMMA sweep) or 1 (rank-1 sweep)");
     p->potrf_impl = (int)value;

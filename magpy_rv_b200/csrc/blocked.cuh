@@ -465,6 +465,8 @@ struct GemmArgs {
   int p_begin;       // UPDATE: panel of operand tile columns [p_begin, p_end)
   int p_end;
   int gen;           // UPDATE: 1 = target tiles are generated from t (first touch) instead of loaded
+  int band;          // UPDATE rasterisation band height in tile rows (0 = default)
+  int cs_store;      // UPDATE: streaming (evict-first) stores for the C tile
   int kernel_id, variant, nh;
   double* Abase;
   size_t walker_stride;
@@ -531,11 +533,12 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;
 // each B panel row is fetched once per band and shared by the <= UPDATE_BAND co-running CTAs below
 // it.  (Plain column-major order re-fetched the whole 100 MiB panel for every target column:
 // 127 GB of DRAM reads for 30 GB of algorithmic traffic at N = 16384, ncu r1e.)
-#define UPDATE_BAND 24
+#define UPDATE_BAND 64
 __device__ __forceinline__ void decode_update_tile(const GemmArgs& g, int x, int& ti, int& tj) {
   int rem = x;
-  for (int r0 = g.col_begin; r0 < g.nt; r0 += UPDATE_BAND) {
-    const int r1 = min(r0 + UPDATE_BAND, g.nt) - 1;          // last tile row of the band
+  const int band = g.band > 0 ? g.band : UPDATE_BAND;
+  for (int r0 = g.col_begin; r0 < g.nt; r0 += band) {
+    const int r1 = min(r0 + band, g.nt) - 1;          // last tile row of the band
     const int c_last = min(g.col_end - 1, r1);                // last target column with rows in the band
     for (int c = g.col_begin; c <= c_last; ++c) {
       const int top = max(c, r0);
@@ -780,7 +783,8 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
           double2 o;
           o.x = -acc[mi][ni][2 * v1 + 0];
           o.y = -acc[mi][ni][2 * v1 + 1];
-          __stcs(reinterpret_cast<double2*>(Ct + tile_off(R, C)), o);   // not re-read before the next panel
+          if (g.cs_store) __stcs(reinterpret_cast<double2*>(Ct + tile_off(R, C)), o);   // not re-read before the next panel
+          else *reinterpret_cast<double2*>(Ct + tile_off(R, C)) = o;
         }
   } else {
     // TRSM: X = acc is L(i,k); store it and fold r_i -= X z_k
