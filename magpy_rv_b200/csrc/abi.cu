@@ -139,7 +139,7 @@ struct mrv_problem {
   int cs_store = 1;    // streaming stores for updated C tiles
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging
-  DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor;
+  DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter;
   int64_t wave_cur = 0;
   int64_t launches = 0;
   int last_path = 0;
@@ -263,7 +263,7 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
   cudaFree(p->d_yerr);
   cudaFree(p->d_flags);
   DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
-                    &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor};
+                    &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter};
   for (DevBuf* b : bufs) b->release();
   p->prof.destroy();
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -337,7 +337,8 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
     if (p->gemm_impl == 1) {
       const long long total = (long long)grid.x * grid.y;
       const unsigned ctas = (unsigned)std::min<long long>(total, p->num_sms);
-      gemm_persist_kernel<<<ctas, GEMM_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g, (int)grid.x, (int)total);
+      cudaMemsetAsync(p->counter.p, 0, sizeof(int), st);
+      gemm_persist_kernel<<<ctas, GEMM_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g, (int)grid.x, (int)total, p->counter.as<int>());
     } else if (p->gemm_impl == 0) {
       gemm_tile_kernel<true><<<grid, GEMM_TMA_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g);
     } else {
@@ -475,6 +476,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   if ((rc = p->quad.ensure((size_t)W * sizeof(double)))) return rc;
   if ((rc = p->fstatus.ensure((size_t)W * sizeof(int)))) return rc;
   if ((rc = p->zbuf.ensure((size_t)B * TILE * sizeof(double)))) return rc;
+  if ((rc = p->counter.ensure(64))) return rc;
   if ((rc = p->factor.ensure((size_t)B * walker_bytes))) return rc;
 
   CU(cudaMemsetAsync(p->logdet.p, 0, (size_t)W * sizeof(double), st));
@@ -814,7 +816,7 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
   } else if (!strcmp(key, "update_band")) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {
-    p->cs_store = value != 0;
+    p->cs_store = (int)value;   // bit 0: streaming C stores; bit 1: L2 prefetch of the next C tile (persistent GEMM)
   } else if (!strcmp(key, "potrf_impl")) {
     if (value < 0 || value > 1) return fail(-1, "potrf_impl must be 0 (blocked DMMA sweep) or 1 (rank-1 sweep)");
     p->potrf_impl = (int)value;
@@ -856,7 +858,7 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "workspace_bytes")) {
     int64_t s = 0;
     DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
-                      &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor};
+                      &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter};
     for (DevBuf* b : bufs) s += (int64_t)b->bytes;
     return s;
   }

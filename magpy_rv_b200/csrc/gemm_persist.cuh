@@ -43,7 +43,7 @@ __device__ __forceinline__ const double* work_b_src(const GemmArgs& g, const Til
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_persist_kernel(GemmArgs g, int tiles_per_walker, int total_work) {
+gemm_persist_kernel(GemmArgs g, int tiles_per_walker, int total_work, int* __restrict__ work_counter) {
   extern __shared__ double smem[];
   constexpr int NST = GEMM_TMA_STAGES;
   double* stages = smem;
@@ -62,6 +62,11 @@ gemm_persist_kernel(GemmArgs g, int tiles_per_walker, int total_work) {
   const int a_lane = ((wm * 8) << 5) + lane;
   const int b_lane = ((wn * 4) << 5) + lane;
 
+  // Dynamic tile scheduler: the first tile of a CTA is blockIdx.x, every further one comes from a
+  // global counter (static round-robin measured 5 % slower: SMs differ in L2 distance and the slowest
+  // SM set the pace).  seq[] holds the CTA's tile sequence two tiles ahead of the consumer so the
+  // producer lane can stream the next tile's operands before the current tile is finished.
+  __shared__ int seq[4];
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -69,11 +74,13 @@ gemm_persist_kernel(GemmArgs g, int tiles_per_walker, int total_work) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async;\n" ::: "memory");
+    seq[0] = blockIdx.x;
+    seq[1] = ((int)blockIdx.x < total_work) ? atomicAdd(work_counter, 1) + (int)gridDim.x : total_work;
   }
   __syncthreads();
 
   // ---- producer cursor (used by tid 0 only): next slice to issue = (p_work, p_q), global index p_cnt
-  int p_work = blockIdx.x, p_q = 0, p_cnt = 0;
+  int p_work = blockIdx.x, p_q = 0, p_cnt = 0, p_it = 0;
   TileWork p_tile;
   if (p_work < total_work) p_tile = decode_work(g, p_work, tiles_per_walker);
   auto produce_one = [&]() {
@@ -87,7 +94,8 @@ gemm_persist_kernel(GemmArgs g, int tiles_per_walker, int total_work) {
     ++p_cnt;
     if (++p_q == p_tile.nslices) {
       p_q = 0;
-      p_work += gridDim.x;
+      ++p_it;
+      p_work = seq[p_it & 3];
       if (p_work < total_work) p_tile = decode_work(g, p_work, tiles_per_walker);
     }
   };
@@ -109,12 +117,15 @@ gemm_persist_kernel(GemmArgs g, int tiles_per_walker, int total_work) {
     for (int v = 0; v < 4; ++v) bf[0][v] = Bs[v << 5];
   }
 
-  for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+  int it = 0;
+  for (int w = blockIdx.x; w < total_work; ++it) {
     const TileWork t = decode_work(g, w, tiles_per_walker);
-    const bool has_next = w + (int)gridDim.x < total_work;
     double* Ct = t.Aw + tile_index(t.ti, t.tj) * TILE_ELEMS;
 
-    consumer_sync();  // previous tile's epilogue is done with tis / tjs / zs / part
+    consumer_sync();  // previous tile's epilogue is done with tis / tjs / zs / part; seq[it+1] is visible
+    const int w_next = seq[(it + 1) & 3];
+    const bool has_next = w_next < total_work;
+    if (tid == 0) seq[(it + 2) & 3] = has_next ? atomicAdd(work_counter, 1) + (int)gridDim.x : total_work;
     if (g.mode == GEMM_UPDATE && g.gen) {
       if (tid < TILE) {
         const int gi = t.ti * TILE + tid;
@@ -125,9 +136,9 @@ gemm_persist_kernel(GemmArgs g, int tiles_per_walker, int total_work) {
       }
     }
     if (g.mode == GEMM_TRSM && tid < TILE) zs[tid] = g.zbuf[(size_t)t.b * TILE + tid];
-    if (g.mode == GEMM_UPDATE && !g.gen && has_next) {
+    if (g.mode == GEMM_UPDATE && !g.gen && has_next && (g.cs_store & 2)) {
       // pull the NEXT tile's C block into L2 while this tile computes (1024 lines of 128 B)
-      const TileWork nx = decode_work(g, w + gridDim.x, tiles_per_walker);
+      const TileWork nx = decode_work(g, w_next, tiles_per_walker);
       const char* cn = reinterpret_cast<const char*>(nx.Aw + tile_index(nx.ti, nx.tj) * TILE_ELEMS);
 #pragma unroll
       for (int u = 0; u < 4; ++u) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(cn + (size_t)(u * 256 + tid) * 128));
@@ -256,5 +267,6 @@ gemm_persist_kernel(GemmArgs g, int tiles_per_walker, int total_work) {
         ri[tid] -= s;
       }
     }
+    w = w_next;
   }
 }
