@@ -158,7 +158,7 @@ def measured_traffic(args, prob):
     very configuration (profiles/traffic.json); None when no capture matches."""
     try:
         table = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "%s_N%d_wave%d_panel%d" % (args.config, args.n, prob.info("wave_walkers"), args.panel or 8)
+        key = "%s_N%d_wave%d_panel%d" % (args.config, args.n, prob.info("wave_walkers"), prob.info("panel_tiles"))
         return table[key]["dram_bytes_per_launch"] if key in table else None
     except Exception:
         return None
@@ -350,6 +350,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(l_host.nbytes + s_host.nbytes), "matches_device_path": e2e_ok},
             "gpu_launches": int(launches), "clocks": clock_info, "roofline": roofline,
             "status_ok": status_ok, "path": prob.info("path"), "wave_walkers": prob.info("wave_walkers"),
+            "panel_tiles": prob.info("panel_tiles"),
             "tflops_per_gpu": (value / n_gpus) * flops_eval / 1e12,
         }
     prob.close()

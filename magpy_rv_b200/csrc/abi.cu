@@ -288,6 +288,14 @@ static int set_attrs(mrv_problem* p) {
   return 0;
 }
 
+// Panel width (tile columns per trailing update).  Measured optimum (tools/panel_probe.py): 8 up to
+// N = 4096, 12 at 8192, 24 at 16384 -- wider panels amortise the C-tile traffic and the per-tile
+// fill/drain of the trailing GEMM, until the in-panel updates (shorter K) start to dominate.
+static int effective_panel(const mrv_problem* p) {
+  if (p->panel_opt > 0) return p->panel_opt;
+  return std::min(24, std::max(8, (p->nt * 3) / 16));
+}
+
 static int choose_path(const mrv_problem* p) {
   if (p->path_opt == MRV_PATH_FUSED_SMEM) return MRV_PATH_FUSED_SMEM;
   if (p->path_opt == MRV_PATH_BLOCKED) return MRV_PATH_BLOCKED;
@@ -307,7 +315,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   int* fstatus = p->fstatus.as<int>() + w0;
   const double* hp_wave = d_hp + (size_t)w0 * D.nh;
   double* zout = so.z ? so.z + (size_t)w0 * so.ldz : nullptr;
-  const int PW = std::max(1, p->panel_opt > 0 ? p->panel_opt : 8);
+  const int PW = effective_panel(p);
 
   GemmArgs g;
   memset(&g, 0, sizeof g);
@@ -324,7 +332,9 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   g.resid = resid;
   g.ldr = p->n_pad;
   g.zbuf = zbuf;
-  g.band = p->band_opt;
+  // band height x panel width x 128 KiB = A rows that should stay L2-resident while the B rows stream
+  // past once per band: ~48 MiB measured best for DRAM traffic (ncu, profiles/README.md) at <= 0.5 % speed cost
+  g.band = p->band_opt > 0 ? p->band_opt : std::min(64, std::max(14, 384 / PW));
   g.cs_store = p->cs_store;
 
   auto tiles_in_cols = [&](int c0, int c1) {
@@ -836,6 +846,7 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "launches")) return p->launches;
   if (!strcmp(key, "wave_walkers")) return p->wave_cur;
   if (!strcmp(key, "n_pad")) return p->n_pad;
+  if (!strcmp(key, "panel_tiles")) return effective_panel(p);
   if (!strcmp(key, "small_n_max")) return SMALL_N_MAX;
   if (!strncmp(key, "prof_", 5)) {
     // prof_<ns|alg|exec|n>_<category>; the caller must have synchronised the stream it launched on

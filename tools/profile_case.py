@@ -9,6 +9,9 @@ name = sys.argv[4] if len(sys.argv) > 4 else "C5"
 cfg = workloads.make_config(name, W=W, N=N)
 prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["model_list"], cfg["prior_list"],
                                 flags=cfg["flags"], kernel_variant=cfg["kernel_variant"])
+for kv in os.environ.get("MRV_OPTS", "").split(","):
+    if "=" in kv:
+        prob.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 for _ in range(reps):
     l, s = prob.logl(cfg["hp"], cfg["modpar"])
 print("ok", l[:2], int((s != 0).sum()), "launches", prob.info("launches"))
