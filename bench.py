@@ -297,7 +297,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = prob.info("launches") - launches0
     prof = {}
-    for cat in ("gen", "potrf", "trsm", "update_panel", "update_trail", "mean", "final", "fused"):
+    for cat in ("gen", "potrf", "trsm", "update_panel", "update_mid", "update_trail", "mean", "final", "fused"):
         prof[cat] = {k: prob.info("prof_%s_%s" % (k, cat)) for k in ("ns", "alg", "exec", "n")}
     prob.set_option("profile", 0)
     t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)

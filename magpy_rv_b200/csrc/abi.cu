@@ -62,8 +62,8 @@ struct DevBuf {
 };
 
 // Optional per-category kernel timing with CUDA events on the launching stream (bench.py roofline).
-enum { CAT_GEN = 0, CAT_POTRF, CAT_TRSM, CAT_UPDATE_PANEL, CAT_UPDATE_TRAIL, CAT_MEAN, CAT_FINAL, CAT_FUSED, CAT_COUNT };
-static const char* const kCatNames[CAT_COUNT] = {"gen", "potrf", "trsm", "update_panel", "update_trail", "mean", "final", "fused"};
+enum { CAT_GEN = 0, CAT_POTRF, CAT_TRSM, CAT_UPDATE_PANEL, CAT_UPDATE_MID, CAT_UPDATE_TRAIL, CAT_MEAN, CAT_FINAL, CAT_FUSED, CAT_COUNT };
+static const char* const kCatNames[CAT_COUNT] = {"gen", "potrf", "trsm", "update_panel", "update_mid", "update_trail", "mean", "final", "fused"};
 struct ProfRec {
   int cat;
   cudaEvent_t e0, e1;
@@ -136,6 +136,7 @@ struct mrv_problem {
   int num_sms = 148;
   int potrf_impl = 0;  // 0 = blocked rank-16 sweep with DMMA trailing updates, 1 = rank-1 sweep
   int band_opt = 0;    // UPDATE rasterisation band (tile rows), 0 = default
+  int panel_inner_opt = 0;  // inner panel width of the two-level scheme, 0 = default (8)
   int cs_store = 1;    // streaming stores for updated C tiles
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging
@@ -372,56 +373,55 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
                                                             hp_wave, A, walker_stride);
   p->prof.end(st);
   p->launches++;
-  for (int p0 = 0; p0 < nt; p0 += PW) {
-    const int p1 = std::min(p0 + PW, nt);
-    for (int k = p0; k < p1; ++k) {
-      if (k > p0) {  // bring column k up to date with the part of this panel already factored
-        g.mode = GEMM_UPDATE;
-        g.col_begin = k;
-        g.col_end = k + 1;
-        g.p_begin = p0;
-        g.p_end = k;
-        g.gen = (p0 == 0);
-        double ex = 0.0;
-        const double al = update_flops(k, k + 1, k - p0, &ex);
-        p->prof.begin(CAT_UPDATE_PANEL, st, al, ex);
-        launch_gemm(dim3(tiles_in_cols(k, k + 1), (unsigned)B));
+  auto launch_update = [&](int cat, int c0, int c1, int pb, int pe) {
+    g.mode = GEMM_UPDATE;
+    g.col_begin = c0;
+    g.col_end = c1;
+    g.p_begin = pb;
+    g.p_end = pe;
+    g.gen = (pb == 0);   // the operand range starts at column 0 <=> this is the first touch of the targets
+    double ex = 0.0;
+    const double al = update_flops(c0, c1, pe - pb, &ex);
+    p->prof.begin(cat, st, al, ex);
+    launch_gemm(dim3(tiles_in_cols(c0, c1), (unsigned)B));
+    p->prof.end(st);
+    p->launches++;
+  };
+  // Two-level panels: outer panels of PW tile columns get one big trailing update (K = 128 PW);
+  // inside an outer panel, inner panels of PWI columns are factored column by column (short-K
+  // in-panel updates) and then applied to the rest of the outer panel in one mid-level update
+  // (K = 128 PWI), so only ~PWI/2 of every PW columns' worth of flops runs at short K.
+  // (measured, tools/panel_probe.py: the mid-level updates run at the same rate as the in-panel ones, so the
+  // second level buys nothing -- 24/8: 33.19, 24/12: 33.24, 24/24: 33.40 TFLOP/s at N = 16384; default = one level)
+  const int PWI = std::min(PW, p->panel_inner_opt > 0 ? p->panel_inner_opt : PW);
+  for (int P0 = 0; P0 < nt; P0 += PW) {
+    const int P1 = std::min(P0 + PW, nt);
+    for (int p0 = P0; p0 < P1; p0 += PWI) {
+      const int p1 = std::min(p0 + PWI, P1);
+      for (int k = p0; k < p1; ++k) {
+        if (k > p0) launch_update(CAT_UPDATE_PANEL, k, k + 1, p0, k);
+        p->prof.begin(CAT_POTRF, st, (T3 / 3.0 + 2.0 * TILE * TILE) * (double)B, 1.5 * T3 * (double)B);
+        if (p->potrf_impl == 0)
+          potrf_tile_blk_kernel<<<(unsigned)B, POTRF_BLK_THREADS, POTRF_BLK_SMEM_BYTES, st>>>(
+              k, N, A, walker_stride, resid, p->n_pad, zbuf, logdet, quad, fstatus, zout, so.ldz);
+        else
+          potrf_tile_kernel<<<(unsigned)B, 256, POTRF_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad, zbuf,
+                                                                        logdet, quad, fstatus, zout, so.ldz);
         p->prof.end(st);
         p->launches++;
+        if (k + 1 < nt) {
+          g.mode = GEMM_TRSM;
+          g.k = k;
+          p->prof.begin(CAT_TRSM, st, (T3 + 2.0 * TILE * TILE) * (nt - k - 1) * (double)B,
+                        2.0 * T3 * (nt - k - 1) * (double)B);
+          launch_gemm(dim3(nt - k - 1, (unsigned)B));
+          p->prof.end(st);
+          p->launches++;
+        }
       }
-      p->prof.begin(CAT_POTRF, st, (T3 / 3.0 + 2.0 * TILE * TILE) * (double)B, 1.5 * T3 * (double)B);
-      if (p->potrf_impl == 0)
-        potrf_tile_blk_kernel<<<(unsigned)B, POTRF_BLK_THREADS, POTRF_BLK_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad,
-                                                                              zbuf, logdet, quad, fstatus, zout, so.ldz);
-      else
-        potrf_tile_kernel<<<(unsigned)B, 256, POTRF_SMEM_BYTES, st>>>(k, N, A, walker_stride, resid, p->n_pad, zbuf,
-                                                                      logdet, quad, fstatus, zout, so.ldz);
-      p->prof.end(st);
-      p->launches++;
-      if (k + 1 < nt) {
-        g.mode = GEMM_TRSM;
-        g.k = k;
-        p->prof.begin(CAT_TRSM, st, (T3 + 2.0 * TILE * TILE) * (nt - k - 1) * (double)B,
-                      2.0 * T3 * (nt - k - 1) * (double)B);
-        launch_gemm(dim3(nt - k - 1, (unsigned)B));
-        p->prof.end(st);
-        p->launches++;
-      }
+      if (p1 < P1) launch_update(CAT_UPDATE_MID, p1, P1, p0, p1);
     }
-    if (p1 < nt) {
-      g.mode = GEMM_UPDATE;
-      g.col_begin = p1;
-      g.col_end = nt;
-      g.p_begin = p0;
-      g.p_end = p1;
-      g.gen = (p0 == 0);
-      double ex = 0.0;
-      const double al = update_flops(p1, nt, p1 - p0, &ex);
-      p->prof.begin(CAT_UPDATE_TRAIL, st, al, ex);
-      launch_gemm(dim3(tiles_in_cols(p1, nt), (unsigned)B));
-      p->prof.end(st);
-      p->launches++;
-    }
+    if (P1 < nt) launch_update(CAT_UPDATE_TRAIL, P1, nt, P0, P1);
   }
   CU(cudaGetLastError());
   return 0;
@@ -823,6 +823,8 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
   } else if (!strcmp(key, "gemm_impl")) {
     if (value < 0 || value > 2) return fail(-1, "gemm_impl must be 0 (bulk copy per tile), 1 (persistent) or 2 (cp.async)");
     p->gemm_impl = (int)value;
+  } else if (!strcmp(key, "panel_inner")) {
+    p->panel_inner_opt = (int)value;
   } else if (!strcmp(key, "update_band")) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {

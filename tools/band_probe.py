@@ -11,7 +11,7 @@ for pw, band in ((24, 64), (24, 32), (24, 24), (24, 16), (16, 32), (16, 24), (12
     prob.set_option("update_band", band)
     prob.set_option("profile", 1)
     prob.logl(cfg["hp"], cfg["modpar"])
-    cats = ("gen", "potrf", "trsm", "update_panel", "update_trail", "mean", "final")
+    cats = ("gen", "potrf", "trsm", "update_panel", "update_mid", "update_trail", "mean", "final")
     ns = {c: prob.info("prof_ns_" + c) for c in cats}
     alg = prob.info("prof_alg_update_trail")
     prob.set_option("profile", 0)

@@ -27,7 +27,7 @@ for N, W in sizes:
         fl = workloads.flops_per_eval(N) * W
         prob.set_option("profile", 1)
         prob.logl(cfg["hp"], cfg["modpar"])
-        cats = ("gen", "potrf", "trsm", "update_panel", "update_trail", "mean", "final", "fused")
+        cats = ("gen", "potrf", "trsm", "update_panel", "update_mid", "update_trail", "mean", "final", "fused")
         ns = {c: prob.info("prof_ns_" + c) for c in cats}
         nl = {c: prob.info("prof_n_" + c) for c in cats}
         prob.set_option("profile", 0)

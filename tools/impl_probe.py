@@ -13,7 +13,7 @@ for impl, cs in ((0, 1), (1, 1), (1, 3), (1, 1), (1, 3)):
     prob.set_option("cs_store", cs)
     prob.set_option("profile", 1)
     prob.logl(cfg["hp"], cfg["modpar"])
-    cats = ("gen", "potrf", "trsm", "update_panel", "update_trail", "mean", "final")
+    cats = ("gen", "potrf", "trsm", "update_panel", "update_mid", "update_trail", "mean", "final")
     ns = {c: prob.info("prof_ns_" + c) for c in cats}
     alg = {c: prob.info("prof_alg_" + c) for c in cats}
     prob.set_option("profile", 0)
