@@ -76,6 +76,27 @@ __device__ __noinline__ double gen_element(const CovParams& cp, int N, int gi, i
   return (gi == gj) ? 1.0 : 0.0;
 }
 
+// Four elements of one accumulator fragment at once: rows gi0, gi0+8; columns gj0, gj0+1 (order of
+// the DMMA accumulator registers c[0..3]).  One call site per fragment, ILP 4 inside.
+__device__ __noinline__ void gen_fragment4(const CovParams& cp, int N, int gi0, int gj0, double ti0, double ti1,
+                                           double tj0, double tj1, const double* __restrict__ yerr, double (&out)[4]) {
+  const double tis4[4] = {ti0, ti0, ti1, ti1}, tjs4[4] = {tj0, tj1, tj0, tj1};
+  double d[4], d2[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const double dt = tis4[e] - tjs4[e];
+    d[e] = fabs(dt);
+    d2[e] = dt * dt;
+  }
+  cov_from_dist_n<4>(cp, d, d2, out);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int gi = gi0 + 8 * (e >> 1), gj = gj0 + (e & 1);
+    if (gi >= N || gj >= N) out[e] = (gi == gj) ? 1.0 : 0.0;
+    else if (gi == gj) out[e] = cov_diag(cp, yerr[gi]);
+  }
+}
+
 // Write the covariance tiles of tile-column `col` for every walker of the wave (needed before
 // potrf/trsm touch a column that no UPDATE has generated yet, i.e. column 0).
 __global__ void __launch_bounds__(256)
@@ -92,10 +113,26 @@ gen_column_kernel(int N, int nt, int col, int kernel_id, int variant, int nh, co
   __syncthreads();
   const CovParams cp = make_cov_params(kernel_id, variant, hp_wave + (size_t)b * nh);
   double* tile = Abase + (size_t)b * walker_stride + tile_index(i, col) * TILE_ELEMS;
-  for (int e = tid; e < TILE_ELEMS; e += 256) {
-    const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7, k3 = e & 3;
-    const int R = m8 * 8 + g, C = kg * 4 + k3;
-    tile[e] = gen_element(cp, N, i * TILE + R, col * TILE + C, ti_s[R], tj_s[C], yerr);
+  // four consecutive elements (same row R, columns C..C+3) per trip: one switch, ILP 4, 32-byte stores
+  for (int e4 = tid; e4 < TILE_ELEMS / 4; e4 += 256) {
+    const int e = e4 * 4;
+    const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7;
+    const int R = m8 * 8 + g, C = kg * 4;
+    double d[4], d2[4], out[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const double dt = ti_s[R] - tj_s[C + u];
+      d[u] = fabs(dt);
+      d2[u] = dt * dt;
+    }
+    cov_from_dist_n<4>(cp, d, d2, out);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int gi = i * TILE + R, gj = col * TILE + C + u;
+      if (gi >= N || gj >= N) out[u] = (gi == gj) ? 1.0 : 0.0;
+      else if (gi == gj) out[u] = cov_diag(cp, yerr[gi]);
+      tile[e + u] = out[u];
+    }
   }
 }
 
@@ -674,11 +711,13 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
       for (int ni = 0; ni < 4; ++ni)
+        {
+          const int R = wm * 64 + mi * 16 + gq;
+          const int C = wn * 32 + ni * 8 + 2 * tig;
+          double frag[4];
+          gen_fragment4(cp, g.N, ti * TILE + R, tj * TILE + C, tis[R], tis[R + 8], tjs[C], tjs[C + 1], g.yerr, frag);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int R = wm * 64 + mi * 16 + gq + 8 * (v >> 1);
-          const int C = wn * 32 + ni * 8 + 2 * tig + (v & 1);
-          acc[mi][ni][v] = -gen_element(cp, g.N, ti * TILE + R, tj * TILE + C, tis[R], tjs[C], g.yerr);
+          for (int v = 0; v < 4; ++v) acc[mi][ni][v] = -frag[v];
         }
   } else {
 #pragma unroll

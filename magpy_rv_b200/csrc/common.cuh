@@ -130,6 +130,65 @@ __device__ __forceinline__ double cov_from_dist(const CovParams& p, double d, do
   return 0.0;
 }
 
+// NV independent evaluations with the kernel switch hoisted OUTSIDE the element loop, so the NV
+// fp64 exp / sin dependency chains are interleaved by the compiler (instruction-level parallelism;
+// a lone evaluation is a ~500-cycle serial chain on a pipe that could start a new op every 2).
+template <int NV>
+__device__ __forceinline__ void cov_from_dist_n(const CovParams& p, const double (&d)[NV], const double (&d2)[NV],
+                                                double (&out)[NV]) {
+  switch (p.kind) {
+    case 0:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) out[e] = p.a2 * cos(p.c1 * d[e]);
+      break;
+    case 1:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) out[e] = p.a2 * exp(p.c1 * (d[e] * d[e]));
+      break;
+    case 2: {
+      double s[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) s[e] = sin(p.c2 * d[e]);
+#pragma unroll
+      for (int e = 0; e < NV; ++e) out[e] = p.a2 * exp(p.c1 * (s[e] * s[e]));
+      break;
+    }
+    case 3:
+    case 4: {
+      double s[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) s[e] = sin(p.c2 * d[e]);
+#pragma unroll
+      for (int e = 0; e < NV; ++e) out[e] = p.a2 * exp(p.c1 * d2[e] + p.c3 * (s[e] * s[e]));
+      break;
+    }
+    case 5:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const double x = p.c1 * d[e];
+        out[e] = p.a2 * (1.0 + x + ((5.0 * (d2[e] * d2[e])) / 3.0 * p.c2) * exp(-x));
+      }
+      break;
+    case 7:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const double x = p.c1 * d[e];
+        out[e] = p.a2 * (1.0 + x + p.c2 * d2[e]) * exp(-x);
+      }
+      break;
+    case 6:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const double x = p.c1 * d[e];
+        out[e] = p.a2 * (1.0 + x) * exp(-x);
+      }
+      break;
+    default:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) out[e] = 0.0;
+  }
+}
+
 __device__ __forceinline__ double cov_eval(const CovParams& p, double ti, double tj) {
   double dt = ti - tj;
   return cov_from_dist(p, fabs(dt), dt * dt);

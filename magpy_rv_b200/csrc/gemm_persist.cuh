@@ -165,11 +165,13 @@ gemm_persist_kernel(GemmArgs g, int tiles_per_walker, int total_work, int* __res
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int ni = 0; ni < 4; ++ni)
+          {
+            const int R = wm * 64 + mi * 16 + gq;
+            const int C = wn * 32 + ni * 8 + 2 * tig;
+            double frag[4];
+            gen_fragment4(cp, g.N, t.ti * TILE + R, t.tj * TILE + C, tis[R], tis[R + 8], tjs[C], tjs[C + 1], g.yerr, frag);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int R = wm * 64 + mi * 16 + gq + 8 * (v >> 1);
-            const int C = wn * 32 + ni * 8 + 2 * tig + (v & 1);
-            acc[mi][ni][v] = -gen_element(cp, g.N, t.ti * TILE + R, t.tj * TILE + C, tis[R], tjs[C], g.yerr);
+            for (int v = 0; v < 4; ++v) acc[mi][ni][v] = -frag[v];
           }
     } else {
 #pragma unroll

@@ -210,8 +210,13 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
       const int c0 = (v0 < lenA) ? cA : cB, i0 = (v0 < lenA) ? cA + v0 : cB + (v0 - lenA);
       const int c1 = (!ok1 || v1 < lenA) ? cA : cB;
       const int i1 = !ok1 ? cA : ((v1 < lenA) ? cA + v1 : cB + (v1 - lenA));
-      const double e0 = (i0 == c0) ? cov_diag(cp, yerr[i0]) : cov_eval(cp, ts[i0], ts[c0]);
-      const double e1 = (i1 == c1) ? cov_diag(cp, yerr[i1]) : cov_eval(cp, ts[i1], ts[c1]);
+      // both evaluations through one switch so their exp / sin chains interleave (ILP 2)
+      const double dt0 = ts[i0] - ts[c0], dt1 = ts[i1] - ts[c1];
+      const double dd[2] = {fabs(dt0), fabs(dt1)}, dd2[2] = {dt0 * dt0, dt1 * dt1};
+      double ev[2];
+      cov_from_dist_n<2>(cp, dd, dd2, ev);
+      const double e0 = (i0 == c0) ? cov_diag(cp, yerr[i0]) : ev[0];
+      const double e1 = (i1 == c1) ? cov_diag(cp, yerr[i1]) : ev[1];
       bad |= !isfinite(e0);
       S[(size_t)c0 * ld + i0] = e0;
       if (ok1) {
