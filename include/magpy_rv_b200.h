@@ -139,8 +139,20 @@ int mrv_covmatrix_from_dist(int device, int kernel_id, int kernel_variant, const
 int mrv_distances(int device, const double* t1, int64_t n1, const double* t2, int64_t n2,
                   double* dist_e_out, double* dist_se_out);
 
+/* Host-only helper (no GPU work): the sequential scan of one stretch-move split, MCMC.split_step
+ * (mcmc.py:322-376).  Chains chain_begin..n_chains-1 consume the uniforms u[0..n_u) in order,
+ * z = (u (a-1) + 1)^2 / a, proposal = Xj + dX z, redrawing while a hyper-parameter is negative or
+ * mcmc_aux.parameter_check (mcmc_aux.py:187-231) fails for a Keplerian starting at one of
+ * kepler_offsets.  Xj_* / dX_* / new_* are [n_chains, nh|nm] row-major, z_out [n_chains].  Returns
+ * the number of uniforms consumed by COMPLETED chains; *chains_done = first chain not completed
+ * (== n_chains when all are done; otherwise call again with more uniforms). */
+int64_t mrv_stretch_scan(const double* u, int64_t n_u, int64_t chain_begin, int64_t n_chains, int32_t nh,
+                         int32_t nm, const double* Xj_hp, const double* dX_hp, const double* Xj_mod,
+                         const double* dX_mod, double a, const int32_t* kepler_offsets, int32_t n_kepler,
+                         int64_t* chains_done, double* z_out, double* new_hp, double* new_mod);
+
 /* Introspection / tuning (no reference counterpart). */
-enum { MRV_PATH_AUTO = 0, MRV_PATH_FUSED_SMEM = 1, MRV_PATH_BLOCKED = 2 };
+enum { MRV_PATH_AUTO = 0, MRV_PATH_FUSED_SMEM = 1, MRV_PATH_BLOCKED = 2, MRV_PATH_MID = 3 };
 int mrv_set_option(mrv_problem* p, const char* key, int64_t value); /* "path", "wave_walkers", "panel_tiles" */
 int64_t mrv_get_info(mrv_problem* p, const char* key); /* "path", "launches", "wave_walkers", "n_pad", "workspace_bytes" */
 int mrv_device_count(void);

@@ -9,7 +9,7 @@ OUT_DIR = os.path.join(HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "libmagpy_rv_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
 
 
 def _nvcc():
@@ -18,7 +18,7 @@ def _nvcc():
 
 def sources():
     d = os.path.join(HERE, "csrc")
-    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith((".cu", ".cuh")))
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith((".cu", ".cuh", ".h")))
 
 
 def needs_build():

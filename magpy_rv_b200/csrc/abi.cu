@@ -18,6 +18,8 @@
 #include "gemm_persist.cuh"
 #include "mean_model.cuh"
 #include "small_logl.cuh"
+#include "mid_logl.cuh"
+#include "host_sampler.h"
 
 static thread_local std::string g_err;
 
@@ -140,7 +142,7 @@ struct mrv_problem {
   int cs_store = 1;    // streaming stores for updated C tiles
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging
-  DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter;
+  DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter, midws;
   int64_t wave_cur = 0;
   int64_t launches = 0;
   int last_path = 0;
@@ -264,7 +266,7 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
   cudaFree(p->d_yerr);
   cudaFree(p->d_flags);
   DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
-                    &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter};
+                    &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter, &p->midws};
   for (DevBuf* b : bufs) b->release();
   p->prof.destroy();
   if (p->stream) cudaStreamDestroy(p->stream);
@@ -279,6 +281,8 @@ static int set_attrs(mrv_problem* p) {
   if (p->attrs_set) return 0;
   CU(cudaFuncSetAttribute(fused_small_logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(fused_small_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(mid_logl_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(mid_logl_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_BYTES));
   CU(cudaFuncSetAttribute(potrf_tile_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_BLK_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
@@ -300,7 +304,11 @@ static int effective_panel(const mrv_problem* p) {
 static int choose_path(const mrv_problem* p) {
   if (p->path_opt == MRV_PATH_FUSED_SMEM) return MRV_PATH_FUSED_SMEM;
   if (p->path_opt == MRV_PATH_BLOCKED) return MRV_PATH_BLOCKED;
-  return p->desc.N <= SMALL_N_MAX ? MRV_PATH_FUSED_SMEM : MRV_PATH_BLOCKED;
+  if (p->path_opt == MRV_PATH_MID) return MRV_PATH_MID;
+  // measured crossovers (profiles/README.md): fused shared-memory kernels up to 144 points, the
+  // one-CTA-per-walker streamed-panel kernel up to 512, the tiled wave factorisation above
+  if (p->desc.N <= MRV_SMALL_BLK_N_MAX) return MRV_PATH_FUSED_SMEM;
+  return p->desc.N <= MID_N_MAX ? MRV_PATH_MID : MRV_PATH_BLOCKED;
 }
 
 // Blocked path for one wave of `B` walkers starting at walker w0.
@@ -453,6 +461,28 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
       fused_small_logl_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags,
                                                                             d_hp, d_modpar, d_model_given, to_ecc,
                                                                             d_logl, d_status, so);
+    p->prof.end(st);
+    p->launches++;
+    CU(cudaGetLastError());
+    return 0;
+  }
+
+  if (path == MRV_PATH_MID) {
+    if (D.N > MID_N_MAX) return fail(-1, "streamed-panel path needs N <= %d (N=%d)", MID_N_MAX, D.N);
+    const int nw = mid_warps(D.N);
+    const size_t smem = mid_smem_bytes(D.N);
+    const int per_sm = (nw == 8 && 2 * (smem + 1024) <= (size_t)227 * 1024) ? 2 : 1;
+    const unsigned grid = (unsigned)std::min<int64_t>(W, (int64_t)p->num_sms * per_sm);
+    const size_t ws_stride = mid_ws_doubles(D.N);
+    if (int rc = p->midws.ensure(std::max<size_t>(1, (size_t)grid * ws_stride) * sizeof(double))) return rc;
+    const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)W;
+    p->prof.begin(CAT_FUSED, st, fl, fl);
+    if (nw == 8)
+      mid_logl_kernel<8><<<grid, 256, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar, d_model_given,
+                                                  to_ecc, (int)W, d_logl, d_status, so, p->midws.as<double>(), ws_stride);
+    else
+      mid_logl_kernel<16><<<grid, 512, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar, d_model_given,
+                                                   to_ecc, (int)W, d_logl, d_status, so, p->midws.as<double>(), ws_stride);
     p->prof.end(st);
     p->launches++;
     CU(cudaGetLastError());
@@ -814,7 +844,7 @@ extern "C" int mrv_distances(int device, const double* t1, int64_t n1, const dou
 extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
   if (!p || !key) return fail(-1, "null argument");
   if (!strcmp(key, "path")) {
-    if (value < 0 || value > 2) return fail(-1, "path must be 0 (auto), 1 (fused smem) or 2 (blocked)");
+    if (value < 0 || value > 3) return fail(-1, "path must be 0 (auto), 1 (fused smem), 2 (blocked) or 3 (streamed panel)");
     p->path_opt = (int)value;
   } else if (!strcmp(key, "wave_walkers")) {
     p->wave_opt = value;
@@ -850,6 +880,7 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "n_pad")) return p->n_pad;
   if (!strcmp(key, "panel_tiles")) return effective_panel(p);
   if (!strcmp(key, "small_n_max")) return SMALL_N_MAX;
+  if (!strcmp(key, "mid_n_max")) return MID_N_MAX;
   if (!strncmp(key, "prof_", 5)) {
     // prof_<ns|alg|exec|n>_<category>; the caller must have synchronised the stream it launched on
     cudaSetDevice(p->device);
@@ -871,7 +902,7 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "workspace_bytes")) {
     int64_t s = 0;
     DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
-                      &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter};
+                      &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter, &p->midws};
     for (DevBuf* b : bufs) s += (int64_t)b->bytes;
     return s;
   }

@@ -279,40 +279,18 @@ class MCMC:
             dX, dX_mod = S1_hp - Xj, S1_mod - Xj_mod
 
             # np.random stream: chain i consumes the next uniform and keeps consuming while its proposal
-            # is invalid.  Evaluate speculatively in bulk (chain first+i <-> i-th number of the batch);
-            # at the first invalid chain rewind the stream to just after that chain's first draw,
-            # redraw for that chain with the scalar rule, and resume in bulk.  The sequence of numbers
-            # each chain sees is exactly the reference's.
+            # is invalid, so the numbers a chain sees depend on every chain before it.  The sequential
+            # scan runs in the native host helper mrv_stretch_scan (csrc/host_sampler.h) over a buffer
+            # of pre-drawn uniforms; surplus draws are handed back by rewinding the stream, so the
+            # sequence of numbers each chain sees -- and the stream position afterwards -- is exactly
+            # the reference's.
             z = np.empty(N_chains1)
             new_hp = np.empty_like(S1_hp)
             new_mod = np.empty_like(S1_mod)
-            first = 0
-            while first < N_chains1:
-                n = min(N_chains1 - first, 128)      # bounded speculation: a redraw costs <= one chunk
-                state = np.random.get_state()
-                u = np.random.rand(n).tolist()
-                zz = np.array([stretch(x) for x in u])
-                cand_hp = Xj[first:first + n] + dX[first:first + n] * zz[:, None]
-                cand_mod = Xj_mod[first:first + n] + dX_mod[first:first + n] * zz[:, None]
-                ok = ~(np.min(cand_hp, axis=1) < 0)
-                ok &= _parameter_check_rows(cand_mod, self.model_name, check_args)
-                nok = n if ok.all() else int(np.argmin(ok))
-                z[first:first + nok] = zz[:nok]
-                new_hp[first:first + nok] = cand_hp[:nok]
-                new_mod[first:first + nok] = cand_mod[:nok]
-                first += nok
-                if nok == n:
-                    continue
-                np.random.set_state(state)
-                np.random.rand(nok + 1)          # replay: the accepted chains' draws + this chain's first
-                while True:
-                    zc = stretch(np.random.rand())
-                    Xk_new = Xj[first] + dX[first] * zc
-                    Xk_new_mod = Xj_mod[first] + dX_mod[first] * zc
-                    if not (np.min(Xk_new) < 0) and parameter_check(Xk_new_mod, self.model_name, *check_args):
-                        break
-                z[first], new_hp[first], new_mod[first] = zc, Xk_new, Xk_new_mod
-                first += 1
+            if check_args:
+                self._scan_python(N_chains1, Xj, dX, Xj_mod, dX_mod, stretch, check_args, z, new_hp, new_mod)
+            else:
+                self._scan_native(N_chains1, Xj, dX, Xj_mod, dX_mod, a, z, new_hp, new_mod)
 
             positions = [last_match[keys[i]] for i in np.nonzero(in_s1)[0].tolist()]
             out_hp = np.where(hp_vary, new_hp, S1_hp)
@@ -325,6 +303,71 @@ class MCMC:
             else:   # duplicated keys: later chains overwrite earlier ones, as in the reference's loop
                 for c, pos in enumerate(positions):
                     self.hp[0, pos], self.modpar[0, pos], self.logz[pos] = out_hp[c], out_mod[c], logz[c]
+
+    def _kepler_offsets(self):
+        offs, o = [], 0
+        for name in self.model_name:
+            if name.startswith(('kepl', 'Kepl')):
+                offs.append(o)
+            o += numb_param_per_model(name)
+        return np.array(offs, dtype=np.int32)
+
+    def _scan_native(self, n_chains, Xj, dX, Xj_mod, dX_mod, a, z, new_hp, new_mod):
+        """Validity-redraw scan of one split through the C ABI host helper (no GPU involved)."""
+        import ctypes
+        from . import _native as nat
+        lib = nat.lib()
+        Xj, dX = np.ascontiguousarray(Xj), np.ascontiguousarray(dX)
+        Xj_mod, dX_mod = np.ascontiguousarray(Xj_mod), np.ascontiguousarray(dX_mod)
+        kep = self._kepler_offsets()
+        kep_p = kep.ctypes.data_as(nat.c_int32_p) if kep.size else None
+        done = ctypes.c_int64(0)
+        state0 = np.random.get_state()
+        buf = np.empty(0)
+        consumed = drawn = 0
+        while done.value < n_chains:
+            fresh = (n_chains - done.value) + (16 if drawn else 0)
+            buf = np.concatenate([buf, np.random.rand(fresh)]) if buf.size else np.random.rand(fresh)
+            drawn += fresh
+            used = lib.mrv_stretch_scan(nat.dptr(buf), buf.size, done.value, n_chains, Xj.shape[1], Xj_mod.shape[1],
+                                        nat.dptr(Xj), nat.dptr(dX), nat.dptr(Xj_mod), nat.dptr(dX_mod), float(a), kep_p,
+                                        int(kep.size), ctypes.byref(done), nat.dptr(z), nat.dptr(new_hp), nat.dptr(new_mod))
+            consumed += used
+            buf = buf[used:]
+        if consumed != drawn:               # hand the surplus back: rewind and replay what was consumed
+            np.random.set_state(state0)
+            np.random.rand(consumed)
+
+    def _scan_python(self, n_chains, Xj, dX, Xj_mod, dX_mod, stretch, check_args, z, new_hp, new_mod):
+        """Same scan in NumPy/Python (used when Rstar and Mstar are given: the reference's orbit_check
+        path raises from inside parameter_check)."""
+        first = 0
+        while first < n_chains:
+            n = min(n_chains - first, 128)      # bounded speculation: a redraw costs <= one chunk
+            state = np.random.get_state()
+            u = np.random.rand(n).tolist()
+            zz = np.array([stretch(x) for x in u])
+            cand_hp = Xj[first:first + n] + dX[first:first + n] * zz[:, None]
+            cand_mod = Xj_mod[first:first + n] + dX_mod[first:first + n] * zz[:, None]
+            ok = ~(np.min(cand_hp, axis=1) < 0)
+            ok &= _parameter_check_rows(cand_mod, self.model_name, check_args)
+            nok = n if ok.all() else int(np.argmin(ok))
+            z[first:first + nok] = zz[:nok]
+            new_hp[first:first + nok] = cand_hp[:nok]
+            new_mod[first:first + nok] = cand_mod[:nok]
+            first += nok
+            if nok == n:
+                continue
+            np.random.set_state(state)
+            np.random.rand(nok + 1)          # replay: the accepted chains' draws + this chain's first
+            while True:
+                zc = stretch(np.random.rand())
+                Xk_new = Xj[first] + dX[first] * zc
+                Xk_new_mod = Xj_mod[first] + dX_mod[first] * zc
+                if not (np.min(Xk_new) < 0) and parameter_check(Xk_new_mod, self.model_name, *check_args):
+                    break
+            z[first], new_hp[first], new_mod[first] = zc, Xk_new, Xk_new_mod
+            first += 1
 
     # -- likelihood ----------------------------------------------------------------------------------
     def compute(self):

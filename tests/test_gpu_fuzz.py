@@ -65,11 +65,12 @@ def test_random_configuration_matches_oracle(N):
     got, st = prob.logl(c["hp"], c["modpar"])
     paths = [prob.info("path")]
     results = [got]
-    if N <= prob.info("small_n_max"):
-        prob.set_option("path", 2)
-        got2, st2 = prob.logl(c["hp"], c["modpar"])
-        results.append(got2)
-        assert np.all(st2 == 0)
+    for path, n_max in ((1, prob.info("small_n_max")), (2, 1 << 30), (3, prob.info("mid_n_max"))):
+        if N <= n_max and path != paths[0]:
+            prob.set_option("path", path)
+            got2, st2 = prob.logl(c["hp"], c["modpar"])
+            results.append(got2)
+            assert np.all(st2 == 0), (path, st2)
     prob.close()
     assert np.all(st == 0), (st, c["kernel"], c["model_list"])
     for g in results:

@@ -63,11 +63,13 @@ def test_logl_matches_reference_goldens(case):
     err = relerr(got, case["logL"])
     print("%s: N=%d path=%d max rel err %.2e" % (case["name"], case["N"], prob.info("path"), err))
     assert err < RTOL
-    # the same walkers through the other path (fused smem <-> blocked DMMA) where both apply
-    if case["N"] <= prob.info("small_n_max"):
-        prob.set_option("path", 2)
-        got2, status2 = prob.logl(case["hp"], case["modpar"], to_ecc=True)
-        assert np.all(status2 == 0) and relerr(got2, case["logL"]) < RTOL
+    # the same walkers through every other path that applies (fused smem / blocked DMMA / streamed panel)
+    for path, n_max in ((1, prob.info("small_n_max")), (2, 1 << 30), (3, prob.info("mid_n_max"))):
+        if case["N"] <= n_max and path != prob.info("path"):
+            prob.set_option("path", path)
+            got2, status2 = prob.logl(case["hp"], case["modpar"], to_ecc=True)
+            assert prob.info("path") == path
+            assert np.all(status2 == 0) and relerr(got2, case["logL"]) < RTOL, (path, relerr(got2, case["logL"]))
     prob.close()
 
 
@@ -184,6 +186,7 @@ def test_blocked_path_invariances_and_large_n():
     at N = 4096 one walker is checked against the oracle, the rest through self-consistency."""
     cfg = workloads.make_config("C5", W=6, N=700)
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"])
+    prob.set_option("path", 2)
     base, st = prob.logl(cfg["hp"], cfg["modpar"])
     assert np.all(st == 0)
     for wave in (1, 4):
@@ -213,18 +216,38 @@ def test_blocked_path_invariances_and_large_n():
     prob.close()
 
 
+def test_streamed_panel_path_persistent_slots():
+    """More walkers than resident CTAs on the one-CTA-per-walker path (N = 200: two 8-warp CTAs per SM;
+    N = 330: one 16-warp CTA per SM): every slot's workspace and barrier ring is reused across walkers;
+    results must be bitwise independent of the walker -> slot assignment and match the oracle."""
+    for N, W in ((200, 700), (330, 400)):
+        cfg = workloads.make_config("C2", W=W, N=N)
+        prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["model_list"], cfg["prior_list"])
+        prob.set_option("path", 3)
+        got, st = prob.logl(cfg["hp"], cfg["modpar"])
+        assert np.all(st == 0) and prob.info("path") == 3
+        perm = np.random.default_rng(N).permutation(W)
+        got_p, _ = prob.logl(cfg["hp"][perm], cfg["modpar"][perm])
+        np.testing.assert_array_equal(got_p, got[perm])
+        pick = perm[:6]
+        want = port.logL_batch(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["hp"][pick], cfg["model_list"],
+                               cfg["modpar"][pick], cfg["prior_list"])
+        assert relerr(got[pick], want) < RTOL
+        prob.close()
+
+
 def test_edge_sizes():
     rng = np.random.default_rng(3)
-    for N in (1, 2, 3, 127, 128, 129, 255, 257):
+    for N in (1, 2, 3, 31, 32, 33, 127, 128, 129, 255, 256, 257, 479, 480, 481, 511, 512):
         t = np.sort(rng.uniform(0, 50, N))
         y = rng.normal(0, 2, N)
         e = rng.uniform(0.5, 1.0, N)
         hp = np.array([[20., .5, 30., 4.], [18., .6, 25., 3.]])
         mp = np.zeros((2, 1))
         want = port.logL_batch(t, y, e, "QuasiPer", hp, ["no"], mp)
-        for path in (1, 2):
+        for path in (1, 2, 3):
             prob = engine.LikelihoodProblem(t, y, e, "QuasiPer")
-            if path == 1 and N > prob.info("small_n_max"):
+            if (path == 1 and N > prob.info("small_n_max")) or (path == 3 and N > prob.info("mid_n_max")):
                 prob.close()
                 continue
             prob.set_option("path", path)
@@ -324,7 +347,7 @@ def test_solve_batch_blocked_and_fused_agree():
         K = port.compute_kernel("QuasiPer", hp, t, t, t, yerr)
         L = cholesky(K, lower=True)
         want = solve_triangular(L, rhs.T, lower=True).T
-        for path in (1, 2):
+        for path in (1, 2, 3):
             prob = engine.LikelihoodProblem(t, np.zeros(N), yerr, "QuasiPer")
             if path == 1 and N > prob.info("small_n_max"):
                 prob.close()
@@ -378,14 +401,16 @@ def test_full_size_properties_n16384():
 
 def test_status_words_on_both_paths():
     """Non-PD covariance -> LAPACK-style status > 0 (first non-positive pivot), non-finite input ->
-    status -1, on the fused and on the blocked path; healthy walkers in the same batch unaffected."""
+    status -1, on the fused, the streamed-panel and the blocked path; healthy walkers in the same batch
+    unaffected."""
     rng = np.random.default_rng(5)
-    for N in (60, 300):
+    for N, path in ((60, 0), (300, 0), (300, 2), (60, 3), (700, 0)):
         t = np.sort(rng.uniform(0, 100, N))
         y = rng.normal(0, 1, N)
         e = rng.uniform(0.5, 1.0, N)
         # as-coded Matern 5/2 is indefinite (SURVEY.md F1)
         prob = engine.LikelihoodProblem(t, y, e, "Matern5/2")
+        prob.set_option("path", path)
         _, st = prob.logl([[5.0, 12.0], [4.0, 9.0]], np.zeros((2, 1)))
         K = port.compute_kernel("Matern5/2", [5.0, 12.0], t, t, t, e)
         with pytest.raises(np.linalg.LinAlgError):
@@ -394,6 +419,7 @@ def test_status_words_on_both_paths():
         prob.close()
         # NaN hyper-parameter in one walker only
         prob = engine.LikelihoodProblem(t, y, e, "QuasiPer")
+        prob.set_option("path", path)
         hp = np.array([[20., .5, 30., 4.], [np.nan, .5, 30., 4.], [21., .6, 28., 3.]])
         got, st = prob.logl(hp, np.zeros((3, 1)))
         want = port.logL_batch(t, y, e, "QuasiPer", hp[[0, 2]], ["no"], np.zeros((2, 1)))
