@@ -34,7 +34,8 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    extra = os.environ.get("MRV_NVCC_EXTRA", "").split()      # e.g. -DMID_TIMING for the phase timers
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))

@@ -281,8 +281,8 @@ static int set_attrs(mrv_problem* p) {
   if (p->attrs_set) return 0;
   CU(cudaFuncSetAttribute(fused_small_logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(fused_small_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(mid_logl_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(mid_logl_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(mid_logl_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(mid_logl_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_BYTES));
   CU(cudaFuncSetAttribute(potrf_tile_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_BLK_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
@@ -471,17 +471,17 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
     if (D.N > MID_N_MAX) return fail(-1, "streamed-panel path needs N <= %d (N=%d)", MID_N_MAX, D.N);
     const int nw = mid_warps(D.N);
     const size_t smem = mid_smem_bytes(D.N);
-    const int per_sm = (nw == 8 && 2 * (smem + 1024) <= (size_t)227 * 1024) ? 2 : 1;
+    const int per_sm = (nw == 7 && 2 * (smem + 1024) <= (size_t)227 * 1024) ? 2 : 1;
     const unsigned grid = (unsigned)std::min<int64_t>(W, (int64_t)p->num_sms * per_sm);
     const size_t ws_stride = mid_ws_doubles(D.N);
     if (int rc = p->midws.ensure(std::max<size_t>(1, (size_t)grid * ws_stride) * sizeof(double))) return rc;
     const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)W;
     p->prof.begin(CAT_FUSED, st, fl, fl);
-    if (nw == 8)
-      mid_logl_kernel<8><<<grid, 256, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar, d_model_given,
+    if (nw == 7)
+      mid_logl_kernel<7><<<grid, 256, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar, d_model_given,
                                                   to_ecc, (int)W, d_logl, d_status, so, p->midws.as<double>(), ws_stride);
     else
-      mid_logl_kernel<16><<<grid, 512, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar, d_model_given,
+      mid_logl_kernel<15><<<grid, 512, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar, d_model_given,
                                                    to_ecc, (int)W, d_logl, d_status, so, p->midws.as<double>(), ws_stride);
     p->prof.end(st);
     p->launches++;
@@ -881,6 +881,19 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "panel_tiles")) return effective_panel(p);
   if (!strcmp(key, "small_n_max")) return SMALL_N_MAX;
   if (!strcmp(key, "mid_n_max")) return MID_N_MAX;
+  if (!strncmp(key, "mid_t", 5)) {   // phase timers of the streamed-panel kernel (only with -DMID_TIMING); reading resets
+    long long v[32];
+    cudaSetDevice(p->device);
+    if (cudaMemcpyFromSymbol(v, g_mid_timing, sizeof v) != cudaSuccess) return -1;
+    const int i = atoi(key + 5);
+    if (i < 0 || i > 32) return -1;
+    if (i == 32) {
+      memset(v, 0, sizeof v);
+      cudaMemcpyToSymbol(g_mid_timing, v, sizeof v);
+      return 0;
+    }
+    return v[i];
+  }
   if (!strncmp(key, "prof_", 5)) {
     // prof_<ns|alg|exec|n>_<category>; the caller must have synchronised the stream it launched on
     cudaSetDevice(p->device);

@@ -1,25 +1,29 @@
 // Mid-N log-likelihood (144 < N <= 512, tutorial-2 / 51-Peg sizes): ONE CTA PER WALKER, one launch.
 //
-// The dense covariance K is never written anywhere.  A walker's CTA runs a left-looking blocked
-// Cholesky over block columns of 32 (panel j = rows [32 j, R) x 32 columns, R = N padded to 32):
-//   1. every thread GENERATES its share of the panel of K from t / yerr straight into its DMMA
-//      accumulator registers (as -K, like the large-N GEMM: the epilogue is a negate).  Half of the
-//      fragments are generated one step early, while a single warp factors the previous diagonal
-//      block, the other half while the first operand slices are in flight -- the two latency-bound
-//      sections hide behind the FP64-ALU-bound one;
+// The dense covariance K is never written anywhere.  A walker's CTA (NWM tensor warps + one factor
+// warp) runs a left-looking blocked Cholesky over block columns of 32 (panel j = rows [32 j, R) x 32
+// columns, R = N padded to 32):
+//   1. the tensor warps GENERATE their share of the panel of K from t / yerr straight into their
+//      DMMA accumulator registers (as -K, like the large-N GEMM: the epilogue is a negate).  The two
+//      column halves of panel j + 1 are generated while the factor warp works on the two 16 x 16
+//      diagonal blocks of panel j, so the latency-bound single-warp sections hide behind the
+//      FP64-ALU-bound one;
 //   2. acc += L(rows, 0:32 j) * L(block-j rows, 0:32 j)^T on the FP64 tensor pipe: the already
 //      factored block columns stream back from a per-CTA workspace that stays L2-resident
 //      (<= 1.1 MB per CTA slot), k8 slices of ALL panel rows as two 1-D bulk copies (TMA engine)
-//      into a 6-stage mbarrier ring -- no CTA-wide barrier in the loop.  The B operand (the 32 rows
-//      of block j) is simply the first 32 rows of the same slice, so nothing is loaded twice; one
-//      warp per slice also folds the residual update r_j -= L(block-j rows, k) z_k into its pass
-//      over the slice (fixed warp / order => bitwise reproducible);
-//   3. the panel goes to shared memory in operand order; ONE warp factors the 32 x 32 diagonal block
-//      in registers (row per lane, column broadcast through shared memory), inverts the factor
-//      (column per lane) and forms z_j = L_jj^-1 r_j;
-//   4. X = P inv(L_jj)^T for the rows below the block runs on the tensor pipe again and goes from the
-//      accumulator registers straight to the workspace in operand order [k4 chunk][row][4 columns],
-//      i.e. exactly the DMMA fragment layout step 2 reads back.
+//      into an mbarrier ring -- no CTA-wide barrier in the loop.  The factor warp is the producer: it
+//      runs as far ahead as the ring allows, so consumers wait for data only, never for each other
+//      (with a consumer-side producer the loop spent half its time in empty-barrier waits).  The B operand (the 32 rows of
+//      block j) is simply the first 32 rows of the same slice, so nothing is loaded twice; one warp
+//      per slice also folds the residual update r_j -= L(block-j rows, k) z_k into its pass over the
+//      slice (fixed warp / order => bitwise reproducible);
+//   3. the panel goes to shared memory in operand order and is finished in two 16-column halves:
+//      the factor warp factors the 16 x 16 diagonal block (rolled loops on shared memory: straight-
+//      line code on a single warp was instruction-fetch bound), inverts it and forms z; the tensor
+//      warps then apply X = P inv(L)^T to the rows below with DMMA, update the right half with the
+//      rank-16 product (DMMA again) and repeat for the second half;
+//   4. X goes from the accumulator registers straight to the workspace in operand order
+//      [k4 chunk][row][4 columns], i.e. exactly the DMMA fragment layout step 2 reads back.
 //   logdet = sum ln d_k (pivots before the square root), quad = z^T z, then the closed form and the
 //   priors (reference gp_likelihood.py:250-278, 357-402).  A non-positive pivot is reported like
 //   LAPACK potrf info (index of the leading minor); NaN pivots give -1.
@@ -32,10 +36,9 @@
 #include "mean_model.cuh"
 
 #define MID_NB 32
-#define MID_STAGES 6
-#define MID_LOOKAHEAD 4
+#define MID_STAGES 6      // ring stages for R > 256 (one fewer below, so two CTAs fit an SM); look-ahead = stages - 2
 #define MID_N_MAX 512
-#define MID_INV_LD 36   // == 4 (mod 16): conflict-free B-fragment loads of inv(L_jj)
+#define MID_INV_LD 36     // == 4 (mod 16): conflict-free B-fragment loads of inv(L)
 
 __host__ __device__ inline int mid_npad(int N) { return (N + MID_NB - 1) & ~(MID_NB - 1); }
 // first element of block column p in a workspace slot: sum_{p' < p} (R - 32 p') * 32
@@ -46,39 +49,227 @@ __host__ inline size_t mid_ws_doubles(int N) {
   const int R = mid_npad(N);
   return mid_colblk_base(R, R / MID_NB);
 }
-__host__ inline int mid_warps(int N) { return mid_npad(N) <= 256 ? 8 : 16; }
-// ring (MID_STAGES k8 slices of at most R - 32 rows) and panel (8 chunks of 4 R + 8 doubles) share one region
+__host__ inline int mid_warps(int N) { return mid_npad(N) <= 256 ? 7 : 15; }   // tensor warps (+ 1 factor warp)
+__host__ __device__ inline int mid_stages(int R) { return R <= 256 ? MID_STAGES - 1 : MID_STAGES; }
+// ring (k8 slices of at most R - 32 rows) and panel (8 chunks of 4 R + 8 doubles) share one region
 __host__ __device__ inline size_t mid_buf_doubles(int R) {
-  const size_t ring = (size_t)MID_STAGES * 8 * (R > 32 ? R - 32 : 32);
+  const size_t ring = (size_t)mid_stages(R) * 8 * (R > 32 ? R - 32 : 32);
   const size_t panel = (size_t)8 * (4 * R + 8);
   return ring > panel ? ring : panel;
 }
 __host__ inline size_t mid_smem_bytes(int N) {
   const int R = mid_npad(N), nw = mid_warps(N);
-  return (mid_buf_doubles(R) + 4 * (size_t)R + (size_t)nw * 32 + 32 * MID_INV_LD + 32 + MRV_MAX_MODPAR + MRV_MAX_HP + 32 +
-          16 + 2 * MID_STAGES) * sizeof(double);
+  return (mid_buf_doubles(R) + 4 * (size_t)R + (size_t)nw * 32 + 32 * MID_INV_LD + 32 + 32 + 16 + 32 * 17 + MRV_MAX_MODPAR +
+          MRV_MAX_HP + 32 + 16 + 2 * MID_STAGES) * sizeof(double);
 }
 
-template <int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 8 ? 2 : 1)
+// Optional phase timers (clock64 deltas of CTA 0, warps 0 and FW), read back via mrv_get_info("mid_t<i>").
+__device__ long long g_mid_timing[32];
+#ifdef MID_TIMING
+#define MID_TICK(i)                              \
+  do {                                           \
+    const long long now_ = clock64();            \
+    tacc_[i] += now_ - tick_;                    \
+    tick_ = now_;                                \
+  } while (0)
+#else
+#define MID_TICK(i) do { } while (0)
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// The factor warp's role, as its own non-inlined function: its register allocation is then free of the
+// tensor warps' 64 accumulator registers (inlined into the kernel the compiler rematerialised
+// addresses with S2R / LDC and spilled inside the pivot loop).  It meets the tensor warps at the
+// seven CTA barriers of every step.
+// ------------------------------------------------------------------------------------------------
+struct MidShared {
+  double *buf, *r, *dvec, *zvec, *rpart, *invL, *rj, *rdiag, *rhsb, *Dm;
+  const double* ws;                         // this CTA's workspace slot (factored block columns)
+  unsigned long long *full_bar, *empty_bar;
+  int stage_stride;
+  unsigned nst;
+};
+
+// Factor the 16 x 16 diagonal sub-block at offset o of the panel: lane = row (rr) x column group (g)
+// -- the two half-warps split the columns of every update.
+__device__ __forceinline__ void mid_factor16(const MidShared& sh, const double* P, int CS, int row0, int o, int lane,
+                                             int& fb, int& fb_nan) {
+  double* const Dm = sh.Dm;
+  double* const invL = sh.invL;
+  double* const rdiag = sh.rdiag;
+  double* const dvec = sh.dvec;
+  double* const zvec = sh.zvec;
+  double* const rhsb = sh.rhsb;
+  const double* const rj = sh.rj;
+
+      // Lean rolled loops: explicit pointers with constant offsets (no per-element index
+      // arithmetic), over-reads past column 15 land in the padding columns 16..31 of Dm / in the
+      // arrays behind invL and are never stored.  Dm[c * 17 + row], c < 32.
+      const int rr = lane & 15, g = lane >> 4;
+      {
+        const double* src = P + (size_t)((o + 8 * g) >> 2) * CS + 4 * (o + rr);
+        double* dst = Dm + (8 * g) * 17 + rr;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dst[u * 17] = src[(size_t)(u >> 2) * CS + (u & 3)];
+      }
+      __syncwarp();
+      double* colk = Dm;
+#pragma unroll 1
+      for (int k = 0; k < 16; ++k, colk += 17) {
+        const double dk = colk[k];
+        if (fb == 0x7fffffff && !(dk > 0.0)) {
+          fb = row0 + o + k + 1;
+          fb_nan = isnan(dk) ? 1 : 0;
+        }
+        const double rs = rsqrt(dk);
+        const double lik = colk[rr] * rs;
+        if (lane == k) {
+          rdiag[k] = rs;
+          dvec[row0 + o + k] = dk;
+        }
+        __syncwarp();
+        if (lane >= k && lane < 16) colk[rr] = lik;
+        __syncwarp();
+        const int cb = k + 1 + 8 * g;                  // first column of this half-warp's batch
+        const double* pl = colk + cb;                  // L[c][k]
+        double* pa = Dm + cb * 17 + rr;                // A[rr][c]
+        const int nst = min(16 - cb, rr - cb + 1);     // store u < nst  <=>  c < 16 && rr >= c
+        double lv[8], av[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          lv[u] = pl[u];
+          av[u] = pa[u * 17];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) av[u] = fma(-lik, lv[u], av[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (u < nst) pa[u * 17] = av[u];
+        __syncwarp();
+      }
+      
+      // inverse of the 16 x 16 factor: column rr per lane, rows split between the half-warps
+      double* X = invL + o * MID_INV_LD + o;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) X[(8 * g + u) * MID_INV_LD + rr] = 0.0;
+      __syncwarp();
+      const double* colq = Dm;
+#pragma unroll 1
+      for (int q = 0; q < 16; ++q, colq += 17) {
+        const double xq = (q >= rr) ? ((q == rr ? 1.0 : 0.0) + X[q * MID_INV_LD + rr]) * rdiag[q] : 0.0;
+        __syncwarp();
+        if (g == 0) X[q * MID_INV_LD + rr] = xq;
+        const int ib = q + 1 + 8 * g;
+        const double* pl = colq + ib;                  // L[i][q]
+        double* px = X + ib * MID_INV_LD + rr;         // X[i][rr]
+        const int nst = 16 - ib;
+        double lv[8], xv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          lv[u] = pl[u];
+          xv[u] = px[u * MID_INV_LD];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) xv[u] = fma(-lv[u], xq, xv[u]);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (u < nst) px[u * MID_INV_LD] = xv[u];
+        __syncwarp();
+      }
+      
+      // z block: rhs = r_block (second half: minus L_BA z_A), z = inv(L) rhs
+      if (g == 0) {
+        double rhs = rj[o + rr];
+        if (o != 0) {
+          const double* lba = P + 4 * (16 + rr);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) rhs = fma(-lba[(size_t)(c >> 2) * CS + (c & 3)], zvec[row0 + c], rhs);
+        }
+        rhsb[rr] = rhs;
+      }
+      __syncwarp();
+      if (g == 0) {
+        double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          z0 = fma(X[rr * MID_INV_LD + c], rhsb[c], z0);
+          z1 = fma(X[rr * MID_INV_LD + c + 1], rhsb[c + 1], z1);
+        }
+        zvec[row0 + o + rr] = z0 + z1;
+      }
+      __syncwarp();
+    }
+
+template <int NWM>
+__device__ __noinline__ void mid_factor_role(MidShared sh, int R, int nblk, unsigned* qg_io, int* fb_out, int* fb_nan_out) {
+  const int lane = threadIdx.x & 31;
+  int fb = 0x7fffffff, fb_nan = 0;
+  unsigned qg = *qg_io;
+  for (int j = 0; j < nblk; ++j) {
+    const int row0 = MID_NB * j, M = R - row0, CS = 4 * M + 8, nsl = 4 * j;
+    // Producer of the operand stream while the tensor warps run the update loop of this step: slice q =
+    // k8 columns [8 (q&3), +8) of block column q >> 2, rows [row0, R), two 1-D bulk copies into ring
+    // stage (qg + q) % nst.  A dedicated producer runs as far ahead as the ring allows (all stages in
+    // flight), so the consumers only ever wait for data, never for each other.
+    if (lane == 0) {
+      const unsigned chunk_bytes = (unsigned)M * 4u * (unsigned)sizeof(double);
+      for (int q = 0; q < nsl; ++q) {
+        const unsigned qglob = qg + (unsigned)q, st = qglob % sh.nst, u = qglob / sh.nst;
+        if (u > 0) mbar_wait(&sh.empty_bar[st], (u - 1) & 1u);
+        const int p = q >> 2, c0 = 2 * (q & 3), Rp = R - MID_NB * p;
+        const double* src = sh.ws + mid_colblk_base(R, p) + (size_t)c0 * Rp * 4 + (size_t)(row0 - MID_NB * p) * 4;
+        double* dst = sh.buf + (size_t)st * sh.stage_stride;
+        mbar_expect_tx(&sh.full_bar[st], 2u * chunk_bytes);
+        bulk_g2s(dst, src, chunk_bytes, &sh.full_bar[st]);
+        bulk_g2s(dst + (size_t)M * 4, src + (size_t)Rp * 4, chunk_bytes, &sh.full_bar[st]);
+      }
+    }
+    qg += (unsigned)nsl;
+    __syncwarp();
+    __syncthreads();                                   // B1: update loop done, rpart complete
+    {
+      double s = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < NWM; ++ww) s += sh.rpart[ww * 32 + lane];   // fixed order
+      sh.rj[lane] = sh.r[row0 + lane] - s;
+    }
+    __syncthreads();                                   // B2: panel is in shared memory
+    mid_factor16(sh, sh.buf, CS, row0, 0, lane, fb, fb_nan);
+    __syncthreads();                                   // B3
+    __syncthreads();                                   // B4: X_A applied
+    __syncthreads();                                   // B5: right half updated
+    mid_factor16(sh, sh.buf, CS, row0, 16, lane, fb, fb_nan);
+    __syncthreads();                                   // B6
+    __syncthreads();                                   // B7: block column stored
+  }
+  *qg_io = qg;
+  *fb_out = fb;
+  *fb_nan_out = fb_nan;
+}
+
+template <int NWM>
+__global__ void __launch_bounds__((NWM + 1) * 32, NWM == 7 ? 2 : 1)
 mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __restrict__ y,
                 const double* __restrict__ yerr, const double* __restrict__ flags,
                 const double* __restrict__ hp_all, const double* __restrict__ modpar_all,
                 const double* __restrict__ model_given, int to_ecc, int W, double* __restrict__ logl_out,
                 int* __restrict__ status_out, SolveOut so, double* __restrict__ workspace, size_t ws_stride) {
   extern __shared__ double smem[];
-  constexpr int NT = NW * 32;
-  constexpr int FW = NW - 1;                // the warp that factors the diagonal blocks (fewest fragments)
+  constexpr int NT = (NWM + 1) * 32;
+  constexpr int FW = NWM;                   // the dedicated factor warp
   const int N = D.N, R = mid_npad(N), nblk = R / MID_NB;
   double* buf = smem;                       // ring of operand slices  |  panel in operand order
   double* ts = buf + mid_buf_doubles(R);    // R   t (zero padded)
   double* r = ts + R;                       // R   residual (zero padded)
   double* dvec = r + R;                     // R   pivots
   double* zvec = dvec + R;                  // R   z = L^-1 r
-  double* rpart = zvec + R;                 // NW x 32  per-warp partials of the residual update
-  double* invL = rpart + NW * 32;           // 32 x MID_INV_LD  inverse of the current diagonal factor
+  double* rpart = zvec + R;                 // NWM x 32  per-warp partials of the residual update
+  double* invL = rpart + NWM * 32;          // 32 x MID_INV_LD  inverses of the two 16 x 16 diagonal factors
   double* rj = invL + 32 * MID_INV_LD;      // 32  updated residual block
-  double* phys = rj + 32;                   // MRV_MAX_MODPAR
+  double* rdiag = rj + 32;                  // 32  1 / L_kk of the current diagonal block
+  double* rhsb = rdiag + 32;                // 16  right-hand side of the current 16-block solve
+  double* Dm = rhsb + 16;                   // 32 x 17  the diagonal block while it is factored (+ padding columns)
+  double* phys = Dm + 32 * 17;              // MRV_MAX_MODPAR
   double* hpv = phys + MRV_MAX_MODPAR;      // MRV_MAX_HP
   double* red = hpv + MRV_MAX_HP;           // 32
   int* ired = (int*)(red + 32);             // 32 ints
@@ -87,13 +278,15 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tig = lane & 3;
+  const bool is_fw = warp == FW;
   const int stage_stride = (R > 32 ? R - 32 : 32) * 8;   // doubles per ring stage
+  const unsigned NST = (unsigned)mid_stages(R);
   double* ws = workspace + (size_t)blockIdx.x * ws_stride;
 
   if (tid == 0) {
     for (int s = 0; s < MID_STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], NW);
+      mbar_init(&empty_bar[s], NWM);
     }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     asm volatile("fence.proxy.async;\n" ::: "memory");
@@ -134,212 +327,233 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
     __syncthreads();
 
     const CovParams cp = make_cov_params(D.kernel_id, D.variant, hpv);
-    int fb = 0x7fffffff, fb_nan = 0;   // first non-positive pivot (tracked by warp FW)
+    int fb = 0x7fffffff, fb_nan = 0;   // first non-positive pivot (tracked by the factor warp)
 
-    // -K for the m16 row fragment f = warp + NW s of panel jj, into acc[s]
+    // -K for column half h (columns 16 h .. 16 h + 15) of the m16 row fragments f = warp + NWM s of panel jj
     double acc[2][4][4];
-    auto gen_slot = [&](int jj, int s) {
-      const int rw0 = MID_NB * jj, Fj = (R - rw0) >> 4, f = warp + NW * s;
-      if (f < Fj) {
+    auto gen_half = [&](int jj, int h) {
+      const int rw0 = MID_NB * jj, Fj = (R - rw0) >> 4;
 #pragma unroll
-        for (int ni = 0; ni < 4; ++ni) {
-          const int gi0 = rw0 + 16 * f + gq, gj0 = rw0 + 8 * ni + 2 * tig;
-          double frag[4];
-          gen_fragment4(cp, N, gi0, gj0, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1], yerr, frag);
+      for (int s = 0; s < 2; ++s) {
+        const int f = warp + NWM * s;
 #pragma unroll
-          for (int v = 0; v < 4; ++v) acc[s][ni][v] = -frag[v];
+        for (int nh = 0; nh < 2; ++nh) {
+          const int ni = 2 * h + nh;
+          if (f < Fj) {
+            const int gi0 = rw0 + 16 * f + gq, gj0 = rw0 + 8 * ni + 2 * tig;
+            double frag[4];
+            gen_fragment4(cp, N, gi0, gj0, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1], yerr, frag);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[s][ni][v] = -frag[v];
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[s][ni][v] = 0.0;
+          }
         }
-      } else {
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) acc[s][ni][v] = 0.0;
       }
     };
+#ifdef MID_TIMING
+    long long tacc_[16];
+    for (int i_ = 0; i_ < 16; ++i_) tacc_[i_] = 0;
+    long long tick_ = clock64();
+#endif
 
+    if (is_fw) {
+      MidShared sh{buf, r, dvec, zvec, rpart, invL, rj, rdiag, rhsb, Dm, ws, full_bar, empty_bar, stage_stride, NST};
+      mid_factor_role<NWM>(sh, R, nblk, &qg, &fb, &fb_nan);
+    } else
     for (int j = 0; j < nblk; ++j) {
       const int row0 = MID_NB * j, M = R - row0, F = M >> 4, nsl = 4 * j;
       const int CS = 4 * M + 8;   // panel chunk stride (doubles): +8 keeps the fragment stores conflict-free
-      const unsigned chunk_bytes = (unsigned)M * 4u * (unsigned)sizeof(double);
-
-      // slice q of this step = k8 columns [8 (q&3), 8 (q&3) + 8) of block column q >> 2, rows [row0, R)
-      auto issue = [&](int q, unsigned qglob) {
-        const int p = q >> 2, c0 = 2 * (q & 3);
-        const int Rp = R - MID_NB * p;
-        const double* src = ws + mid_colblk_base(R, p) + (size_t)c0 * Rp * 4 + (size_t)(row0 - MID_NB * p) * 4;
-        const unsigned st = qglob % MID_STAGES, u = qglob / MID_STAGES;
-        if (u > 0) mbar_wait(&empty_bar[st], (u - 1) & 1u);
-        double* dst = buf + (size_t)st * stage_stride;
-        mbar_expect_tx(&full_bar[st], 2u * chunk_bytes);
-        bulk_g2s(dst, src, chunk_bytes, &full_bar[st]);
-        bulk_g2s(dst + (size_t)M * 4, src + (size_t)Rp * 4, chunk_bytes, &full_bar[st]);
-      };
-      if (tid == 0) {
-        for (int q = 0; q < MID_LOOKAHEAD && q < nsl; ++q) issue(q, qg + q);
-      }
-
-      // 1. second half of this panel's generation (the first half was generated during the previous
-      //    step's diagonal-block factorisation; the factoring warp catches up on both halves here)
-      if (j == 0 || warp == FW) gen_slot(j, 0);
-      gen_slot(j, 1);
-
-      // 2. stream the factored block columns: acc += A B^T, residual block update on the side
-      double racc = 0.0;
-      for (int q = 0; q < nsl; ++q, ++qg) {
-        if (tid == 0 && q + MID_LOOKAHEAD < nsl) issue(q + MID_LOOKAHEAD, qg + MID_LOOKAHEAD);
-        __syncwarp();
-        const unsigned st = qg % MID_STAGES;
-        mbar_wait(&full_bar[st], (qg / MID_STAGES) & 1u);
-        const double* Sl = buf + (size_t)st * stage_stride;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const double* base = Sl + (size_t)h * M * 4;
-          double b[4];
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni) b[ni] = base[ni * 32 + lane];
-#pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            const int f = warp + NW * s;
-            if (f < F) {   // warp-uniform
-              const double a0 = base[(2 * f) * 32 + lane], a1 = base[(2 * f + 1) * 32 + lane];
-#pragma unroll
-              for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[s][ni], a0, a1, b[ni]);
-            }
-          }
-        }
-        if ((q % NW) == warp) {   // r_j[lane] -= sum_k L[row0 + lane][k] z[k] over this slice's 8 columns
-          const int kbase = MID_NB * (q >> 2) + 8 * (q & 3);
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              racc = fma(Sl[(size_t)h * M * 4 + lane * 4 + kk], zvec[kbase + 4 * h + kk], racc);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[st]);
-      }
-      rpart[warp * 32 + lane] = racc;
-      __syncthreads();   // every warp is done with the ring: buf becomes the panel
-
-      // 3. panel -> shared memory in operand order: (row, col) at (col >> 2) CS + 4 row + (col & 3)
+      const bool more = j + 1 < nblk;
       double* P = buf;
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int f = warp + NW * s;
-        if (f < F) {
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-            for (int v1 = 0; v1 < 2; ++v1) {
-              const int row = 16 * f + gq + 8 * v1;
-              double2 o;
-              o.x = -acc[s][ni][2 * v1 + 0];
-              o.y = -acc[s][ni][2 * v1 + 1];
-              *reinterpret_cast<double2*>(P + (size_t)(2 * ni + (tig >> 1)) * CS + 4 * row + 2 * (tig & 1)) = o;
-            }
-        }
-      }
-      if (tid < 32) {
-        double s = 0.0;
-#pragma unroll
-        for (int ww = 0; ww < NW; ++ww) s += rpart[ww * 32 + tid];   // fixed order
-        rj[tid] = r[row0 + tid] - s;
-      }
-      __syncthreads();
+      double* dstb = ws + mid_colblk_base(R, j);
 
-      if (warp == FW) {
-        // diagonal block: Cholesky of rows 0..31 in registers (lane = row); column k is broadcast
-        // through the panel itself
-        double a[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) a[c] = P[(size_t)(c >> 2) * CS + 4 * lane + (c & 3)];
-        double myrs = 0.0;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const double dk = __shfl_sync(0xffffffffu, a[k], k);
-          if (fb == 0x7fffffff && !(dk > 0.0)) {
-            fb = row0 + k + 1;
-            fb_nan = isnan(dk) ? 1 : 0;
-          }
-          const double rs = rsqrt(dk);
-          const double lik = a[k] * rs;
-          if (lane == k) {
-            myrs = rs;
-            dvec[row0 + k] = dk;
-          }
-          double* colk = P + (size_t)(k >> 2) * CS + (k & 3);
-          if (lane >= k) colk[4 * lane] = lik;
-          __syncwarp();
-#pragma unroll
-          for (int c = k + 1; c < 32; ++c) a[c] = fma(-lik, colk[4 * c], a[c]);
-        }
-        // inverse of the factor, column per lane: x[i] = inv(L)[i][lane]
-        double x[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) x[i] = 0.0;
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const double rdq = __shfl_sync(0xffffffffu, myrs, q);
-          x[q] = (q >= lane) ? ((q == lane ? 1.0 : 0.0) + x[q]) * rdq : 0.0;
-          const double* colq = P + (size_t)(q >> 2) * CS + (q & 3);
-#pragma unroll
-          for (int i = q + 1; i < 32; ++i) x[i] = fma(-colq[4 * i], x[q], x[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) invL[i * MID_INV_LD + lane] = x[i];
-        __syncwarp();
-        // z_j = inv(L_jj) r_j
-        double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
-#pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          z0 = fma(invL[lane * MID_INV_LD + c + 0], rj[c + 0], z0);
-          z1 = fma(invL[lane * MID_INV_LD + c + 1], rj[c + 1], z1);
-          z2 = fma(invL[lane * MID_INV_LD + c + 2], rj[c + 2], z2);
-          z3 = fma(invL[lane * MID_INV_LD + c + 3], rj[c + 3], z3);
-        }
-        zvec[row0 + lane] = (z0 + z1) + (z2 + z3);
-      } else if (j + 1 < nblk) {
-        gen_slot(j + 1, 0);   // hides the single-warp section above
-      }
-      __syncthreads();
-
-      // 4. rows below the diagonal block: X = P inv(L_jj)^T on the tensor pipe, straight to the workspace
-      if (j + 1 < nblk) {
-        double* dstb = ws + mid_colblk_base(R, j);
+      // X = P[rows, 16 h .. 16 h + 15] inv(L_h)^T for the fragments f >= f_min; back into the panel
+      // (first half: the right half still needs it) and, for rows below the diagonal block, to the workspace
+      auto trsm_half = [&](int h, int f_min, bool to_panel) {
 #pragma unroll 1
-        for (int s = 0; s < 2; ++s) {
-          const int f = warp + NW * s;
-          if (f < 2 || f >= F) continue;
-          double X[4][4];
+        for (int f = warp; f < F; f += NWM) {
+          if (f < f_min) continue;
+          double X[2][4];
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni)
+          for (int nh = 0; nh < 2; ++nh)
 #pragma unroll
-            for (int v = 0; v < 4; ++v) X[ni][v] = 0.0;
+            for (int v = 0; v < 4; ++v) X[nh][v] = 0.0;
 #pragma unroll
-          for (int kc = 0; kc < 8; ++kc) {
+          for (int kq = 0; kq < 4; ++kq) {
+            const int kc = 4 * h + kq;
             const double* Pc = P + (size_t)kc * CS + (size_t)(2 * f) * 32 + lane;
             const double a0 = Pc[0], a1 = Pc[32];
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni)
-              if (2 * ni + 1 >= kc)   // inv(L) is lower triangular: columns 8 ni.. need k <= 8 ni + 7
-                dmma_1684(X[ni], a0, a1, invL[(8 * ni + gq) * MID_INV_LD + 4 * kc + tig]);
+            for (int nh = 0; nh < 2; ++nh)
+              if (2 * nh + 1 >= kq)   // inv(L) is lower triangular
+                dmma_1684(X[nh], a0, a1, invL[(16 * h + 8 * nh + gq) * MID_INV_LD + 4 * kc + tig]);
           }
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni)
+          for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+            for (int v1 = 0; v1 < 2; ++v1) {
+              const int row = 16 * f + gq + 8 * v1, chunk = 4 * h + 2 * nh + (tig >> 1);
+              double2 o2;
+              o2.x = X[nh][2 * v1 + 0];
+              o2.y = X[nh][2 * v1 + 1];
+              if (to_panel) *reinterpret_cast<double2*>(P + (size_t)chunk * CS + 4 * row + 2 * (tig & 1)) = o2;
+              if (f >= 2 && more)
+                *reinterpret_cast<double2*>(dstb + (size_t)chunk * M * 4 + (size_t)row * 4 + 2 * (tig & 1)) = o2;
+            }
+        }
+      };
+
+      {
+        // (the operand slices of this step are streamed in by the factor warp, see mid_factor_role)
+        MID_TICK(0);
+
+        // 2. stream the factored block columns: acc += A B^T, residual block update on the side
+        double racc = 0.0;
+        for (int q = 0; q < nsl; ++q) {
+          const unsigned qq = qg + q;
+          MID_TICK(13);
+          const unsigned st = qq % NST;
+          mbar_wait(&full_bar[st], (qq / NST) & 1u);
+          MID_TICK(14);
+          const double* Sl = buf + (size_t)st * stage_stride;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double* base = Sl + (size_t)h * M * 4;
+            double b[4];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = base[ni * 32 + lane];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              const int f = warp + NWM * s;
+              if (f < F) {   // warp-uniform
+                const double a0 = base[(2 * f) * 32 + lane], a1 = base[(2 * f + 1) * 32 + lane];
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[s][ni], a0, a1, b[ni]);
+              }
+            }
+          }
+          if ((q % NWM) == warp) {   // r_j[lane] -= sum_k L[row0 + lane][k] z[k] over this slice's 8 columns
+            const int kbase = MID_NB * (q >> 2) + 8 * (q & 3);
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                racc = fma(Sl[(size_t)h * M * 4 + lane * 4 + kk], zvec[kbase + 4 * h + kk], racc);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[st]);
+          MID_TICK(15);
+        }
+        rpart[warp * 32 + lane] = racc;
+      }
+      qg += (unsigned)nsl;
+      MID_TICK(1);
+      __syncthreads();   // every warp is done with the ring: buf becomes the panel
+      MID_TICK(2);
+
+      // 3. panel -> shared memory in operand order: (row, col) at (col >> 2) CS + 4 row + (col & 3).
+      //    Panel 0 has no update and up to 2 NWM + 2 row fragments: it is generated straight into the
+      //    panel; every later panel has at most 2 NWM fragments and sits in the accumulators.
+      if (j == 0) {
+        for (int f = warp; f < F; f += NWM) {
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) {
+            const int gi0 = 16 * f + gq, gj0 = 8 * ni + 2 * tig;
+            double frag[4];
+            gen_fragment4(cp, N, gi0, gj0, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1], yerr, frag);
+#pragma unroll
+            for (int v1 = 0; v1 < 2; ++v1) {
+              double2 o2;
+              o2.x = frag[2 * v1 + 0];
+              o2.y = frag[2 * v1 + 1];
+              *reinterpret_cast<double2*>(P + (size_t)(2 * ni + (tig >> 1)) * CS + 4 * (gi0 + 8 * v1) + 2 * (tig & 1)) = o2;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int f = warp + NWM * s;
+          if (f < F) {
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+              for (int v1 = 0; v1 < 2; ++v1) {
+                const int row = 16 * f + gq + 8 * v1;
+                double2 o2;
+                o2.x = -acc[s][ni][2 * v1 + 0];
+                o2.y = -acc[s][ni][2 * v1 + 1];
+                *reinterpret_cast<double2*>(P + (size_t)(2 * ni + (tig >> 1)) * CS + 4 * row + 2 * (tig & 1)) = o2;
+              }
+          }
+        }
+      }
+      __syncthreads();
+      MID_TICK(3);
+
+      // first 16 columns: factor | generate, then X_A for all rows below (kept in the panel)
+      if (more) gen_half(j + 1, 0);
+      MID_TICK(4);
+      __syncthreads();
+      MID_TICK(5);
+      trsm_half(0, 1, true);
+      MID_TICK(8);
+      __syncthreads();
+      MID_TICK(9);
+      // right half: P[rows >= 16, 16:32] -= X_A[rows] X_A[16:32]^T (rank 16, DMMA out of the panel)
+      {
+#pragma unroll 1
+        for (int f = warp; f < F; f += NWM) {
+          if (f < 1) continue;
+          double C[2][4];
+#pragma unroll
+          for (int nh = 0; nh < 2; ++nh)
 #pragma unroll
             for (int v1 = 0; v1 < 2; ++v1) {
               const int row = 16 * f + gq + 8 * v1;
-              double2 o;
-              o.x = X[ni][2 * v1 + 0];
-              o.y = X[ni][2 * v1 + 1];
-              *reinterpret_cast<double2*>(dstb + (size_t)(2 * ni + (tig >> 1)) * M * 4 + (size_t)row * 4 + 2 * (tig & 1)) = o;
+              const double2 c2 = *reinterpret_cast<const double2*>(P + (size_t)(4 + 2 * nh + (tig >> 1)) * CS + 4 * row + 2 * (tig & 1));
+              C[nh][2 * v1 + 0] = -c2.x;
+              C[nh][2 * v1 + 1] = -c2.y;
+            }
+#pragma unroll
+          for (int kc = 0; kc < 4; ++kc) {
+            const double* Pc = P + (size_t)kc * CS + lane;
+            const double a0 = Pc[(2 * f) * 32], a1 = Pc[(2 * f + 1) * 32];
+#pragma unroll
+            for (int nh = 0; nh < 2; ++nh) dmma_1684(C[nh], a0, a1, Pc[(2 + nh) * 32]);
+          }
+#pragma unroll
+          for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+            for (int v1 = 0; v1 < 2; ++v1) {
+              const int row = 16 * f + gq + 8 * v1;
+              double2 o2;
+              o2.x = -C[nh][2 * v1 + 0];
+              o2.y = -C[nh][2 * v1 + 1];
+              *reinterpret_cast<double2*>(P + (size_t)(4 + 2 * nh + (tig >> 1)) * CS + 4 * row + 2 * (tig & 1)) = o2;
             }
         }
       }
+      MID_TICK(10);
+      __syncthreads();
+      MID_TICK(11);
+      // second 16 columns
+      if (more) gen_half(j + 1, 1);
+      MID_TICK(6);
+      __syncthreads();
+      MID_TICK(12);
+      trsm_half(1, 2, false);
       asm volatile("fence.proxy.async;\n" ::: "memory");   // generic writes (workspace, buf) before the next bulk copies
       __syncthreads();
+      MID_TICK(7);
     }
 
+#ifdef MID_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1))
+      for (int i_ = 0; i_ < 16; ++i_) g_mid_timing[(warp == 0 ? 0 : 16) + i_] += tacc_[i_];
+#endif
     // reductions, closed form, priors
     double ld_part = 0.0, q_part = 0.0;
     for (int k = tid; k < N; k += NT) {
