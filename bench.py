@@ -332,7 +332,9 @@ def run_ours(args):
         step_ns = ms * 1e6 / args.steps
         shares = {k: (v["ns"] / args.steps) / step_ns for k, v in prof.items() if v["n"] > 0}
         roofline = {
-            "bound": "tensor", "kernel": "gemm_tile_kernel (trailing SYRK/GEMM update, DMMA)" if dom != "fused" else "fused_small_logl_kernel",
+            "bound": "tensor", "kernel": "gemm_tile_kernel (trailing SYRK/GEMM update, DMMA)" if dom != "fused" else
+            {1: "fused_small_blk_kernel (one CTA per walker, K in shared memory)",
+             3: "mid_logl_kernel (one CTA per walker, streamed panel)"}.get(prob.info("path"), "fused"),
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
             "traffic": measured_traffic(args, prob),
             "peak_source": "FP64 DMMA issue microbenchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); "

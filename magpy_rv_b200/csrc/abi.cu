@@ -475,14 +475,37 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
     const unsigned grid = (unsigned)std::min<int64_t>(W, (int64_t)p->num_sms * per_sm);
     const size_t ws_stride = mid_ws_doubles(D.N);
     if (int rc = p->midws.ensure(std::max<size_t>(1, (size_t)grid * ws_stride) * sizeof(double))) return rc;
+    // Keplerian mean models: residuals of ALL walkers first (one CTA each, many per SM), so the up to 200
+    // block-wide Newton reductions per walker do not serialise in front of every factorisation
+    const double* resid_ready = nullptr;
+    const double* phys_ready = nullptr;
+    const int* nonfinite_ready = nullptr;
+    if (p->has_kepler && d_model_given == nullptr) {
+      int rc = 0;
+      if ((rc = p->resid.ensure((size_t)W * p->n_pad * sizeof(double)))) return rc;
+      if ((rc = p->escratch.ensure((size_t)W * p->n_pad * sizeof(double)))) return rc;
+      if ((rc = p->phys.ensure(std::max<size_t>(1, (size_t)W * D.nm) * sizeof(double)))) return rc;
+      if ((rc = p->nonfinite.ensure((size_t)W * sizeof(int)))) return rc;
+      p->prof.begin(CAT_MEAN, st, 0.0, 0.0);
+      mean_residual_kernel<<<(unsigned)W, 256, 0, st>>>(D, p->d_t, p->d_y, p->d_flags, d_modpar, nullptr, to_ecc,
+                                                        p->resid.as<double>(), p->n_pad, p->escratch.as<double>(),
+                                                        p->phys.as<double>(), p->nonfinite.as<int>());
+      p->prof.end(st);
+      p->launches++;
+      resid_ready = p->resid.as<double>();
+      phys_ready = p->phys.as<double>();
+      nonfinite_ready = p->nonfinite.as<int>();
+    }
     const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)W;
     p->prof.begin(CAT_FUSED, st, fl, fl);
     if (nw == 7)
       mid_logl_kernel<7><<<grid, 256, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar, d_model_given,
-                                                  to_ecc, (int)W, d_logl, d_status, so, p->midws.as<double>(), ws_stride);
+                                                  to_ecc, (int)W, d_logl, d_status, so, p->midws.as<double>(), ws_stride,
+                                                  resid_ready, p->n_pad, phys_ready, nonfinite_ready);
     else
       mid_logl_kernel<15><<<grid, 512, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar, d_model_given,
-                                                   to_ecc, (int)W, d_logl, d_status, so, p->midws.as<double>(), ws_stride);
+                                                   to_ecc, (int)W, d_logl, d_status, so, p->midws.as<double>(), ws_stride,
+                                                   resid_ready, p->n_pad, phys_ready, nonfinite_ready);
     p->prof.end(st);
     p->launches++;
     CU(cudaGetLastError());

@@ -253,7 +253,13 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
                 const double* __restrict__ yerr, const double* __restrict__ flags,
                 const double* __restrict__ hp_all, const double* __restrict__ modpar_all,
                 const double* __restrict__ model_given, int to_ecc, int W, double* __restrict__ logl_out,
-                int* __restrict__ status_out, SolveOut so, double* __restrict__ workspace, size_t ws_stride) {
+                int* __restrict__ status_out, SolveOut so, double* __restrict__ workspace, size_t ws_stride,
+                const double* __restrict__ resid_ready, int resid_ld, const double* __restrict__ phys_ready,
+                const int* __restrict__ nonfinite_ready) {
+  // resid_ready / phys_ready / nonfinite_ready (nullable): residuals, converted model parameters and the
+  // non-finite flag precomputed by mean_residual_kernel for all walkers at once (Keplerian mean models:
+  // the reference's whole-vector Newton stop means up to 200 block-wide reductions per walker, which would
+  // otherwise run serially inside every walker's CTA before its factorisation can start).
   extern __shared__ double smem[];
   constexpr int NT = (NWM + 1) * 32;
   constexpr int FW = NWM;                   // the dedicated factor warp
@@ -297,8 +303,8 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
     __syncthreads();
     if (tid == 0) {
       for (int i = 0; i < D.nh; ++i) hpv[i] = hp_all[(size_t)w * D.nh + i];
-      for (int i = 0; i < D.nm; ++i) phys[i] = modpar_all[(size_t)w * D.nm + i];
-      if (model_given == nullptr) convert_to_ecc(D, phys, to_ecc);
+      for (int i = 0; i < D.nm; ++i) phys[i] = (phys_ready ? phys_ready : modpar_all)[(size_t)w * D.nm + i];
+      if (model_given == nullptr && phys_ready == nullptr) convert_to_ecc(D, phys, to_ecc);
     }
     for (int i = tid; i < R; i += NT) {
       ts[i] = i < N ? t[i] : 0.0;
@@ -308,17 +314,20 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
     __syncthreads();
 
     // residual (same device functions and operation order as the other paths)
-    if (model_given != nullptr) {
+    if (resid_ready != nullptr) {
+      for (int i = tid; i < N; i += NT) r[i] = resid_ready[(size_t)w * resid_ld + i];
+      __syncthreads();
+    } else if (model_given != nullptr) {
       for (int i = tid; i < N; i += NT) r[i] = model_given[(size_t)w * N + i];
       __syncthreads();
     } else {
       cta_mean_model(D, ts, flags, phys, r, /*E scratch=*/buf, red);
     }
-    int bad = 0;
+    int bad = nonfinite_ready ? nonfinite_ready[w] : 0;
     for (int i = tid; i < R; i += NT) {
       double v = 0.0;
       if (i < N) {
-        v = so.given_is_resid ? r[i] : __dsub_rn(y[i], r[i]);
+        v = (so.given_is_resid || resid_ready != nullptr) ? r[i] : __dsub_rn(y[i], r[i]);
         bad |= !isfinite(v);
       }
       r[i] = v;

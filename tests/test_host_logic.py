@@ -241,3 +241,44 @@ def test_chain_parity_with_options(oracle_backend):
     np.testing.assert_array_equal(logL, g["logL"])
     np.testing.assert_array_equal(mass, g["mass"])
     assert np.all(mp[:, :, 4] [mp[:, :, 4] != 0] == mp[0, 0, 4]) or True   # t0_0 does not vary where recorded
+
+
+def test_native_stretch_scan_matches_python_scan(oracle_backend):
+    """mrv_stretch_scan (csrc/host_sampler.h) against the NumPy/Python scan it replaces, on inputs that
+    force many redraws (negative hyper-parameters, Keplerians with P, K, t0 < 0 or Sk^2 + Ck^2 > 1):
+    same z, same proposals, same position of the np.random stream afterwards; also with a uniform
+    buffer that runs dry in the middle of a chain."""
+    cfg = workloads.make_config("C3", W=24, N=20)
+    random.seed(3)
+    np.random.seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = mcmc.MCMC(cfg["t"], cfg["y"], cfg["yerr"], cfg["hparam0"], cfg["kernel"], cfg["model_par0"],
+                      cfg["model_list"], cfg["prior_list"], 24)
+    rng = np.random.default_rng(12)
+    for trial in range(20):
+        n = int(rng.integers(1, 70))
+        a = float(rng.choice([2.0, 2.5, 1.3]))
+        Xj = np.abs(rng.normal(1.0, 0.3, (n, 5)))
+        dX = np.maximum(rng.normal(0.0, 0.9, (n, 5)), -1.2 * Xj)       # z <= a keeps some proposals valid
+        # every chain has a non-empty valid window z <= 0.83 (z >= 1/a <= 0.77), so the redraw loops terminate
+        Xjm = np.column_stack([np.abs(rng.normal(4, 1, n)), np.abs(rng.normal(50, 5, n)), rng.uniform(-.3, .3, n),
+                               rng.uniform(-.3, .3, n), np.abs(rng.normal(10, 2, n))])
+        dXm = rng.normal(0, 1, (n, 5)) * np.array([2.0, 20.0, 0.5, 0.5, 4.0])
+        dXm = np.maximum(dXm, -0.9 * np.abs(Xjm) * np.array([1, 1, 0, 0, 1]) - np.array([0, 0, 9, 9, 0]))
+        dXm[:, 2:4] = np.clip(dXm[:, 2:4], -0.4, 0.4)
+
+        def stretch(u):
+            return (u * (a - 1) + 1) ** 2 / a
+
+        out = []
+        for which in ("python", "native"):
+            np.random.seed(1000 + trial)
+            z, h, mm = np.empty(n), np.empty((n, 5)), np.empty((n, 5))
+            if which == "python":
+                m._scan_python(n, Xj, dX, Xjm, dXm, stretch, (), z, h, mm)
+            else:
+                m._scan_native(n, Xj, dX, Xjm, dXm, a, z, h, mm)
+            out.append((z, h, mm, np.random.rand()))
+        for x, y in zip(out[0][:3], out[1][:3]):
+            np.testing.assert_array_equal(x, y)
+        assert out[0][3] == out[1][3], "np.random stream left at a different position"

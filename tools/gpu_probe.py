@@ -8,12 +8,15 @@ from magpy_rv_b200 import _native, engine
 
 lib = _native.lib()
 print("DMMA peak TF/s:", lib.mrv_fp64_mma_peak(0, 20000) / 1e12, " DFMA peak TF/s:", lib.mrv_fp64_fma_peak(0, 20000) / 1e12, flush=True)
+path_opt = int(os.environ.get("MRV_PATH", "0"))
 sizes = [(100, 1024), (168, 1024), (300, 512), (500, 512), (1024, 512), (2048, 128), (4096, 64), (8192, 16)]
 if len(sys.argv) > 1:
     sizes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
 for N, W in sizes:
     cfg = workloads.make_config("C5", W=W, N=N)
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"])
+    if path_opt:
+        prob.set_option("path", path_opt)
     for panel, impl in (((8, 0),) if N > 168 else ((1, 0),)):
         prob.set_option("panel_tiles", panel)
         prob.set_option("gemm_impl", impl)
