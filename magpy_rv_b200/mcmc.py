@@ -322,21 +322,21 @@ class MCMC:
         kep = self._kepler_offsets()
         kep_p = kep.ctypes.data_as(nat.c_int32_p) if kep.size else None
         done = ctypes.c_int64(0)
-        state0 = np.random.get_state()
-        buf = np.empty(0)
-        consumed = drawn = 0
+        # Every chain that is not finished needs at least one more uniform, so drawing exactly
+        # (chains left) numbers per round never overdraws: the np.random stream ends where the
+        # reference leaves it without any get_state / set_state rewind.  Draws of a chain that ran
+        # dry in the middle of its redraws stay at the head of `buf` and are re-scanned.
+        buf = None
+        nh, nm, n_kep = Xj.shape[1], Xj_mod.shape[1], int(kep.size)
+        p_Xj, p_dX, p_Xjm, p_dXm = Xj.ctypes.data, dX.ctypes.data, Xj_mod.ctypes.data, dX_mod.ctypes.data
+        p_z, p_hp, p_mod = z.ctypes.data, new_hp.ctypes.data, new_mod.ctypes.data
+        p_done = ctypes.byref(done)
         while done.value < n_chains:
-            fresh = (n_chains - done.value) + (16 if drawn else 0)
-            buf = np.concatenate([buf, np.random.rand(fresh)]) if buf.size else np.random.rand(fresh)
-            drawn += fresh
-            used = lib.mrv_stretch_scan(nat.dptr(buf), buf.size, done.value, n_chains, Xj.shape[1], Xj_mod.shape[1],
-                                        nat.dptr(Xj), nat.dptr(dX), nat.dptr(Xj_mod), nat.dptr(dX_mod), float(a), kep_p,
-                                        int(kep.size), ctypes.byref(done), nat.dptr(z), nat.dptr(new_hp), nat.dptr(new_mod))
-            consumed += used
+            fresh = np.random.rand(n_chains - done.value)
+            buf = fresh if buf is None or buf.size == 0 else np.concatenate([buf, fresh])
+            used = lib.mrv_stretch_scan(buf.ctypes.data, buf.size, done.value, n_chains, nh, nm, p_Xj, p_dX, p_Xjm, p_dXm,
+                                        float(a), kep_p, n_kep, p_done, p_z, p_hp, p_mod)
             buf = buf[used:]
-        if consumed != drawn:               # hand the surplus back: rewind and replay what was consumed
-            np.random.set_state(state0)
-            np.random.rand(consumed)
 
     def _scan_python(self, n_chains, Xj, dX, Xj_mod, dX_mod, stretch, check_args, z, new_hp, new_mod):
         """Same scan in NumPy/Python (used when Rstar and Mstar are given: the reference's orbit_check
