@@ -139,6 +139,14 @@ int mrv_covmatrix_from_dist(int device, int kernel_id, int kernel_variant, const
 int mrv_distances(int device, const double* t1, int64_t n1, const double* t2, int64_t n2,
                   double* dist_e_out, double* dist_se_out);
 
+/* Gelman-Rubin statistic per parameter over the walker chains, chains [n_steps, n_chains, n_par]
+ * row-major (the layout of MCMC.hparameter_list / model_parameter_list), the first burn_in steps
+ * dropped.  NOT a parity entry: the reference's gelman_rubin_calc (mcmc.py:571-662) mislabels the axes
+ * and drops into pdb; this computes the statistic it intends,
+ * R = ((1 - 1/L) W + B/L) / W, and 1 for a parameter that never moves (mcmc.py:632-638). */
+int mrv_gelman_rubin(int device, const double* chains, int64_t n_steps, int64_t n_chains, int64_t n_par,
+                     int64_t burn_in, double* R_out);
+
 /* Host-only helper (no GPU work): the sequential scan of one stretch-move split, MCMC.split_step
  * (mcmc.py:322-376).  Chains chain_begin..n_chains-1 consume the uniforms u[0..n_u) in order,
  * z = (u (a-1) + 1)^2 / a, proposal = Xj + dX z, redrawing while a hyper-parameter is negative or

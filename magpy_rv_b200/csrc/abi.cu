@@ -863,6 +863,28 @@ extern "C" int mrv_distances(int device, const double* t1, int64_t n1, const dou
   return 0;
 }
 
+extern "C" int mrv_gelman_rubin(int device, const double* chains, int64_t n_steps, int64_t n_chains, int64_t n_par,
+                                int64_t burn_in, double* R_out) {
+  if (!chains || !R_out) return fail(-1, "null argument");
+  if (n_par <= 0) return 0;
+  if (burn_in < 0 || n_steps - burn_in < 2) return fail(-1, "need at least 2 steps after the burn-in (steps=%lld, burn_in=%lld)", (long long)n_steps, (long long)burn_in);
+  if (n_chains < 2) return fail(-1, "need at least 2 chains");
+  if (int rc = require_device(device)) return rc;
+  double *d_c = nullptr, *d_R = nullptr;
+  int rc = 0;
+  if ((rc = upload(&d_c, chains, (size_t)n_steps * n_chains * n_par))) return rc;
+  cudaError_t e = cudaMalloc((void**)&d_R, n_par * sizeof(double));
+  if (e == cudaSuccess) {
+    gelman_rubin_kernel<<<(unsigned)n_par, 256>>>(d_c, n_steps, n_chains, n_par, burn_in, d_R);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(R_out, d_R, n_par * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_c);
+  cudaFree(d_R);
+  if (e != cudaSuccess) return fail(-2, "mrv_gelman_rubin: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
   if (!p || !key) return fail(-1, "null argument");

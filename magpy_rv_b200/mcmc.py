@@ -431,9 +431,23 @@ class MCMC:
         return self.logL_list, self.hparameter_list, self.model_parameter_list, self.accepted, self.mass_list
 
     def gelman_rubin_calc(self, burn_in=200):
-        """The reference's implementation (mcmc.py:571-662) is broken (mislabelled axes, drops
-        into pdb) and is out of the hot-path scope."""
-        raise NotImplementedError("gelman_rubin_calc is out of scope (SURVEY.md F10 / 8(f) item 4)")
+        """Gelman-Rubin statistic of every hyper-parameter, then every model parameter, over the walker
+        chains after ``burn_in`` steps, computed on the GPU (``mrv_gelman_rubin``).
+
+        NOT a parity function: the reference's implementation (mcmc.py:571-662) reads the
+        [steps, walkers, parameters] history with its axes mislabelled and drops into pdb
+        (SURVEY.md F10); this returns the statistic it intends, R = ((1 - 1/L) W + B/L) / W with
+        chains = walkers, and 1.0 for a parameter that never moves (mcmc.py:632-638)."""
+        from . import _native as nat
+        out = []
+        for hist in (self.hparameter_list, self.model_parameter_list):
+            arr = nat.as_f64(hist)
+            R = np.empty(arr.shape[2])
+            rc = nat.lib().mrv_gelman_rubin(nat.default_device(), nat.dptr(arr), arr.shape[0], arr.shape[1], arr.shape[2],
+                                            int(burn_in), nat.dptr(R))
+            nat.check(rc, "mrv_gelman_rubin")
+            out.append(R)
+        return np.concatenate(out)
 
 
 def run_MCMC(iterations, t, rv, rv_err, hparam0, kernel_name, model_param0=None, model_name=["no_model"], prior_list=[], numb_chains=None, n_splits=None, a=None, Rstar=None, Mstar=None, flags=None, plot_convergence=False, saving_folder=None, gelman_rubin_limit=1.1):

@@ -426,3 +426,26 @@ def test_status_words_on_both_paths():
         assert st[0] == 0 and st[2] == 0 and st[1] == -1, st
         assert relerr(got[[0, 2]], want) < RTOL
         prob.close()
+
+
+def test_gelman_rubin_on_device():
+    """mrv_gelman_rubin against the textbook formula in NumPy (not a parity test: the reference's
+    gelman_rubin_calc is broken)."""
+    import ctypes
+    from magpy_rv_b200 import _native as nat
+    rng = np.random.default_rng(8)
+    S, W, P, burn = 60, 37, 5, 11
+    chains = rng.normal(0, 1, (S, W, P)) + np.linspace(0, 2, W)[None, :, None] * np.array([0, .1, 1, 3, 0])
+    chains[:, :, 4] = 2.5                      # a parameter that never moves
+    R = np.empty(P)
+    rc = nat.lib().mrv_gelman_rubin(0, nat.dptr(nat.as_f64(chains)), S, W, P, burn, nat.dptr(R))
+    assert rc == 0, nat.last_error()
+    x = chains[burn:]
+    L = x.shape[0]
+    m = x.mean(axis=0)
+    Wv = x.var(axis=0, ddof=1).mean(axis=0)
+    B = L / (W - 1) * ((m - m.mean(axis=0)) ** 2).sum(axis=0)
+    want = ((1 - 1 / L) * Wv + B / L) / np.where(Wv == 0, 1, Wv)
+    want[4] = 1.0
+    np.testing.assert_allclose(R, want, rtol=1e-12)
+    assert np.all(R >= 1.0 - 1e-12) and R[3] > R[2] > R[1]
