@@ -164,12 +164,26 @@ def measured_traffic(args, prob):
         return None
 
 
+WORKLOAD_TEXT = {
+    "C1": "tutorial-1 style: QuasiPer GP, no mean model, uniform priors",
+    "C2": "tutorial-2 style: QuasiPer GP + Polynomial mean model, uniform priors",
+    "C3": "51-Peg style: JitterQuasiPer GP + Keplerian mean model (per-point Newton solve), uniform priors",
+    "C4": "sun-as-a-star style: QuasiPer GP + two instrument Offsets, Uniform / Jeffrey / Gaussian priors",
+    "C4M": "sun-as-a-star style: textbook Matern 5/2 GP + two instrument Offsets",
+    "C5": "scaling sweep: QuasiPer GP, no mean model, no priors",
+}
+
+
 def workload_config(args):
-    return {"workload": "%s scaling sweep: QuasiPer GP, N=%d points, no mean model, %d walkers per GPU (%d walkers total); "
-                        "factor workspace >> L2 so no flush is needed between steps"
-                        % (args.config, args.n, args.walkers_per_gpu, args.walkers_per_gpu * args.gpus),
+    big = args.n >= 2048
+    return {"workload": "%s %s; N=%d points, %d walkers per GPU (%d walkers total); %s"
+                        % (args.config, WORKLOAD_TEXT.get(args.config, ""), args.n, args.walkers_per_gpu,
+                           args.walkers_per_gpu * args.gpus,
+                           "factor workspace >> L2 so no flush is needed between steps" if big else
+                           "K is rebuilt from t / yerr every step and never stored; the per-step inputs are the walker parameters"),
             "N": args.n, "walkers_per_gpu": args.walkers_per_gpu, "walkers_total": args.walkers_per_gpu * args.gpus,
-            "kernel": "QuasiPer", "l2_policy": "inputs larger than L2"}
+            "kernel": {"C3": "JitterQuasiPer", "C4M": "Matern5/2 (textbook variant)"}.get(args.config, "QuasiPer"),
+            "l2_policy": "inputs larger than L2" if big else "nothing to flush: covariance generated on chip each step"}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -448,4 +448,4 @@ def test_gelman_rubin_on_device():
     want = ((1 - 1 / L) * Wv + B / L) / np.where(Wv == 0, 1, Wv)
     want[4] = 1.0
     np.testing.assert_allclose(R, want, rtol=1e-12)
-    assert np.all(R >= 1.0 - 1e-12) and R[3] > R[2] > R[1]
+    assert R[3] > R[2] > R[1] and R[4] == 1.0      # stronger between-chain drift -> larger R
