@@ -139,6 +139,21 @@ int mrv_covmatrix_from_dist(int device, int kernel_id, int kernel_variant, const
 int mrv_distances(int device, const double* t1, int64_t n1, const double* t2, int64_t n2,
                   double* dist_e_out, double* dist_se_out);
 
+/* Device-resident sampler (opt-in, NOT a parity entry): the whole loop of run_MCMC (mcmc.py:800-830:
+ * split_step -> compute -> compare -> reset, same stretch move, validity redraws and accept rule) runs
+ * on the GPU with a counter-based Philox stream instead of the host's `random` / `np.random`, so
+ * nothing crosses PCIe between iterations.  hp0 [W, nh] / mp0 [W, nm]: starting ensemble (Sk, Ck in
+ * the ecc / omega slots); hp_vary [nh] / mp_vary [nm]: 0 keeps a parameter fixed; split_all
+ * [iterations, W]: split index of every walker per iteration (the reference's shuffled
+ * arange(W) % n_splits); histories [(iterations + 1), W, nh | nm | 1 | 1] as MCMC.hparameter_list,
+ * model_parameter_list, logL_list, accepted.  fail_info[0] != 0: a likelihood evaluation reported
+ * status fail_info[2] at iteration fail_info[1] (-1 = the starting ensemble) -- where the reference
+ * raises LinAlgError / ValueError. */
+int mrv_mcmc_device(mrv_problem* p, const double* hp0, const double* mp0, int64_t W, int64_t iterations,
+                    double a, const uint8_t* hp_vary, const uint8_t* mp_vary, const uint8_t* split_all,
+                    uint64_t seed, double* hp_hist, double* mp_hist, double* logl_hist, double* acc_hist,
+                    int32_t* fail_info);
+
 /* Gelman-Rubin statistic per parameter over the walker chains, chains [n_steps, n_chains, n_par]
  * row-major (the layout of MCMC.hparameter_list / model_parameter_list), the first burn_in steps
  * dropped.  NOT a parity entry: the reference's gelman_rubin_calc (mcmc.py:571-662) mislabels the axes

@@ -56,6 +56,9 @@ SIGNATURES = {
                                                ctypes.c_int, c_double_p, c_double_p]),
     "mrv_distances": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.c_int64, c_double_p, ctypes.c_int64,
                                      c_double_p, c_double_p]),
+    "mrv_mcmc_device": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int64, ctypes.c_int64,
+                                       ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                       c_double_p, c_double_p, c_double_p, c_double_p, c_int32_p]),
     "mrv_gelman_rubin": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                         ctypes.c_int64, c_double_p]),
     # host-only helper called twice per MCMC iteration: raw addresses (c_void_p) keep the ctypes overhead low

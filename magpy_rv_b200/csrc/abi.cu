@@ -20,6 +20,7 @@
 #include "small_logl.cuh"
 #include "mid_logl.cuh"
 #include "host_sampler.h"
+#include "device_sampler.cuh"
 
 static thread_local std::string g_err;
 
@@ -861,6 +862,109 @@ extern "C" int mrv_distances(int device, const double* t1, int64_t n1, const dou
   cleanup();
   if (e != cudaSuccess) return fail(-2, "distances: %s", cudaGetErrorString(e));
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-resident sampler loop (device_sampler.cuh): proposals, batched likelihood and accept / reject
+// are enqueued back to back on the handle's stream for all iterations; the host only uploads the
+// starting ensemble and the per-iteration split assignment and downloads the histories at the end.
+// ------------------------------------------------------------------------------------------------
+extern "C" int mrv_mcmc_device(mrv_problem* p, const double* hp0, const double* mp0, int64_t W, int64_t iterations,
+                               double a, const uint8_t* hp_vary, const uint8_t* mp_vary, const uint8_t* split_all,
+                               uint64_t seed, double* hp_hist, double* mp_hist, double* logl_hist, double* acc_hist,
+                               int32_t* fail_info) {
+  if (!p || !hp0 || !mp0 || !hp_vary || !mp_vary || !split_all || !hp_hist || !mp_hist || !logl_hist || !acc_hist || !fail_info)
+    return fail(-1, "null argument");
+  if (W <= 1 || iterations < 0) return fail(-1, "need W > 1 walkers and iterations >= 0");
+  CU(cudaSetDevice(p->device));
+  const ProblemDesc& D = p->desc;
+  const int nh = D.nh, nm = D.nm;
+  SamplerArgs A;
+  memset(&A, 0, sizeof A);
+  A.W = (int)W;
+  A.nh = nh;
+  A.nm = nm;
+  A.a = a;
+  A.rng.seed = seed;
+  for (int i = 0; i < D.n_ops; ++i)
+    if (D.ops[i].type == MRV_MODEL_KEPLER) A.kep[A.n_kep++] = D.ops[i].param_offset;
+  for (int i = 0; i < nh; ++i) A.hp_vary[i] = hp_vary[i];
+  for (int i = 0; i < nm; ++i) A.mp_vary[i] = mp_vary[i];
+
+  const size_t rows = (size_t)iterations + 1;
+  DevBuf b_hp0, b_mp0, b_l0, b_hp, b_mp, b_l, b_st, b_split, b_hh, b_mh, b_lh, b_ah, b_fail;
+  DevBuf* all[] = {&b_hp0, &b_mp0, &b_l0, &b_hp, &b_mp, &b_l, &b_st, &b_split, &b_hh, &b_mh, &b_lh, &b_ah, &b_fail};
+  auto done = [&](int code) {
+    for (DevBuf* b : all) b->release();
+    return code;
+  };
+  int rc = 0;
+  if ((rc = b_hp0.ensure((size_t)W * nh * 8)) || (rc = b_mp0.ensure(std::max<size_t>(1, (size_t)W * nm) * 8)) ||
+      (rc = b_l0.ensure((size_t)W * 8)) || (rc = b_hp.ensure((size_t)W * nh * 8)) ||
+      (rc = b_mp.ensure(std::max<size_t>(1, (size_t)W * nm) * 8)) || (rc = b_l.ensure((size_t)W * 8)) ||
+      (rc = b_st.ensure((size_t)W * 4)) || (rc = b_split.ensure(std::max<size_t>(1, (size_t)iterations * W))) ||
+      (rc = b_hh.ensure(rows * W * nh * 8)) || (rc = b_mh.ensure(std::max<size_t>(1, rows * W * nm) * 8)) ||
+      (rc = b_lh.ensure(rows * W * 8)) || (rc = b_ah.ensure(rows * W * 8)) || (rc = b_fail.ensure(8 * sizeof(int))))
+    return done(rc);
+  cudaStream_t st = p->stream;
+  cudaError_t e = cudaMemcpyAsync(b_hp0.p, hp0, (size_t)W * nh * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && nm > 0) e = cudaMemcpyAsync(b_mp0.p, mp0, (size_t)W * nm * 8, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && iterations > 0)
+    e = cudaMemcpyAsync(b_split.p, split_all, (size_t)iterations * W, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(b_fail.p, 0, 8 * sizeof(int), st);
+  if (e != cudaSuccess) return done(fail(-2, "mrv_mcmc_device upload: %s", cudaGetErrorString(e)));
+  // initial state = history row 0 (accepted = 1, as the reference records)
+  if ((rc = run_logl(p, b_hp0.as<double>(), b_mp0.as<double>(), nullptr, W, 1, b_l0.as<double>(), b_st.as<int>(), st))) return done(rc);
+  std::vector<int> st0((size_t)W);
+  e = cudaMemcpyAsync(st0.data(), b_st.p, (size_t)W * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return done(fail(-2, "mrv_mcmc_device initial evaluation: %s", cudaGetErrorString(e)));
+  fail_info[0] = fail_info[1] = fail_info[2] = 0;
+  for (int64_t w = 0; w < W; ++w)
+    if (st0[(size_t)w] != 0) {
+      fail_info[0] = 1;
+      fail_info[1] = -1;
+      fail_info[2] = st0[(size_t)w];
+      return done(0);
+    }
+  e = cudaMemcpyAsync(b_hh.p, b_hp0.p, (size_t)W * nh * 8, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess && nm > 0) e = cudaMemcpyAsync(b_mh.p, b_mp0.p, (size_t)W * nm * 8, cudaMemcpyDeviceToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(b_lh.p, b_l0.p, (size_t)W * 8, cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return done(fail(-2, "mrv_mcmc_device history init: %s", cudaGetErrorString(e)));
+  {
+    std::vector<double> ones((size_t)W, 1.0);
+    e = cudaMemcpyAsync(b_ah.p, ones.data(), (size_t)W * 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(fail(-2, "mrv_mcmc_device history init: %s", cudaGetErrorString(e)));
+  }
+  const unsigned blocks = (unsigned)((W + 127) / 128);
+  for (int64_t it = 0; it < iterations; ++it) {
+    stretch_propose_kernel<<<blocks, 128, 0, st>>>(A, (unsigned)it, b_split.as<unsigned char>() + (size_t)it * W,
+                                                   b_hp0.as<double>(), b_mp0.as<double>(), b_hp.as<double>(),
+                                                   b_mp.as<double>(), b_fail.as<int>() + 4);
+    if ((rc = run_logl(p, b_hp.as<double>(), b_mp.as<double>(), nullptr, W, 1, b_l.as<double>(), b_st.as<int>(), st)))
+      return done(rc);
+    stretch_accept_kernel<<<blocks, 128, 0, st>>>(A, (unsigned)it, (long long)it + 1, b_hp.as<double>(), b_mp.as<double>(),
+                                                  b_l.as<double>(), b_st.as<int>(), b_hp0.as<double>(),
+                                                  b_mp0.as<double>(), b_l0.as<double>(), b_hh.as<double>(),
+                                                  b_mh.as<double>(), b_lh.as<double>(), b_ah.as<double>(),
+                                                  b_fail.as<int>());
+    p->launches += 2;
+  }
+  e = cudaGetLastError();
+  int fl[8] = {0};
+  if (e == cudaSuccess) e = cudaMemcpyAsync(hp_hist, b_hh.p, rows * W * nh * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && nm > 0) e = cudaMemcpyAsync(mp_hist, b_mh.p, rows * W * nm * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(logl_hist, b_lh.p, rows * W * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(acc_hist, b_ah.p, rows * W * 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(fl, b_fail.p, sizeof fl, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return done(fail(-2, "mrv_mcmc_device: %s", cudaGetErrorString(e)));
+  fail_info[0] = fl[0];
+  fail_info[1] = fl[1];
+  fail_info[2] = fl[2];
+  if (fl[4] != 0) return done(fail(-5, "mrv_mcmc_device: proposal kernel could not find a %s", fl[4] == 1 ? "partner walker in another split" : "valid stretch for some walker"));
+  return done(0);
 }
 
 extern "C" int mrv_gelman_rubin(int device, const double* chains, int64_t n_steps, int64_t n_chains, int64_t n_par,

@@ -430,6 +430,70 @@ class MCMC:
         self.mass0_list[0, acc] = self.mass[0, acc]
         return self.logL_list, self.hparameter_list, self.model_parameter_list, self.accepted, self.mass_list
 
+    # -- device-resident loop (opt-in, non-parity) ----------------------------------------------------------
+    def run_device(self, iterations, n_splits=2, a=2., seed=0):
+        """Run ``iterations`` stretch-move iterations entirely on the GPU (``mrv_mcmc_device``,
+        csrc/device_sampler.cuh) starting from the current state, and append them to the histories.
+
+        Same algorithm as split_step / compute / compare / reset, but with a counter-based Philox
+        stream on the device instead of the host's ``random`` / ``np.random``: reproducible for a
+        ``seed``, NOT comparable step by step with the reference (the host loop stays the parity
+        path).  Nothing crosses PCIe between iterations, so small problems are no longer bound by the
+        host sampler.  Single GPU; masses are recomputed on the host
+        from the recorded chains with the reference's argument order (F9), vectorised."""
+        import ctypes
+        from . import _native as nat
+        prob = getattr(self._backend, "problem", None)
+        if prob is None:
+            raise RuntimeError("run_device needs the CUDA backend (no CPU fallback)")
+        W, it = self.numb_chains, int(iterations)
+        rng = np.random.default_rng(seed)
+        base = (np.arange(W) % int(n_splits)).astype(np.uint8)
+        split_all = rng.permuted(np.tile(base, (max(it, 1), 1)), axis=1)[:it]
+        split_all = np.ascontiguousarray(split_all, dtype=np.uint8)
+        hp_vary = np.ascontiguousarray(self.hp_vary, dtype=np.uint8)
+        mp_vary = np.ascontiguousarray(self.modpar_vary, dtype=np.uint8)
+        hp0 = nat.as_f64(self.hp0[0])
+        mp0 = nat.as_f64(self.modpar0[0])
+        hh = np.empty((it + 1, W, self.hlen))
+        mh = np.empty((it + 1, W, self.plen))
+        lh = np.empty((it + 1, W, 1))
+        ah = np.empty((it + 1, W, 1))
+        fail = np.zeros(3, dtype=np.int32)
+        rc = nat.lib().mrv_mcmc_device(prob._handle, nat.dptr(hp0), nat.dptr(mp0), W, it, float(a), hp_vary.ctypes.data,
+                                       mp_vary.ctypes.data, split_all.ctypes.data, int(seed) & (2**64 - 1), nat.dptr(hh),
+                                       nat.dptr(mh), nat.dptr(lh), nat.dptr(ah), fail.ctypes.data_as(nat.c_int32_p))
+        nat.check(rc, "mrv_mcmc_device")
+        if fail[0]:
+            engine.raise_for_status(np.array([fail[2]], dtype=np.int32))
+        # row 0 repeats the current state: append rows 1.. to the histories and move the state
+        for k in range(1, it + 1):
+            self._hist_hp.append(hh[k:k + 1])
+            self._hist_mod.append(mh[k:k + 1])
+            self._hist_logL.append(lh[k:k + 1])
+            self._hist_acc.append(ah[k:k + 1])
+        acc = ah[1:, :, 0] == 1.0
+        if it > 0 and acc.any():
+            last = it - np.argmax(acc[::-1], axis=0)              # last accepted row per walker (valid where any)
+            moved = acc.any(axis=0)
+            cols = np.nonzero(moved)[0]
+            self.hp0[0, cols] = hh[last[cols], cols]
+            self.modpar0[0, cols] = mh[last[cols], cols]
+            self.logL0[0, cols] = lh[last[cols], cols]
+        if self._n_planets:
+            masses = np.zeros((it, W, self._n_planets))
+            names = self.modpar_names
+            for i in range(self._n_planets):
+                sfx = "" if "P" in names else "_" + str(i)
+                iP, iK, iO = names.index("P" + sfx), names.index("K" + sfx), names.index("omega" + sfx)
+                masses[:, :, i] = aux.mass_calc([mh[1:, :, iP], mh[1:, :, iK], mh[1:, :, iO]], self.Mstar)
+            for k in range(it):
+                self._hist_mass.append(masses[k:k + 1])
+        else:
+            for k in range(it):
+                self._hist_mass.append(np.zeros((1, W, 0)))
+        return self.logL_list, self.hparameter_list, self.model_parameter_list, self.accepted, self.mass_list
+
     def gelman_rubin_calc(self, burn_in=200):
         """Gelman-Rubin statistic of every hyper-parameter, then every model parameter, over the walker
         chains after ``burn_in`` steps, computed on the GPU (``mrv_gelman_rubin``).
@@ -514,3 +578,34 @@ def run_MCMC(iterations, t, rv, rv_err, hparam0, kernel_name, model_param0=None,
     if Mstar is None:
         return logL_list, hparameter_list, model_parameter_list, completed_iterations
     return logL_list, hparameter_list, model_parameter_list, completed_iterations, mass
+
+
+def run_MCMC_device(iterations, t, rv, rv_err, hparam0, kernel_name, model_param0=None, model_name=["no_model"], prior_list=[], numb_chains=None, n_splits=None, a=None, Mstar=None, flags=None, seed=0):
+    """``run_MCMC`` with the whole sampling loop on the GPU (``MCMC.run_device``): same arguments and
+    return tuple, plus ``seed`` for the device random stream.  Opt-in and NOT step-for-step comparable
+    with the reference (different random stream, same algorithm); starting positions are drawn on
+    the host exactly as ``run_MCMC`` draws them."""
+    if model_param0 == None:  # noqa: E711
+        if model_name[0].startswith("no") or model_name[0].startswith("No"):
+            model_param0 = modl.mod_create(["no_model"])
+            model_param0["no"] = par.parameter(value=0., error=0., vary=False)
+        else:
+            raise KeyError("model parameters and model list must be provided when using a model")
+    if numb_chains is not None:
+        assert numb_chains > (len(model_param0) + len(hparam0)) * 2, "number of chains should be larger than the number of free parameters"
+    kwargs = {}
+    if flags is not None:
+        kwargs["flags"] = flags
+    if Mstar is not None:
+        kwargs["Mstar"] = Mstar
+    sampler = MCMC(t, rv, rv_err, hparam0, kernel_name, model_param0, model_name, prior_list,
+                   100 if numb_chains is None else numb_chains, **kwargs)
+    start = time.time()
+    logL_list, hparameter_list, model_parameter_list, accepted, mass = sampler.run_device(
+        iterations, n_splits=2 if n_splits is None else n_splits, a=2. if a is None else a, seed=seed)
+    print("{} iterations have been completed with {} contemporaneous chains".format(iterations, sampler.numb_chains))
+    print("Acceptance Rate = ", int(np.count_nonzero(accepted)) / (iterations * sampler.numb_chains + sampler.numb_chains))
+    print(" ---- %s minutes ----" % ((time.time() - start) / 60))
+    if Mstar is None:
+        return logL_list, hparameter_list, model_parameter_list, iterations
+    return logL_list, hparameter_list, model_parameter_list, iterations, mass

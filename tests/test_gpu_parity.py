@@ -449,3 +449,49 @@ def test_gelman_rubin_on_device():
     want[4] = 1.0
     np.testing.assert_allclose(R, want, rtol=1e-12)
     assert R[3] > R[2] > R[1] and R[4] == 1.0      # stronger between-chain drift -> larger R
+
+
+def test_device_resident_sampler_invariants():
+    """run_MCMC_device (opt-in, non-parity): same seed -> same chains; every recorded step is either the
+    previous position or a valid proposal whose recorded log L is what the likelihood gives for that
+    position; acceptance behaves like the host sampler's on the same problem; non-varying parameters
+    never move."""
+    import contextlib, io, random
+    from magpy_rv_b200 import mcmc
+    cfg = workloads.make_config("C3", W=48, N=120)
+    cfg["model_par0"]["t0"] = par.parameter(value=2450001., error=10., vary=False)
+
+    def run(seed, iters=25):
+        random.seed(5)
+        np.random.seed(5)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return mcmc.run_MCMC_device(iters, cfg["t"], cfg["y"], cfg["yerr"], cfg["hparam0"], cfg["kernel"], cfg["model_par0"],
+                                        cfg["model_list"], cfg["prior_list"], numb_chains=48, seed=seed)
+
+    logL, hp, mp, done = run(7)
+    logL2, hp2, mp2, _ = run(7)
+    np.testing.assert_array_equal(hp, hp2)
+    np.testing.assert_array_equal(logL, logL2)
+    logL3, hp3, _, _ = run(8)
+    assert not np.array_equal(hp, hp3)
+    assert hp.shape == (26, 48, 5) and mp.shape == (26, 48, 5) and logL.shape == (26, 48, 1) and done == 25
+    assert np.all(hp >= 0) and np.all(mp[:, :, 4] == mp[0:1, :, 4])         # validity; t0 never moves from its start
+    assert np.all(mp[:, :, 2] ** 2 + mp[:, :, 3] ** 2 <= 1.0)
+    moved = np.any(hp[1:] != hp[:-1], axis=2)
+    stayed = ~moved
+    assert np.all(logL[1:, :, 0][stayed] == logL[:-1, :, 0][stayed])
+    rate = moved.mean()
+    assert 0.05 < rate < 0.95, rate
+    # recorded log L of the last row == the likelihood at the recorded positions
+    prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["model_list"], cfg["prior_list"])
+    want, st = prob.logl(hp[-1], mp[-1], to_ecc=True)
+    prob.close()
+    assert np.all(st == 0) and relerr(logL[-1, :, 0], want) < RTOL
+    # the host sampler on the same problem accepts at a comparable rate
+    random.seed(5)
+    np.random.seed(5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        _, hp_h, _, _ = mcmc.run_MCMC(25, cfg["t"], cfg["y"], cfg["yerr"], cfg["hparam0"], cfg["kernel"], cfg["model_par0"],
+                                      cfg["model_list"], cfg["prior_list"], numb_chains=48)
+    rate_h = np.any(hp_h[1:] != hp_h[:-1], axis=2).mean()
+    assert abs(rate - rate_h) < 0.2, (rate, rate_h)

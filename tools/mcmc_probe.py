@@ -29,3 +29,10 @@ for a in args:
     print("%s N=%d W=%d kernel=%s models=%s: %.3f ms/iteration -> %.0f evals/s end to end | " % (
         name, cfg["N"], cfg["W"], cfg["kernel"], cfg["model_list"], 1e3 * tot / iters, cfg["W"] * iters / tot)
         + "  ".join("%s %.3f ms" % (k, 1e3 * v / iters) for k, v in tt.items()), flush=True)
+    # the same number of iterations with the device-resident loop (opt-in, non-parity random stream)
+    n_dev = max(iters, 200 if cfg["N"] <= 1000 else iters)
+    m.run_device(5)
+    t0 = time.perf_counter(); m.run_device(n_dev, seed=1); dt = time.perf_counter() - t0
+    acc = float(m.accepted[-n_dev:].mean())
+    print("   device-resident loop: %.3f ms/iteration -> %.0f evals/s end to end (%d iterations, acceptance %.2f)"
+          % (1e3 * dt / n_dev, cfg["W"] * n_dev / dt, n_dev, acc), flush=True)
