@@ -302,6 +302,10 @@ static int effective_panel(const mrv_problem* p) {
   return std::min(24, std::max(8, (p->nt * 3) / 16));
 }
 
+// one point per thread up to 512 points: the Keplerian Newton loop is a chain of up to 200 block-wide
+// reductions per walker, so fewer points per thread shortens every link
+static unsigned mean_threads(int N) { return N > 256 ? 512u : 256u; }
+
 static int choose_path(const mrv_problem* p) {
   if (p->path_opt == MRV_PATH_FUSED_SMEM) return MRV_PATH_FUSED_SMEM;
   if (p->path_opt == MRV_PATH_BLOCKED) return MRV_PATH_BLOCKED;
@@ -488,7 +492,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
       if ((rc = p->phys.ensure(std::max<size_t>(1, (size_t)W * D.nm) * sizeof(double)))) return rc;
       if ((rc = p->nonfinite.ensure((size_t)W * sizeof(int)))) return rc;
       p->prof.begin(CAT_MEAN, st, 0.0, 0.0);
-      mean_residual_kernel<<<(unsigned)W, 256, 0, st>>>(D, p->d_t, p->d_y, p->d_flags, d_modpar, nullptr, to_ecc,
+      mean_residual_kernel<<<(unsigned)W, mean_threads(D.N), 0, st>>>(D, p->d_t, p->d_y, p->d_flags, d_modpar, nullptr, to_ecc,
                                                         p->resid.as<double>(), p->n_pad, p->escratch.as<double>(),
                                                         p->phys.as<double>(), p->nonfinite.as<int>());
       p->prof.end(st);
@@ -547,7 +551,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   CU(cudaMemsetAsync(p->quad.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->fstatus.p, 0, (size_t)W * sizeof(int), st));
   p->prof.begin(CAT_MEAN, st, 0.0, 0.0);
-  mean_residual_kernel<<<(unsigned)W, 256, 0, st>>>(D, p->d_t, so.given_is_resid ? nullptr : p->d_y, p->d_flags, d_modpar,
+  mean_residual_kernel<<<(unsigned)W, mean_threads(D.N), 0, st>>>(D, p->d_t, so.given_is_resid ? nullptr : p->d_y, p->d_flags, d_modpar,
                                                     d_model_given, to_ecc,
                                                     p->resid.as<double>(), p->n_pad, p->escratch.as<double>(),
                                                     p->phys.as<double>(), p->nonfinite.as<int>());

@@ -223,6 +223,8 @@ class MCMC:
         out = np.zeros(shape=(1, W, self._n_planets))
         if self._n_planets == 0:
             return out
+        if isinstance(self.Mstar, (int, float)) and self.Mstar == 0 and np.all(np.isfinite(modpar)):
+            return out      # Mstar = 0 (the default): every mass is exactly 0.0, skip the per-walker loop
         names = self.modpar_names
         for i in range(self._n_planets):
             sfx = "" if "P" in names else "_" + str(i)
