@@ -80,13 +80,20 @@ def use_all_host_threads():
         pass
 
 
-def cpu_sample(cfg_name, N_target, budget_s):
+def cpu_sample(cfg_name, N_target, budget_s, threads=None):
     """Time the oracle's LogL on a bounded sample: the largest N_s <= N_target (halving from the
     target) whose predicted cost fits the budget; scale to N_target by the cubic law of the
     factorisations.  Returns (evals_per_s at N_target, description, seconds spent)."""
     import workloads
     from oracle import logl_port as port
-    use_all_host_threads()
+    if threads is None:
+        use_all_host_threads()
+    else:
+        try:
+            from threadpoolctl import threadpool_limits
+            threadpool_limits(limits=int(threads))
+        except Exception:
+            pass
     t_start = time.perf_counter()
     n = min(N_target, 1024)
     cfg = workloads.make_config(cfg_name, W=2, N=n)
@@ -378,6 +385,9 @@ def run_ours(args):
         if not args.no_cpu_baseline:
             v, desc, _ = cpu_sample(args.config, args.n, args.cpu_budget_s)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_threads(), "kind": "port", "sample": desc}
+            # per-core figure beside the all-cores one; small extra budget
+            v1, desc1, _ = cpu_sample(args.config, args.n, min(8.0, args.cpu_budget_s), threads=1)
+            out["cpu_baseline_1thread"] = {"value": v1, "unit": UNIT, "cores": 1, "kind": "port", "sample": desc1}
         print(json.dumps(out), flush=True)
 
 
