@@ -141,6 +141,9 @@ struct mrv_problem {
   int band_opt = 0;    // UPDATE rasterisation band (tile rows), 0 = default
   int panel_inner_opt = 0;  // inner panel width of the two-level scheme, 0 = default (8)
   int cs_store = 1;    // streaming stores for updated C tiles
+  int substreams_opt = 0;  // 0 = auto (two half-waves on two streams up to 32 tile columns), 1 = one stream
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging
   DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter, midws;
@@ -271,6 +274,9 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
   for (DevBuf* b : bufs) b->release();
   p->prof.destroy();
   if (p->stream) cudaStreamDestroy(p->stream);
+  if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
   delete p;
 }
 
@@ -317,13 +323,15 @@ static int choose_path(const mrv_problem* p) {
 }
 
 // Blocked path for one wave of `B` walkers starting at walker w0.
-static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so) {
+// `slot0`: first walker slot of this (sub-)wave inside the factor / z workspaces of the current wave.
+static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so,
+                    int64_t slot0 = 0) {
   const ProblemDesc& D = p->desc;
   const int nt = p->nt, N = D.N;
   const size_t walker_stride = tile_index(nt - 1, nt - 1) * TILE_ELEMS + TILE_ELEMS;
-  double* A = p->factor.as<double>();
+  double* A = p->factor.as<double>() + (size_t)slot0 * walker_stride;
   double* resid = p->resid.as<double>() + (size_t)w0 * p->n_pad;
-  double* zbuf = p->zbuf.as<double>();
+  double* zbuf = p->zbuf.as<double>() + (size_t)slot0 * TILE;
   double* logdet = p->logdet.as<double>() + w0;
   double* quad = p->quad.as<double>() + w0;
   int* fstatus = p->fstatus.as<int>() + w0;
@@ -558,8 +566,32 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   p->prof.end(st);
   p->launches++;
   CU(cudaGetLastError());
+  // Mid sizes: a wave is cut into two halves on two streams, so the latency-bound
+  // diagonal-tile kernels and the small launches near the end of every tile column of one half overlap
+  // with the GEMMs of the other (per-walker results do not depend on the split: nothing is shared).
+  // measured (tools/substream_probe.py, medians of interleaved runs): +2..12 % for N = 640..4096, -1..+3 % at
+  // 8192, no change at 16384 (left on one stream there: the trailing GEMM's band rasterisation owns the L2)
+  int nsub = p->substreams_opt > 0 ? p->substreams_opt : ((nt <= 64 && B >= 16) ? 2 : 1);
+  nsub = std::min(nsub, 2);
+  if (p->gemm_impl == 1) nsub = 1;   // the persistent GEMM variant shares one tile counter
+  if (nsub == 2 && (!p->aux_stream || !p->ev_fork || !p->ev_join)) {
+    if (!p->aux_stream) CU(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
+    if (!p->ev_fork) CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    if (!p->ev_join) CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  }
   for (int64_t w0 = 0; w0 < W; w0 += B) {
-    if ((rc = run_wave(p, d_hp, w0, std::min<int64_t>(B, W - w0), st, so))) return rc;
+    const int64_t Bw = std::min<int64_t>(B, W - w0);
+    if (nsub == 2 && Bw >= 2) {
+      const int64_t h = (Bw + 1) / 2;
+      CU(cudaEventRecord(p->ev_fork, st));
+      CU(cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0));
+      if ((rc = run_wave(p, d_hp, w0, h, st, so, 0))) return rc;
+      if ((rc = run_wave(p, d_hp, w0 + h, Bw - h, p->aux_stream, so, h))) return rc;
+      CU(cudaEventRecord(p->ev_join, p->aux_stream));
+      CU(cudaStreamWaitEvent(st, p->ev_join, 0));
+    } else if ((rc = run_wave(p, d_hp, w0, Bw, st, so))) {
+      return rc;
+    }
   }
   p->prof.begin(CAT_FINAL, st, 0.0, 0.0);
   finalize_logl_kernel<<<(unsigned)((W + 127) / 128), 128, 0, st>>>(D, (int)W, d_hp, p->phys.as<double>(),
@@ -1012,6 +1044,8 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {
     p->cs_store = (int)value;   // bit 0: streaming C stores; bit 1: L2 prefetch of the next C tile (persistent GEMM)
+  } else if (!strcmp(key, "substreams")) {
+    p->substreams_opt = (int)value;
   } else if (!strcmp(key, "potrf_impl")) {
     if (value < 0 || value > 1) return fail(-1, "potrf_impl must be 0 (blocked DMMA sweep) or 1 (rank-1 sweep)");
     p->potrf_impl = (int)value;

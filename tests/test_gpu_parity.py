@@ -194,6 +194,11 @@ def test_blocked_path_invariances_and_large_n():
         got, _ = prob.logl(cfg["hp"], cfg["modpar"])
         np.testing.assert_array_equal(got, base)          # bitwise: no cross-walker reduction anywhere
     prob.set_option("wave_walkers", 0)
+    for sub in (1, 2):                                    # one stream / two half-waves on two streams
+        prob.set_option("substreams", sub)
+        got, _ = prob.logl(cfg["hp"], cfg["modpar"])
+        np.testing.assert_array_equal(got, base)
+    prob.set_option("substreams", 0)
     for panel in (2, 3):
         prob.set_option("panel_tiles", panel)
         got, _ = prob.logl(cfg["hp"], cfg["modpar"])
