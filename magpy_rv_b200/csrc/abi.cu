@@ -142,8 +142,8 @@ struct mrv_problem {
   int panel_inner_opt = 0;  // inner panel width of the two-level scheme, 0 = default (8)
   int cs_store = 1;    // streaming stores for updated C tiles
   int substreams_opt = 0;  // 0 = auto (two half-waves on two streams up to 32 tile columns), 1 = one stream
-  cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging
   DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter, midws;
@@ -274,9 +274,11 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
   for (DevBuf* b : bufs) b->release();
   p->prof.destroy();
   if (p->stream) cudaStreamDestroy(p->stream);
-  if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
+  for (int i = 0; i < 3; ++i) {
+    if (p->aux_stream[i]) cudaStreamDestroy(p->aux_stream[i]);
+    if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+  }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-  if (p->ev_join) cudaEventDestroy(p->ev_join);
   delete p;
 }
 
@@ -569,26 +571,37 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   // Mid sizes: a wave is cut into two halves on two streams, so the latency-bound
   // diagonal-tile kernels and the small launches near the end of every tile column of one half overlap
   // with the GEMMs of the other (per-walker results do not depend on the split: nothing is shared).
-  // measured (tools/substream_probe.py, medians of interleaved runs): +2..12 % for N = 640..4096, -1..+3 % at
-  // 8192, no change at 16384 (left on one stream there: the trailing GEMM's band rasterisation owns the L2)
-  int nsub = p->substreams_opt > 0 ? p->substreams_opt : ((nt <= 64 && B >= 16) ? 2 : 1);
-  nsub = std::min(nsub, 2);
+  // measured (tools/substream_probe.py, medians of interleaved runs): two half-waves give +6..12 % up to
+  // 8 tile columns and +3..9 % for waves of <= 64 walkers up to N = 8192; with 128 walkers at N = 2048 / 4096 the
+  // difference is inside the +-3 % run-to-run noise, and three or four streams never add anything (and
+  // occasionally lose 10..40 %), so the automatic choice is two streams exactly where they were a robust win
+  int nsub = p->substreams_opt > 0 ? p->substreams_opt : (((nt <= 8 && B >= 16) || (nt <= 64 && B >= 16 && B <= 64)) ? 2 : 1);
+  nsub = std::max(1, std::min(nsub, 4));
   if (p->gemm_impl == 1) nsub = 1;   // the persistent GEMM variant shares one tile counter
-  if (nsub == 2 && (!p->aux_stream || !p->ev_fork || !p->ev_join)) {
-    if (!p->aux_stream) CU(cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking));
+  if (nsub > 1) {
     if (!p->ev_fork) CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
-    if (!p->ev_join) CU(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    for (int i = 0; i < nsub - 1; ++i) {
+      if (!p->aux_stream[i]) CU(cudaStreamCreateWithFlags(&p->aux_stream[i], cudaStreamNonBlocking));
+      if (!p->ev_join[i]) CU(cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming));
+    }
   }
   for (int64_t w0 = 0; w0 < W; w0 += B) {
     const int64_t Bw = std::min<int64_t>(B, W - w0);
-    if (nsub == 2 && Bw >= 2) {
-      const int64_t h = (Bw + 1) / 2;
+    const int parts = (int)std::min<int64_t>(nsub, Bw);
+    if (parts > 1) {
       CU(cudaEventRecord(p->ev_fork, st));
-      CU(cudaStreamWaitEvent(p->aux_stream, p->ev_fork, 0));
-      if ((rc = run_wave(p, d_hp, w0, h, st, so, 0))) return rc;
-      if ((rc = run_wave(p, d_hp, w0 + h, Bw - h, p->aux_stream, so, h))) return rc;
-      CU(cudaEventRecord(p->ev_join, p->aux_stream));
-      CU(cudaStreamWaitEvent(st, p->ev_join, 0));
+      int64_t off = 0;
+      for (int i = 0; i < parts; ++i) {
+        const int64_t n = Bw / parts + (i < Bw % parts ? 1 : 0);
+        cudaStream_t si = i == 0 ? st : p->aux_stream[i - 1];
+        if (i > 0) CU(cudaStreamWaitEvent(si, p->ev_fork, 0));
+        if ((rc = run_wave(p, d_hp, w0 + off, n, si, so, off))) return rc;
+        if (i > 0) {
+          CU(cudaEventRecord(p->ev_join[i - 1], si));
+          CU(cudaStreamWaitEvent(st, p->ev_join[i - 1], 0));
+        }
+        off += n;
+      }
     } else if ((rc = run_wave(p, d_hp, w0, Bw, st, so))) {
       return rc;
     }

@@ -12,15 +12,15 @@ for N, W in sizes:
         prob.logl(cfg["hp"], cfg["modpar"])
     res = {}
     for rnd in range(3):                      # interleave the modes so drifts hit all of them alike
-        for sub in (1, 2):
+        for sub in (1, 2, 3, 4):
             prob.set_option("substreams", sub)
             prob.logl(cfg["hp"], cfg["modpar"])
             for _ in range(3):
                 torch.cuda.synchronize(); t0 = time.perf_counter()
                 prob.logl(cfg["hp"], cfg["modpar"])
                 res.setdefault(sub, []).append(time.perf_counter() - t0)
-    m1, m2 = np.median(res[1]), np.median(res[2])
-    print("N=%d W=%d wave=%d: one stream %.2f ms (%.2f TF/s), two half-waves %.2f ms (%.2f TF/s)  -> %+.1f %%"
-          % (N, W, prob.info("wave_walkers"), m1 * 1e3, workloads.flops_per_eval(N) * W / m1 / 1e12, m2 * 1e3,
-             workloads.flops_per_eval(N) * W / m2 / 1e12, 100 * (m1 / m2 - 1)), flush=True)
+    med = {k: np.median(v) for k, v in res.items()}
+    print("N=%d W=%d wave=%d: " % (N, W, prob.info("wave_walkers")) + "  ".join(
+        "%d stream(s) %.2f ms %.2f TF/s (%+.1f %%)" % (k, med[k] * 1e3, workloads.flops_per_eval(N) * W / med[k] / 1e12,
+                                                       100 * (med[1] / med[k] - 1)) for k in sorted(med)), flush=True)
     prob.close()
