@@ -141,6 +141,7 @@ struct mrv_problem {
   int band_opt = 0;    // UPDATE rasterisation band (tile rows), 0 = default
   int panel_inner_opt = 0;  // inner panel width of the two-level scheme, 0 = default (8)
   int cs_store = 1;    // streaming stores for updated C tiles
+  size_t budget_bytes = 0;  // wave workspace budget, sampled at the first blocked-path call
   int substreams_opt = 0;  // 0 = auto (two half-waves on two streams up to 32 tile columns), 1 = one stream
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
@@ -314,14 +315,20 @@ static int effective_panel(const mrv_problem* p) {
 // reductions per walker, so fewer points per thread shortens every link
 static unsigned mean_threads(int N) { return N > 256 ? 512u : 256u; }
 
-static int choose_path(const mrv_problem* p) {
+static int choose_path(const mrv_problem* p, int64_t W = 0) {
   if (p->path_opt == MRV_PATH_FUSED_SMEM) return MRV_PATH_FUSED_SMEM;
   if (p->path_opt == MRV_PATH_BLOCKED) return MRV_PATH_BLOCKED;
   if (p->path_opt == MRV_PATH_MID) return MRV_PATH_MID;
   // measured crossovers (profiles/README.md): fused shared-memory kernels up to 144 points, the
   // one-CTA-per-walker streamed-panel kernel up to 512, the tiled wave factorisation above
   if (p->desc.N <= MRV_SMALL_BLK_N_MAX) return MRV_PATH_FUSED_SMEM;
-  return p->desc.N <= MID_N_MAX ? MRV_PATH_MID : MRV_PATH_BLOCKED;
+  if (p->desc.N > MID_N_MAX) return MRV_PATH_BLOCKED;
+  // 320 < N <= 512: the tiled path wins when N nearly fills its 128-wide tiles (padding < 32 points) AND the
+  // ensemble needs more than one round of one-CTA-per-walker (measured, one B200: N = 384 x 512 walkers
+  // 338 k vs 315 k evals/s, 512 x 512 199 k vs 175 k; but 448 x 512 198 k vs 242 k, 512 x 148 170 k vs 181 k)
+  const int pad128 = p->n_pad - p->desc.N;
+  if (p->desc.N > 320 && pad128 < 32 && W > p->num_sms) return MRV_PATH_BLOCKED;
+  return MRV_PATH_MID;
 }
 
 // Blocked path for one wave of `B` walkers starting at walker w0.
@@ -458,7 +465,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   CU(cudaSetDevice(p->device));
   if (int rc = set_attrs(p)) return rc;
   const ProblemDesc& D = p->desc;
-  const int path = choose_path(p);
+  const int path = choose_path(p, W);
   p->last_path = path;
   if (path == MRV_PATH_FUSED_SMEM) {
     if (D.N > SMALL_N_MAX) return fail(-1, "fused shared-memory path needs N <= %d (N=%d)", SMALL_N_MAX, D.N);
@@ -532,11 +539,15 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   const size_t walker_bytes = (tile_index(nt - 1, nt - 1) + 1) * TILE_ELEMS * sizeof(double);
   int64_t B = p->wave_opt;
   if (B <= 0) {
-    size_t free_b = 0, total_b = 0;
-    CU(cudaMemGetInfo(&free_b, &total_b));
-    free_b += p->factor.bytes;  // what we already hold can be reused
-    size_t budget = std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)40 << 30);
-    B = (int64_t)std::max<size_t>(1, budget / walker_bytes);
+    // the memory budget is sampled once per handle (cudaMemGetInfo costs milliseconds right after another
+    // handle released its workspace, and the answer only matters for the first allocation)
+    if (p->budget_bytes == 0) {
+      size_t free_b = 0, total_b = 0;
+      CU(cudaMemGetInfo(&free_b, &total_b));
+      free_b += p->factor.bytes;  // what we already hold can be reused
+      p->budget_bytes = std::max<size_t>(1, std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)40 << 30));
+    }
+    B = (int64_t)std::max<size_t>(1, p->budget_bytes / walker_bytes);
   }
   B = std::min<int64_t>(B, W);
   B = std::min<int64_t>(B, 65535);
