@@ -10,7 +10,7 @@
 //      FP64-ALU-bound one;
 //   2. acc += L(rows, 0:32 j) * L(block-j rows, 0:32 j)^T on the FP64 tensor pipe: the already
 //      factored block columns stream back from a per-CTA workspace that stays L2-resident
-//      (<= 1.1 MB per CTA slot), k8 slices of ALL panel rows as two 1-D bulk copies (TMA engine)
+//      (<= 1.1 MB per CTA slot), k16 slices of ALL panel rows as four 1-D bulk copies (TMA engine)
 //      into an mbarrier ring -- no CTA-wide barrier in the loop.  The factor warp is the producer: it
 //      runs as far ahead as the ring allows, so consumers wait for data only, never for each other
 //      (with a consumer-side producer the loop spent half its time in empty-barrier waits).  The B operand (the 32 rows of
@@ -36,7 +36,9 @@
 #include "mean_model.cuh"
 
 #define MID_NB 32
-#define MID_STAGES 6      // ring stages for R > 256 (one fewer below, so two CTAs fit an SM); look-ahead = stages - 2
+#define MID_STAGES 5      // most ring stages of any variant (sizes the mbarrier arrays)
+// R > 256 (15 tensor warps): 3 stages of k16 slices (four 1-D bulk copies each); R <= 256 (7 tensor warps, two
+// CTAs per SM): 5 stages of k8 slices -- measured: k16 is +2..9 % at N = 300..512, k8 +5 % at N = 256
 #define MID_N_MAX 512
 #define MID_INV_LD 36     // == 4 (mod 16): conflict-free B-fragment loads of inv(L)
 
@@ -50,10 +52,11 @@ __host__ inline size_t mid_ws_doubles(int N) {
   return mid_colblk_base(R, R / MID_NB);
 }
 __host__ inline int mid_warps(int N) { return mid_npad(N) <= 256 ? 7 : 15; }   // tensor warps (+ 1 factor warp)
-__host__ __device__ inline int mid_stages(int R) { return R <= 256 ? MID_STAGES - 1 : MID_STAGES; }
-// ring (k8 slices of at most R - 32 rows) and panel (8 chunks of 4 R + 8 doubles) share one region
+__host__ __device__ inline int mid_stages(int R) { return R <= 256 ? 5 : 3; }
+__host__ __device__ inline int mid_ks(int R) { return R <= 256 ? 8 : 16; }
+// ring (k16 slices of at most R - 32 rows) and panel (8 chunks of 4 R + 8 doubles) share one region
 __host__ __device__ inline size_t mid_buf_doubles(int R) {
-  const size_t ring = (size_t)mid_stages(R) * 8 * (R > 32 ? R - 32 : 32);
+  const size_t ring = (size_t)mid_stages(R) * mid_ks(R) * (R > 32 ? R - 32 : 32);
   const size_t panel = (size_t)8 * (4 * R + 8);
   return ring > panel ? ring : panel;
 }
@@ -88,6 +91,7 @@ struct MidShared {
   unsigned long long *full_bar, *empty_bar;
   int stage_stride;
   unsigned nst;
+  int ch;                                   // k4 chunks per slice (2: k8 slices, 4: k16 slices)
 };
 
 // Factor the 16 x 16 diagonal sub-block at offset o of the panel: lane = row (rr) x column group (g)
@@ -206,9 +210,9 @@ __device__ __noinline__ void mid_factor_role(MidShared sh, int R, int nblk, unsi
   int fb = 0x7fffffff, fb_nan = 0;
   unsigned qg = *qg_io;
   for (int j = 0; j < nblk; ++j) {
-    const int row0 = MID_NB * j, M = R - row0, CS = 4 * M + 8, nsl = 4 * j;
+    const int row0 = MID_NB * j, M = R - row0, CS = 4 * M + 8, spb = 8 / sh.ch, nsl = spb * j;   // spb slices per block column
     // Producer of the operand stream while the tensor warps run the update loop of this step: slice q =
-    // k8 columns [8 (q&3), +8) of block column q >> 2, rows [row0, R), two 1-D bulk copies into ring
+    // 4 ch columns of a block column (k8 or k16), rows [row0, R), one 1-D bulk copy per k4 chunk into ring
     // stage (qg + q) % nst.  A dedicated producer runs as far ahead as the ring allows (all stages in
     // flight), so the consumers only ever wait for data, never for each other.
     if (lane == 0) {
@@ -216,12 +220,11 @@ __device__ __noinline__ void mid_factor_role(MidShared sh, int R, int nblk, unsi
       for (int q = 0; q < nsl; ++q) {
         const unsigned qglob = qg + (unsigned)q, st = qglob % sh.nst, u = qglob / sh.nst;
         if (u > 0) mbar_wait(&sh.empty_bar[st], (u - 1) & 1u);
-        const int p = q >> 2, c0 = 2 * (q & 3), Rp = R - MID_NB * p;
+        const int p = q / spb, c0 = sh.ch * (q % spb), Rp = R - MID_NB * p;
         const double* src = sh.ws + mid_colblk_base(R, p) + (size_t)c0 * Rp * 4 + (size_t)(row0 - MID_NB * p) * 4;
         double* dst = sh.buf + (size_t)st * sh.stage_stride;
-        mbar_expect_tx(&sh.full_bar[st], 2u * chunk_bytes);
-        bulk_g2s(dst, src, chunk_bytes, &sh.full_bar[st]);
-        bulk_g2s(dst + (size_t)M * 4, src + (size_t)Rp * 4, chunk_bytes, &sh.full_bar[st]);
+        mbar_expect_tx(&sh.full_bar[st], (unsigned)sh.ch * chunk_bytes);
+        for (int h = 0; h < sh.ch; ++h) bulk_g2s(dst + (size_t)h * M * 4, src + (size_t)h * Rp * 4, chunk_bytes, &sh.full_bar[st]);
       }
     }
     qg += (unsigned)nsl;
@@ -285,7 +288,8 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tig = lane & 3;
   const bool is_fw = warp == FW;
-  const int stage_stride = (R > 32 ? R - 32 : 32) * 8;   // doubles per ring stage
+  constexpr int KS = NWM == 7 ? 8 : 16, CH = KS / 4;        // columns / k4 chunks per slice
+  const int stage_stride = (R > 32 ? R - 32 : 32) * KS;   // doubles per ring stage
   const unsigned NST = (unsigned)mid_stages(R);
   double* ws = workspace + (size_t)blockIdx.x * ws_stride;
 
@@ -368,11 +372,11 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
 #endif
 
     if (is_fw) {
-      MidShared sh{buf, r, dvec, zvec, rpart, invL, rj, rdiag, rhsb, Dm, ws, full_bar, empty_bar, stage_stride, NST};
+      MidShared sh{buf, r, dvec, zvec, rpart, invL, rj, rdiag, rhsb, Dm, ws, full_bar, empty_bar, stage_stride, NST, CH};
       mid_factor_role<NWM>(sh, R, nblk, &qg, &fb, &fb_nan);
     } else
     for (int j = 0; j < nblk; ++j) {
-      const int row0 = MID_NB * j, M = R - row0, F = M >> 4, nsl = 4 * j;
+      const int row0 = MID_NB * j, M = R - row0, F = M >> 4, nsl = (MID_NB / KS) * j;
       const int CS = 4 * M + 8;   // panel chunk stride (doubles): +8 keeps the fragment stores conflict-free
       const bool more = j + 1 < nblk;
       double* P = buf;
@@ -428,7 +432,7 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
           MID_TICK(14);
           const double* Sl = buf + (size_t)st * stage_stride;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < CH; ++h) {
             const double* base = Sl + (size_t)h * M * 4;
             double b[4];
 #pragma unroll
@@ -443,10 +447,10 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
               }
             }
           }
-          if ((q % NWM) == warp) {   // r_j[lane] -= sum_k L[row0 + lane][k] z[k] over this slice's 8 columns
-            const int kbase = MID_NB * (q >> 2) + 8 * (q & 3);
+          if ((q % NWM) == warp) {   // r_j[lane] -= sum_k L[row0 + lane][k] z[k] over this slice's columns
+            const int kbase = KS * q;   // slices walk the columns 0 .. 32 j in order
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < CH; ++h)
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
                 racc = fma(Sl[(size_t)h * M * 4 + lane * 4 + kk], zvec[kbase + 4 * h + kk], racc);
