@@ -582,11 +582,11 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   // Mid sizes: a wave is cut into two halves on two streams, so the latency-bound
   // diagonal-tile kernels and the small launches near the end of every tile column of one half overlap
   // with the GEMMs of the other (per-walker results do not depend on the split: nothing is shared).
-  // measured (tools/substream_probe.py, medians of interleaved runs): two half-waves give +6..12 % up to
-  // 8 tile columns and +3..9 % for waves of <= 64 walkers up to N = 8192; with 128 walkers at N = 2048 / 4096 the
-  // difference is inside the +-3 % run-to-run noise, and three or four streams never add anything (and
+  // measured (tools/substream_probe.py, medians of interleaved runs): two half-waves give +5..12 % up to
+  // 16 tile columns and +3..9 % for waves of <= 64 walkers up to N = 8192; with 128 walkers at N = 4096 the
+  // difference is inside the +-2 % run-to-run noise, and three or four streams never add anything (and
   // occasionally lose 10..40 %), so the automatic choice is two streams exactly where they were a robust win
-  int nsub = p->substreams_opt > 0 ? p->substreams_opt : (((nt <= 8 && B >= 16) || (nt <= 64 && B >= 16 && B <= 64)) ? 2 : 1);
+  int nsub = p->substreams_opt > 0 ? p->substreams_opt : (((nt <= 16 && B >= 16) || (nt <= 64 && B >= 16 && B <= 64)) ? 2 : 1);
   nsub = std::max(1, std::min(nsub, 4));
   if (p->gemm_impl == 1) nsub = 1;   // the persistent GEMM variant shares one tile counter
   if (nsub > 1) {

@@ -97,6 +97,29 @@ __device__ __noinline__ void gen_fragment4(const CovParams& cp, int N, int gi0, 
   }
 }
 
+// Two adjacent accumulator fragments (columns gj0, gj0+1 and gj0+8, gj0+9; rows gi0, gi0+8) in one call:
+// 8 independent exp / sin chains in flight per lane.  The GEMM runs 8 warps per SM, where 4 chains per
+// lane left the FP64 pipe waiting on its own latency during the first-touch generation.
+__device__ __noinline__ void gen_fragment8(const CovParams& cp, int N, int gi0, int gj0, double ti0, double ti1,
+                                           double tj0, double tj1, double tj8, double tj9,
+                                           const double* __restrict__ yerr, double (&out)[8]) {
+  const double tjs[4] = {tj0, tj1, tj8, tj9};
+  double d[8], d2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const double dt = (((e >> 1) & 1) ? ti1 : ti0) - tjs[2 * (e >> 2) + (e & 1)];
+    d[e] = fabs(dt);
+    d2[e] = dt * dt;
+  }
+  cov_from_dist_n<8>(cp, d, d2, out);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int gi = gi0 + 8 * ((e >> 1) & 1), gj = gj0 + 8 * (e >> 2) + (e & 1);
+    if (gi >= N || gj >= N) out[e] = (gi == gj) ? 1.0 : 0.0;
+    else if (gi == gj) out[e] = cov_diag(cp, yerr[gi]);
+  }
+}
+
 // Write the covariance tiles of tile-column `col` for every walker of the wave (needed before
 // potrf/trsm touch a column that no UPDATE has generated yet, i.e. column 0).
 __global__ void __launch_bounds__(256)
@@ -710,14 +733,18 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-      for (int ni = 0; ni < 4; ++ni)
+      for (int np2 = 0; np2 < 2; ++np2)
         {
           const int R = wm * 64 + mi * 16 + gq;
-          const int C = wn * 32 + ni * 8 + 2 * tig;
-          double frag[4];
-          gen_fragment4(cp, g.N, ti * TILE + R, tj * TILE + C, tis[R], tis[R + 8], tjs[C], tjs[C + 1], g.yerr, frag);
+          const int C = wn * 32 + np2 * 16 + 2 * tig;
+          double frag[8];
+          gen_fragment8(cp, g.N, ti * TILE + R, tj * TILE + C, tis[R], tis[R + 8], tjs[C], tjs[C + 1], tjs[C + 8],
+                        tjs[C + 9], g.yerr, frag);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) acc[mi][ni][v] = -frag[v];
+          for (int v = 0; v < 4; ++v) {
+            acc[mi][2 * np2][v] = -frag[v];
+            acc[mi][2 * np2 + 1][v] = -frag[4 + v];
+          }
         }
   } else {
 #pragma unroll
