@@ -141,6 +141,9 @@ struct mrv_problem {
   int band_opt = 0;    // UPDATE rasterisation band (tile rows), 0 = default
   int panel_inner_opt = 0;  // inner panel width of the two-level scheme, 0 = default (8)
   int cs_store = 1;    // streaming stores for updated C tiles
+  int lookahead_opt = 1;    // diagonal-first look-ahead inside a panel (auxiliary stream per sub-wave)
+  cudaStream_t la_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t la_evT[4] = {nullptr, nullptr, nullptr, nullptr}, la_evO[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t budget_bytes = 0;  // wave workspace budget, sampled at the first blocked-path call
   int substreams_opt = 0;  // 0 = auto (two half-waves on two streams up to 32 tile columns), 1 = one stream
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
@@ -279,6 +282,11 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
     if (p->aux_stream[i]) cudaStreamDestroy(p->aux_stream[i]);
     if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
   }
+  for (int i = 0; i < 4; ++i) {
+    if (p->la_stream[i]) cudaStreamDestroy(p->la_stream[i]);
+    if (p->la_evT[i]) cudaEventDestroy(p->la_evT[i]);
+    if (p->la_evO[i]) cudaEventDestroy(p->la_evO[i]);
+  }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   delete p;
 }
@@ -334,7 +342,7 @@ static int choose_path(const mrv_problem* p, int64_t W = 0) {
 // Blocked path for one wave of `B` walkers starting at walker w0.
 // `slot0`: first walker slot of this (sub-)wave inside the factor / z workspaces of the current wave.
 static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so,
-                    int64_t slot0 = 0) {
+                    int64_t slot0 = 0, int sub = 0) {
   const ProblemDesc& D = p->desc;
   const int nt = p->nt, N = D.N;
   const size_t walker_stride = tile_index(nt - 1, nt - 1) * TILE_ELEMS + TILE_ELEMS;
@@ -374,7 +382,20 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
     return (unsigned)n;
   };
 
-  auto launch_gemm = [&](dim3 grid) {
+  // Diagonal-first look-ahead inside a panel: the diagonal tile of column k is updated first and factored on the
+  // main stream while the off-diagonal tiles of the column are updated on an auxiliary stream, so the
+  // latency-bound diagonal-tile kernel (one CTA per walker, ~60 us) leaves the critical path.
+  // measured on top of the two half-waves (tools/substream_probe.py): +5 % at N = 1024 x 128 walkers, +0..1 % for
+  // other small waves, -2 % at 640 x 512 -- so only (sub-)waves of at most 64 walkers use it (option 2 forces it)
+  const bool la = p->gemm_impl == 0 && nt <= 64 && (p->lookahead_opt == 2 || (p->lookahead_opt == 1 && B <= 64));
+  cudaStream_t aux = nullptr;
+  if (la) {
+    if (!p->la_stream[sub]) CU(cudaStreamCreateWithFlags(&p->la_stream[sub], cudaStreamNonBlocking));
+    if (!p->la_evT[sub]) CU(cudaEventCreateWithFlags(&p->la_evT[sub], cudaEventDisableTiming));
+    if (!p->la_evO[sub]) CU(cudaEventCreateWithFlags(&p->la_evO[sub], cudaEventDisableTiming));
+    aux = p->la_stream[sub];
+  }
+  auto launch_gemm = [&](dim3 grid, cudaStream_t st) {
     if (p->gemm_impl == 1) {
       const long long total = (long long)grid.x * grid.y;
       const unsigned ctas = (unsigned)std::min<long long>(total, p->num_sms);
@@ -403,19 +424,30 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
                                                             hp_wave, A, walker_stride);
   p->prof.end(st);
   p->launches++;
-  auto launch_update = [&](int cat, int c0, int c1, int pb, int pe) {
+  // part: 0 = every target tile of the columns, 1 = only the diagonal tile of column c0, 2 = column c0 without it
+  auto launch_update = [&](int cat, int c0, int c1, int pb, int pe, cudaStream_t s, int part = 0) {
     g.mode = GEMM_UPDATE;
     g.col_begin = c0;
     g.col_end = c1;
     g.p_begin = pb;
     g.p_end = pe;
     g.gen = (pb == 0);   // the operand range starts at column 0 <=> this is the first touch of the targets
+    g.x_off = part == 2 ? 1 : 0;
     double ex = 0.0;
-    const double al = update_flops(c0, c1, pe - pb, &ex);
-    p->prof.begin(cat, st, al, ex);
-    launch_gemm(dim3(tiles_in_cols(c0, c1), (unsigned)B));
-    p->prof.end(st);
+    double al = update_flops(c0, c1, pe - pb, &ex);
+    unsigned tiles = tiles_in_cols(c0, c1);
+    if (part != 0) {
+      const double np_ = (double)(pe - pb), diag_al = (double)TILE * (TILE + 1) * TILE * np_ * (double)B,
+                   diag_ex = 2.0 * T3 * np_ * (double)B;
+      al = part == 1 ? diag_al : al - diag_al;
+      ex = part == 1 ? diag_ex : ex - diag_ex;
+      tiles = part == 1 ? 1u : tiles - 1u;
+    }
+    p->prof.begin(cat, s, al, ex);
+    launch_gemm(dim3(tiles, (unsigned)B), s);
+    p->prof.end(s);
     p->launches++;
+    g.x_off = 0;
   };
   // Two-level panels: outer panels of PW tile columns get one big trailing update (K = 128 PW);
   // inside an outer panel, inner panels of PWI columns are factored column by column (short-K
@@ -429,7 +461,15 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
     for (int p0 = P0; p0 < P1; p0 += PWI) {
       const int p1 = std::min(p0 + PWI, P1);
       for (int k = p0; k < p1; ++k) {
-        if (k > p0) launch_update(CAT_UPDATE_PANEL, k, k + 1, p0, k);
+        const bool split = la && k > p0 && k + 1 < nt;
+        if (split) {
+          launch_update(CAT_UPDATE_PANEL, k, k + 1, p0, k, st, 1);
+          CU(cudaStreamWaitEvent(aux, p->la_evT[sub], 0));          // recorded after TRSM(k - 1)
+          launch_update(CAT_UPDATE_PANEL, k, k + 1, p0, k, aux, 2);
+          CU(cudaEventRecord(p->la_evO[sub], aux));
+        } else if (k > p0) {
+          launch_update(CAT_UPDATE_PANEL, k, k + 1, p0, k, st);
+        }
         p->prof.begin(CAT_POTRF, st, (T3 / 3.0 + 2.0 * TILE * TILE) * (double)B, 1.5 * T3 * (double)B);
         if (p->potrf_impl == 0)
           potrf_tile_blk_kernel<<<(unsigned)B, POTRF_BLK_THREADS, POTRF_BLK_SMEM_BYTES, st>>>(
@@ -440,18 +480,20 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
         p->prof.end(st);
         p->launches++;
         if (k + 1 < nt) {
+          if (split) CU(cudaStreamWaitEvent(st, p->la_evO[sub], 0));
           g.mode = GEMM_TRSM;
           g.k = k;
           p->prof.begin(CAT_TRSM, st, (T3 + 2.0 * TILE * TILE) * (nt - k - 1) * (double)B,
                         2.0 * T3 * (nt - k - 1) * (double)B);
-          launch_gemm(dim3(nt - k - 1, (unsigned)B));
+          launch_gemm(dim3(nt - k - 1, (unsigned)B), st);
           p->prof.end(st);
           p->launches++;
+          if (la) CU(cudaEventRecord(p->la_evT[sub], st));
         }
       }
-      if (p1 < P1) launch_update(CAT_UPDATE_MID, p1, P1, p0, p1);
+      if (p1 < P1) launch_update(CAT_UPDATE_MID, p1, P1, p0, p1, st);
     }
-    if (P1 < nt) launch_update(CAT_UPDATE_TRAIL, P1, nt, P0, P1);
+    if (P1 < nt) launch_update(CAT_UPDATE_TRAIL, P1, nt, P0, P1, st);
   }
   CU(cudaGetLastError());
   return 0;
@@ -606,7 +648,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
         const int64_t n = Bw / parts + (i < Bw % parts ? 1 : 0);
         cudaStream_t si = i == 0 ? st : p->aux_stream[i - 1];
         if (i > 0) CU(cudaStreamWaitEvent(si, p->ev_fork, 0));
-        if ((rc = run_wave(p, d_hp, w0 + off, n, si, so, off))) return rc;
+        if ((rc = run_wave(p, d_hp, w0 + off, n, si, so, off, i))) return rc;
         if (i > 0) {
           CU(cudaEventRecord(p->ev_join[i - 1], si));
           CU(cudaStreamWaitEvent(st, p->ev_join[i - 1], 0));
@@ -1068,6 +1110,8 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {
     p->cs_store = (int)value;   // bit 0: streaming C stores; bit 1: L2 prefetch of the next C tile (persistent GEMM)
+  } else if (!strcmp(key, "lookahead")) {
+    p->lookahead_opt = (int)value;
   } else if (!strcmp(key, "substreams")) {
     p->substreams_opt = (int)value;
   } else if (!strcmp(key, "potrf_impl")) {

@@ -527,6 +527,7 @@ struct GemmArgs {
   int gen;           // UPDATE: 1 = target tiles are generated from t (first touch) instead of loaded
   int band;          // UPDATE rasterisation band height in tile rows (0 = default)
   int cs_store;      // UPDATE: streaming (evict-first) stores for the C tile
+  int x_off;         // UPDATE: first target-tile index of this launch (diagonal-first split of a column)
   int kernel_id, variant, nh;
   double* Abase;
   size_t walker_stride;
@@ -652,7 +653,7 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
     tj = g.k;
     np = 1;
   } else {
-    decode_update_tile(g, (int)blockIdx.x, ti, tj);
+    decode_update_tile(g, (int)blockIdx.x + g.x_off, ti, tj);
     np = g.p_end - g.p_begin;
   }
   const int nslices = np * SLICES_PER_TILE;

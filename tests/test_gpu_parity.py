@@ -199,6 +199,10 @@ def test_blocked_path_invariances_and_large_n():
         got, _ = prob.logl(cfg["hp"], cfg["modpar"])
         np.testing.assert_array_equal(got, base)
     prob.set_option("substreams", 0)
+    for la in (0, 2, 1):                                  # without / with the diagonal-first look-ahead stream / auto
+        prob.set_option("lookahead", la)
+        got, _ = prob.logl(cfg["hp"], cfg["modpar"])
+        np.testing.assert_array_equal(got, base)
     for panel in (2, 3):
         prob.set_option("panel_tiles", panel)
         got, _ = prob.logl(cfg["hp"], cfg["modpar"])

@@ -12,8 +12,9 @@ for N, W in sizes:
         prob.logl(cfg["hp"], cfg["modpar"])
     res = {}
     for rnd in range(3):                      # interleave the modes so drifts hit all of them alike
-        for sub in (1, 2, 3, 4):
-            prob.set_option("substreams", sub)
+        for sub in (1, 2, 11, 12):                 # 11 / 12: one / two streams with the diagonal-first look-ahead
+            prob.set_option("substreams", sub % 10)
+            prob.set_option("lookahead", 2 * (sub // 10))
             prob.logl(cfg["hp"], cfg["modpar"])
             for _ in range(3):
                 torch.cuda.synchronize(); t0 = time.perf_counter()
