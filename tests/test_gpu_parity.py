@@ -504,3 +504,26 @@ def test_device_resident_sampler_invariants():
                                       cfg["model_list"], cfg["prior_list"], numb_chains=48)
     rate_h = np.any(hp_h[1:] != hp_h[:-1], axis=2).mean()
     assert abs(rate - rate_h) < 0.2, (rate, rate_h)
+
+
+@pytest.mark.parametrize("name", ["C1", "C3"])
+def test_long_chain_digest_matches_reference(name):
+    """Hundreds of iterations (40 100 / 2 440 accept-reject decisions) under the shared seed: the SHA-256 of the
+    position histories must equal the unmodified reference's (tests/golden/chain_long.json, written by
+    oracle/make_long_chain.py) -- a single flipped decision anywhere changes it -- and the last log L row must
+    agree to the tolerance."""
+    import hashlib
+    g = json.load(open(os.path.join(GOLD, "chain_long.json")))[name]
+    cfg = workloads.make_config(name, W=g["W"], N=g["N"])
+    random.seed(g["seed"])
+    np.random.seed(g["seed"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        logL, hp, mp, done = mcmc.run_MCMC(g["iterations"], cfg["t"], cfg["y"], cfg["yerr"], cfg["hparam0"], cfg["kernel"],
+                                           cfg["model_par0"], cfg["model_list"], cfg["prior_list"], numb_chains=g["W"],
+                                           flags=cfg["flags"])
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(hp).tobytes())
+    h.update(np.ascontiguousarray(mp).tobytes())
+    assert int(np.any(hp[1:] != hp[:-1], axis=2).sum()) == g["accepted_steps"]
+    assert h.hexdigest() == g["positions_sha256"], "chain diverged from the reference"
+    assert relerr(logL[-1, :, 0], np.array(g["last_logL"])) < RTOL
