@@ -141,6 +141,8 @@ struct mrv_problem {
   int band_opt = 0;    // UPDATE rasterisation band (tile rows), 0 = default
   int panel_inner_opt = 0;  // inner panel width of the two-level scheme, 0 = default (8)
   int cs_store = 1;    // streaming stores for updated C tiles
+  int small_blk_min = 32;   // below this the rank-1 shared-memory kernel is used (option "small_blk_min"); measured:
+                            // the packed blocked sweep wins from N = 32 up (tools/small_probe.py), equal at 16
   int lookahead_opt = 1;    // diagonal-first look-ahead inside a panel (auxiliary stream per sub-wave)
   cudaStream_t la_stream[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t la_evT[4] = {nullptr, nullptr, nullptr, nullptr}, la_evO[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -511,9 +513,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   p->last_path = path;
   if (path == MRV_PATH_FUSED_SMEM) {
     if (D.N > SMALL_N_MAX) return fail(-1, "fused shared-memory path needs N <= %d (N=%d)", SMALL_N_MAX, D.N);
-    // measured crossover (profiles/README.md): below ~80 points the rank-1 kernel's smaller footprint
-    // (several CTAs per SM) wins over the blocked DMMA sweep
-    const bool blk = p->potrf_impl == 0 && D.N >= 80 && D.N <= MRV_SMALL_BLK_N_MAX;
+    const bool blk = p->potrf_impl == 0 && D.N >= p->small_blk_min && D.N <= MRV_SMALL_BLK_N_MAX;
     const size_t smem = blk ? small_blk_smem_bytes(D.N) : small_smem_bytes(D.N);
     const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)W;
     p->prof.begin(CAT_FUSED, st, fl, fl);
@@ -1110,6 +1110,8 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {
     p->cs_store = (int)value;   // bit 0: streaming C stores; bit 1: L2 prefetch of the next C tile (persistent GEMM)
+  } else if (!strcmp(key, "small_blk_min")) {
+    p->small_blk_min = (int)value;
   } else if (!strcmp(key, "lookahead")) {
     p->lookahead_opt = (int)value;
   } else if (!strcmp(key, "substreams")) {

@@ -293,7 +293,23 @@ __device__ __forceinline__ void dmma_1684_neg0(double (&d)[4], double a0, double
 // pa_ld, pb_ld == 4 (mod 16).  With WITH_INV the
 // strict upper triangle receives the unscaled inverse factor (see potrf_tile_kernel above);
 // without it only factor rows and the residual row are carried (fused small-N kernel).
-template <bool WITH_INV, int NWARPS>
+// Column base pointer of the swept matrix.  PACKED (fused small-N kernel, factor rows only): the 16-column
+// block b keeps rows >= 16 b only, with leading dimension ld - 16 b, blocks stored back to back -- half the
+// shared memory of the square layout, so two walkers' CTAs fit an SM up to N = 112.  The returned pointer is
+// pre-offset so that colp[row] is valid for every stored row (row >= 16 b).  ld == 8 (mod 16) holds for
+// every block, which is what the conflict-free 16-byte accumulator accesses need.
+template <bool PACKED>
+__device__ __forceinline__ double* sweep_colp(double* S, int ld, int c) {
+  if (!PACKED) return S + (size_t)c * ld;
+  const int b = c >> 4;
+  return S + (16 * b * ld - 128 * b * (b - 1)) + (c & 15) * (ld - 16 * b) - 16 * b;
+}
+__host__ __device__ inline size_t sweep_packed_doubles(int ld, int n_cols) {
+  const int nb = n_cols / 16;
+  return (size_t)16 * nb * ld - (size_t)128 * nb * (nb - 1);
+}
+
+template <bool WITH_INV, int NWARPS, bool PACKED = false>
 __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, double* PA, const int pa_ld, double* PB,
                                        const int pb_ld, double* D, double* wv) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -309,7 +325,7 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
       const int r = (tid >> 4) & 15, c = tid & 15;
       double v = 0.0;
       if (in_blk) {
-        v = S[(k0 + r) + (size_t)(k0 + c) * ld];
+        v = sweep_colp<PACKED>(S, ld, k0 + c)[k0 + r];
         D[r * PB_D_LD + c] = v;
       }
       __syncthreads();
@@ -325,7 +341,7 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
       }
       if (in_blk) {
         if (r == c) wv[r] = 1.0 / v;
-        S[(k0 + r) + (size_t)(k0 + c) * ld] = v;     // final block (lower: factor, upper: inverse part)
+        sweep_colp<PACKED>(S, ld, k0 + c)[k0 + r] = v;     // final block (lower: factor, upper: inverse part)
       }
       __syncthreads();
       // multipliers beta[j][jp] = D[j][jp] / d_jp (j > jp), in place, for the row recurrences below
@@ -340,7 +356,7 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
       double x[PB_NB];
       if (active) {
 #pragma unroll
-        for (int j = 0; j < PB_NB; ++j) x[j] = S[rho + (size_t)(k0 + j) * ld];
+        for (int j = 0; j < PB_NB; ++j) x[j] = sweep_colp<PACKED>(S, ld, k0 + j)[rho];
         // right-looking order: the inner updates are independent (ILP), only x[jp] is on the chain
 #pragma unroll
         for (int jp = 0; jp < PB_NB - 1; ++jp) {
@@ -348,7 +364,7 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
           for (int j = jp + 1; j < PB_NB; ++j) x[j] = fma(-x[jp], D[j * PB_D_LD + jp], x[j]);
         }
 #pragma unroll
-        for (int j = 0; j < PB_NB; ++j) S[rho + (size_t)(k0 + j) * ld] = x[j];
+        for (int j = 0; j < PB_NB; ++j) sweep_colp<PACKED>(S, ld, k0 + j)[rho] = x[j];
       } else if (pivot_row) {
         const int r = rho - k0;
 #pragma unroll
@@ -399,8 +415,8 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
         // needed if the rows are inverse/pivot rows (rho < c_begin) or contain factor rows (rho >= c)
         need[sl] = live[sl] && (rho0s[sl] < c_begin || rho0s[sl] + 7 >= c0);
         if (need[sl] && !pivot[sl]) {
-          const double2 u = *reinterpret_cast<const double2*>(S + (rho0s[sl] + 2 * tig) + (size_t)(c0 + gq) * ld);
-          const double2 v = *reinterpret_cast<const double2*>(S + (rho0s[sl] + 2 * tig) + (size_t)(c0 + gq + 8) * ld);
+          const double2 u = *reinterpret_cast<const double2*>(sweep_colp<PACKED>(S, ld, c0 + gq) + (rho0s[sl] + 2 * tig));
+          const double2 v = *reinterpret_cast<const double2*>(sweep_colp<PACKED>(S, ld, c0 + gq + 8) + (rho0s[sl] + 2 * tig));
           acc[sl][0] = u.x; acc[sl][1] = u.y; acc[sl][2] = v.x; acc[sl][3] = v.y;
         } else {
           acc[sl][0] = acc[sl][1] = acc[sl][2] = acc[sl][3] = 0.0;
@@ -416,8 +432,8 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
         if (need[sl]) {
           double2 u, v;
           u.x = acc[sl][0]; u.y = acc[sl][1]; v.x = acc[sl][2]; v.y = acc[sl][3];
-          *reinterpret_cast<double2*>(S + (rho0s[sl] + 2 * tig) + (size_t)(c0 + gq) * ld) = u;
-          *reinterpret_cast<double2*>(S + (rho0s[sl] + 2 * tig) + (size_t)(c0 + gq + 8) * ld) = v;
+          *reinterpret_cast<double2*>(sweep_colp<PACKED>(S, ld, c0 + gq) + (rho0s[sl] + 2 * tig)) = u;
+          *reinterpret_cast<double2*>(sweep_colp<PACKED>(S, ld, c0 + gq + 8) + (rho0s[sl] + 2 * tig)) = v;
         }
       }
     }

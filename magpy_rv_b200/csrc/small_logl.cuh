@@ -136,11 +136,12 @@ __host__ __device__ inline int sblk_ld(int N) {
 }
 __host__ inline size_t small_blk_smem_bytes(int N) {
   const int nc = sblk_cols(N), ld = sblk_ld(N);
-  return ((size_t)ld * nc + PB_NB * (size_t)(ld + 12) + PB_NB * (size_t)(nc + 4) + PB_NB * PB_D_LD + PB_NB + 2 * (size_t)N +
+  return (sweep_packed_doubles(ld, nc) + PB_NB * (size_t)(ld + 12) + PB_NB * (size_t)(nc + 4) + PB_NB * PB_D_LD + PB_NB + 2 * (size_t)N +
           MRV_MAX_MODPAR + MRV_MAX_HP + 40) * sizeof(double);
 }
 
-__global__ void __launch_bounds__(MRV_SMALL_THREADS)
+// (packed factor storage + a 128-register cap: two walkers' CTAs per SM up to N = 112, three up to N = 80)
+__global__ void __launch_bounds__(MRV_SMALL_THREADS, 2)
 fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double* __restrict__ y,
                        const double* __restrict__ yerr, const double* __restrict__ flags,
                        const double* __restrict__ hp_all, const double* __restrict__ modpar_all,
@@ -148,8 +149,8 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
                        int* __restrict__ status_out, SolveOut so) {
   extern __shared__ double smem[];
   const int N = D.N, nc = sblk_cols(N), ld = sblk_ld(N), pa_ld = ld + 12, pb_ld = nc + 4;
-  double* S = smem;                          // ld x nc column major; row nc = residual row
-  double* PA = S + (size_t)ld * nc;
+  double* S = smem;                          // packed column blocks (sweep_colp<true>); row nc = residual row
+  double* PA = S + sweep_packed_doubles(ld, nc);
   double* PBm = PA + PB_NB * pa_ld;
   double* Dblk = PBm + PB_NB * pb_ld;
   double* wv = Dblk + PB_NB * PB_D_LD;
@@ -186,8 +187,8 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
 
   // (a) everything that is not a real lower-triangle entry: zeros, identity padding, residual row
   for (int c = warp; c < nc; c += nwarps) {
-    double* col = S + (size_t)c * ld;
-    for (int i = lane; i < ld; i += 32) {
+    double* col = sweep_colp<true>(S, ld, c);
+    for (int i = (c & ~15) + lane; i < ld; i += 32) {   // rows above the column's 16-block are not stored
       if (i < N && c < N && i >= c) continue;   // written by (b)
       double v = 0.0;
       if (i == c) v = 1.0;                      // identity padding (c >= N)
@@ -218,21 +219,21 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
       const double e0 = (i0 == c0) ? cov_diag(cp, yerr[i0]) : ev[0];
       const double e1 = (i1 == c1) ? cov_diag(cp, yerr[i1]) : ev[1];
       bad |= !isfinite(e0);
-      S[(size_t)c0 * ld + i0] = e0;
+      sweep_colp<true>(S, ld, c0)[i0] = e0;
       if (ok1) {
         bad |= !isfinite(e1);
-        S[(size_t)c1 * ld + i1] = e1;
+        sweep_colp<true>(S, ld, c1)[i1] = e1;
       }
     }
   }
   __syncthreads();
-  cta_block_sweep<false, MRV_SMALL_THREADS / 32>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
+  cta_block_sweep<false, MRV_SMALL_THREADS / 32, true>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
 
   double ld_part = 0.0, q_part = 0.0;
   int first_bad = 0x7fffffff;
   for (int j = tid; j < N; j += nt) {
-    const double d = S[(size_t)j * ld + j];
-    const double zr = S[(size_t)j * ld + nc];
+    const double d = sweep_colp<true>(S, ld, j)[j];
+    const double zr = sweep_colp<true>(S, ld, j)[nc];
     if (!(d > 0.0)) first_bad = min(first_bad, j + 1);
     ld_part += log(d);
     q_part += (zr * zr) / d;
@@ -242,7 +243,7 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   const int fb = -block_max_int(-first_bad, ired);
   const int anybad = block_max_int(bad, ired);
   if (so.z != nullptr)
-    for (int j = tid; j < N; j += nt) so.z[(size_t)w * so.ldz + j] = S[(size_t)j * ld + nc] / sqrt(S[(size_t)j * ld + j]);
+    for (int j = tid; j < N; j += nt) so.z[(size_t)w * so.ldz + j] = sweep_colp<true>(S, ld, j)[nc] / sqrt(sweep_colp<true>(S, ld, j)[j]);
   if (so.logdet != nullptr && tid == 0) so.logdet[w] = logdet;
   if (tid == 0) {
     double v = -((double)N / 2.0) * log(2.0 * MRV_PI) - 0.5 * logdet - 0.5 * quad;
