@@ -141,6 +141,7 @@ struct mrv_problem {
   int band_opt = 0;    // UPDATE rasterisation band (tile rows), 0 = default
   int panel_inner_opt = 0;  // inner panel width of the two-level scheme, 0 = default (8)
   int cs_store = 1;    // streaming stores for updated C tiles
+  int small_minb_opt = 0;   // 2 / 3 / 4 forces the register-cap variant of the fused kernel (0 = by shared memory)
   int small_blk_min = 32;   // below this the rank-1 shared-memory kernel is used (option "small_blk_min"); measured:
                             // the packed blocked sweep wins from N = 32 up (tools/small_probe.py), equal at 16
   int lookahead_opt = 1;    // diagonal-first look-ahead inside a panel (auxiliary stream per sub-wave)
@@ -300,7 +301,9 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
 static int set_attrs(mrv_problem* p) {
   if (p->attrs_set) return 0;
   CU(cudaFuncSetAttribute(fused_small_logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(fused_small_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(fused_small_blk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(fused_small_blk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CU(cudaFuncSetAttribute(fused_small_blk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(mid_logl_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(mid_logl_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CU(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_BYTES));
@@ -517,10 +520,16 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
     const size_t smem = blk ? small_blk_smem_bytes(D.N) : small_smem_bytes(D.N);
     const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)W;
     p->prof.begin(CAT_FUSED, st, fl, fl);
-    if (blk)
-      fused_small_blk_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp,
-                                                                           d_modpar, d_model_given, to_ecc, d_logl,
-                                                                           d_status, so);
+    if (blk) {
+      // as many resident CTAs as the shared memory allows (1 KiB reserved per CTA), register cap to match
+      const int fit = (int)((227 * 1024) / (smem + 1024));
+      // ... but no tighter than the ensemble needs: a single round of CTAs runs fastest with the loosest cap
+      const int rounds = (int)((W + p->num_sms - 1) / p->num_sms);
+      const int minb = p->small_minb_opt > 0 ? p->small_minb_opt : std::max(2, std::min(4, std::min(fit, rounds)));
+      auto kern = minb >= 4 ? fused_small_blk_kernel<4> : (minb == 3 ? fused_small_blk_kernel<3> : fused_small_blk_kernel<2>);
+      kern<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar,
+                                                         d_model_given, to_ecc, d_logl, d_status, so);
+    }
     else
       fused_small_logl_kernel<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags,
                                                                             d_hp, d_modpar, d_model_given, to_ecc,
@@ -1110,6 +1119,8 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {
     p->cs_store = (int)value;   // bit 0: streaming C stores; bit 1: L2 prefetch of the next C tile (persistent GEMM)
+  } else if (!strcmp(key, "small_minb")) {
+    p->small_minb_opt = (int)value;
   } else if (!strcmp(key, "small_blk_min")) {
     p->small_blk_min = (int)value;
   } else if (!strcmp(key, "lookahead")) {

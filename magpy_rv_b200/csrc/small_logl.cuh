@@ -140,8 +140,10 @@ __host__ inline size_t small_blk_smem_bytes(int N) {
           MRV_MAX_MODPAR + MRV_MAX_HP + 40) * sizeof(double);
 }
 
-// (packed factor storage + a 128-register cap: two walkers' CTAs per SM up to N = 112, three up to N = 80)
-__global__ void __launch_bounds__(MRV_SMALL_THREADS, 2)
+// MINB = resident CTAs per SM the register cap is set for (packed factor storage: 2 CTAs fit up to N = 112,
+// 3 up to N = 80, 4 up to N = 64; the caps cost 24..60 bytes of spills)
+template <int MINB>
+__global__ void __launch_bounds__(MRV_SMALL_THREADS, MINB)
 fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double* __restrict__ y,
                        const double* __restrict__ yerr, const double* __restrict__ flags,
                        const double* __restrict__ hp_all, const double* __restrict__ modpar_all,
