@@ -336,11 +336,15 @@ static int choose_path(const mrv_problem* p, int64_t W = 0) {
   // one-CTA-per-walker streamed-panel kernel up to 512, the tiled wave factorisation above
   if (p->desc.N <= MRV_SMALL_BLK_N_MAX) return MRV_PATH_FUSED_SMEM;
   if (p->desc.N > MID_N_MAX) return MRV_PATH_BLOCKED;
-  // 320 < N <= 512: the tiled path wins when N nearly fills its 128-wide tiles (padding < 32 points) AND the
-  // ensemble needs more than one round of one-CTA-per-walker (measured, one B200: N = 384 x 512 walkers
-  // 338 k vs 315 k evals/s, 512 x 512 199 k vs 175 k; but 448 x 512 198 k vs 242 k, 512 x 148 170 k vs 181 k)
+  // 320 < N <= 512: the two paths are within +-9 % of each other when N nearly fills its 128-wide tiles
+  // (padding < 32 points); the one-CTA-per-walker kernel then wins exactly when its rounds of num_sms CTAs are
+  // well filled (measured, one B200: 384 x 512 walkers = 3.46 rounds 315 k vs 344 k evals/s tiled, 384 x 1024 =
+  // 6.9 rounds 367 k vs 353 k; 512 x 512 191 k vs 205 k, 512 x 1024 219 k vs 210 k, 512 x 148 206 k vs 170 k)
   const int pad128 = p->n_pad - p->desc.N;
-  if (p->desc.N > 320 && pad128 < 32 && W > p->num_sms) return MRV_PATH_BLOCKED;
+  if (p->desc.N > 320 && pad128 < 32 && W > p->num_sms) {
+    const int64_t rounds = (W + p->num_sms - 1) / p->num_sms;
+    if ((double)W < 0.93 * (double)(rounds * p->num_sms)) return MRV_PATH_BLOCKED;
+  }
   return MRV_PATH_MID;
 }
 

@@ -97,6 +97,46 @@ __device__ __noinline__ void gen_fragment4(const CovParams& cp, int N, int gi0, 
   }
 }
 
+// INTERIOR fragments (no diagonal element, nothing in the padding): everything by value and the result in
+// registers.  The general versions above / below take the output array by reference, which routes every
+// value through local memory and adds per-element diagonal / padding tests: measured 3.8 SM-clocks per
+// covariance evaluation in the streamed-panel kernel against 1.1 for the bare evaluation at the same
+// occupancy (tools/micro/gen.cu).  Almost every fragment is interior.
+struct Cov4 { double v0, v1, v2, v3; };
+struct Cov8 { double v0, v1, v2, v3, v4, v5, v6, v7; };
+__device__ __noinline__ Cov4 gen_interior4(int kind, double a2, double c1, double c2, double c3, double ti0, double ti1,
+                                           double tj0, double tj1) {
+  CovParams p;
+  p.kind = kind; p.a2 = a2; p.c1 = c1; p.c2 = c2; p.c3 = c3; p.jit2 = 0.0;
+  const double dt[4] = {ti0 - tj0, ti0 - tj1, ti1 - tj0, ti1 - tj1};
+  double d[4], d2[4], o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    d[e] = fabs(dt[e]);
+    d2[e] = dt[e] * dt[e];
+  }
+  cov_from_dist_n<4>(p, d, d2, o);
+  Cov4 r;
+  r.v0 = o[0]; r.v1 = o[1]; r.v2 = o[2]; r.v3 = o[3];
+  return r;
+}
+__device__ __noinline__ Cov8 gen_interior8(int kind, double a2, double c1, double c2, double c3, double ti0, double ti1,
+                                           double tj0, double tj1, double tj8, double tj9) {
+  CovParams p;
+  p.kind = kind; p.a2 = a2; p.c1 = c1; p.c2 = c2; p.c3 = c3; p.jit2 = 0.0;
+  const double dt[8] = {ti0 - tj0, ti0 - tj1, ti1 - tj0, ti1 - tj1, ti0 - tj8, ti0 - tj9, ti1 - tj8, ti1 - tj9};
+  double d[8], d2[8], o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    d[e] = fabs(dt[e]);
+    d2[e] = dt[e] * dt[e];
+  }
+  cov_from_dist_n<8>(p, d, d2, o);
+  Cov8 r;
+  r.v0 = o[0]; r.v1 = o[1]; r.v2 = o[2]; r.v3 = o[3]; r.v4 = o[4]; r.v5 = o[5]; r.v6 = o[6]; r.v7 = o[7];
+  return r;
+}
+
 // Two adjacent accumulator fragments (columns gj0, gj0+1 and gj0+8, gj0+9; rows gi0, gi0+8) in one call:
 // 8 independent exp / sin chains in flight per lane.  The GEMM runs 8 warps per SM, where 4 chains per
 // lane left the FP64 pipe waiting on its own latency during the first-touch generation.
@@ -747,6 +787,21 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
   } else if (g.mode == GEMM_UPDATE) {
     consumer_sync();  // tis / tjs
     const CovParams cp = make_cov_params(g.kernel_id, g.variant, g.hp_wave + (size_t)b * g.nh);
+    const bool interior = ti > tj && (ti + 1) * TILE <= g.N;   // off-diagonal tile, no padding rows
+    if (interior) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int np2 = 0; np2 < 2; ++np2) {
+          const int R = wm * 64 + mi * 16 + gq;
+          const int C = wn * 32 + np2 * 16 + 2 * tig;
+          const Cov8 f = gen_interior8(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, tis[R], tis[R + 8], tjs[C], tjs[C + 1], tjs[C + 8],
+                                       tjs[C + 9]);
+          acc[mi][2 * np2][0] = -f.v0; acc[mi][2 * np2][1] = -f.v1; acc[mi][2 * np2][2] = -f.v2; acc[mi][2 * np2][3] = -f.v3;
+          acc[mi][2 * np2 + 1][0] = -f.v4; acc[mi][2 * np2 + 1][1] = -f.v5; acc[mi][2 * np2 + 1][2] = -f.v6;
+          acc[mi][2 * np2 + 1][3] = -f.v7;
+        }
+    } else
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi)
 #pragma unroll

@@ -354,10 +354,15 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
           const int ni = 2 * h + nh;
           if (f < Fj) {
             const int gi0 = rw0 + 16 * f + gq, gj0 = rw0 + 8 * ni + 2 * tig;
-            double frag[4];
-            gen_fragment4(cp, N, gi0, gj0, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1], yerr, frag);
+            if (f >= 2 && rw0 + 16 * f + 15 < N) {   // warp-uniform: below the diagonal block, no padding
+              const Cov4 c4 = gen_interior4(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1]);
+              acc[s][ni][0] = -c4.v0; acc[s][ni][1] = -c4.v1; acc[s][ni][2] = -c4.v2; acc[s][ni][3] = -c4.v3;
+            } else {
+              double frag[4];
+              gen_fragment4(cp, N, gi0, gj0, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1], yerr, frag);
 #pragma unroll
-            for (int v = 0; v < 4; ++v) acc[s][ni][v] = -frag[v];
+              for (int v = 0; v < 4; ++v) acc[s][ni][v] = -frag[v];
+            }
           } else {
 #pragma unroll
             for (int v = 0; v < 4; ++v) acc[s][ni][v] = 0.0;
@@ -475,7 +480,12 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
           for (int ni = 0; ni < 4; ++ni) {
             const int gi0 = 16 * f + gq, gj0 = 8 * ni + 2 * tig;
             double frag[4];
-            gen_fragment4(cp, N, gi0, gj0, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1], yerr, frag);
+            if (f >= 2 && 16 * f + 15 < N) {
+              const Cov4 c4 = gen_interior4(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1]);
+              frag[0] = c4.v0; frag[1] = c4.v1; frag[2] = c4.v2; frag[3] = c4.v3;
+            } else {
+              gen_fragment4(cp, N, gi0, gj0, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1], yerr, frag);
+            }
 #pragma unroll
             for (int v1 = 0; v1 < 2; ++v1) {
               double2 o2;
