@@ -202,6 +202,9 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   //     (c, N-1-c), whose lower-triangle lengths add up to N+1, and every lane evaluates two
   //     independent entries per trip (ILP across the fp64 exp/sin dependency chains).
   const CovParams cp = make_cov_params(D.kernel_id, D.variant, hpv);
+  // zero-lag value + jitter once per walker: K_ii = (k(0) + jit^2) + yerr_i^2, the order of cov_diag().  Inside
+  // the `(i == c) ? cov_diag(...) : ev` selects the compiler evaluated k(0) -- a full exp / sin -- per element.
+  const double kdiag0 = cov_from_dist(cp, 0.0, 0.0) + cp.jit2;
   const int npairs = (N + 1) / 2;
   for (int pc = warp; pc < npairs; pc += nwarps) {
     const int cA = pc, cB = N - 1 - pc;
@@ -218,8 +221,15 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
       const double dd[2] = {fabs(dt0), fabs(dt1)}, dd2[2] = {dt0 * dt0, dt1 * dt1};
       double ev[2];
       cov_from_dist_n<2>(cp, dd, dd2, ev);
-      const double e0 = (i0 == c0) ? cov_diag(cp, yerr[i0]) : ev[0];
-      const double e1 = (i1 == c1) ? cov_diag(cp, yerr[i1]) : ev[1];
+      double e0 = ev[0], e1 = ev[1];
+      if (i0 == c0) {
+        const double ye = yerr[i0];
+        e0 = kdiag0 + ye * ye;
+      }
+      if (i1 == c1) {
+        const double ye = yerr[i1];
+        e1 = kdiag0 + ye * ye;
+      }
       bad |= !isfinite(e0);
       sweep_colp<true>(S, ld, c0)[i0] = e0;
       if (ok1) {
