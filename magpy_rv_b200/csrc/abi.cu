@@ -64,6 +64,29 @@ struct DevBuf {
   T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// Pinned host staging (the per-batch parameters in, log L / status out): a pageable cudaMemcpyAsync stages and
+// synchronises inside the driver (~10 us each, four per batch); one pinned buffer each way makes the small
+// batches of the tutorial-size runs one true async copy in and one out.
+struct PinBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t need) {
+    if (need <= bytes) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaHostAlloc(&p, need, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(-3, "cudaHostAlloc(%zu bytes) failed: %s", need, cudaGetErrorString(e));
+    bytes = need;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
 // Optional per-category kernel timing with CUDA events on the launching stream (bench.py roofline).
 enum { CAT_GEN = 0, CAT_POTRF, CAT_TRSM, CAT_UPDATE_PANEL, CAT_UPDATE_MID, CAT_UPDATE_TRAIL, CAT_MEAN, CAT_FINAL, CAT_FUSED, CAT_COUNT };
 static const char* const kCatNames[CAT_COUNT] = {"gen", "potrf", "trsm", "update_panel", "update_mid", "update_trail", "mean", "final", "fused"};
@@ -152,7 +175,8 @@ struct mrv_problem {
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
   // workspace
-  DevBuf hp, modpar, model, logl, status;                      // host-API staging
+  DevBuf hp, modpar, model, logl, status;                      // host-API staging (hp holds hp | modpar, logl holds logL | status)
+  PinBuf pin_in, pin_out;
   DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter, midws;
   int64_t wave_cur = 0;
   int64_t launches = 0;
@@ -279,6 +303,8 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
   DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
                     &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter, &p->midws};
   for (DevBuf* b : bufs) b->release();
+  p->pin_in.release();
+  p->pin_out.release();
   p->prof.destroy();
   if (p->stream) cudaStreamDestroy(p->stream);
   for (int i = 0; i < 3; ++i) {
@@ -696,25 +722,31 @@ static int host_logl(mrv_problem* p, const double* hp, const double* modpar, con
   CU(cudaSetDevice(p->device));
   const ProblemDesc& D = p->desc;
   int rc = 0;
-  if ((rc = p->hp.ensure((size_t)W * D.nh * sizeof(double)))) return rc;
-  if ((rc = p->modpar.ensure(std::max<size_t>(1, (size_t)W * D.nm) * sizeof(double)))) return rc;
-  if ((rc = p->logl.ensure((size_t)W * sizeof(double)))) return rc;
-  if ((rc = p->status.ensure((size_t)W * sizeof(int)))) return rc;
+  const size_t n_hp = (size_t)W * D.nh, n_mp = (size_t)W * D.nm;
+  const size_t in_bytes = (n_hp + std::max<size_t>(1, n_mp)) * sizeof(double);
+  const size_t out_bytes = (size_t)W * (sizeof(double) + sizeof(int));
+  if ((rc = p->hp.ensure(in_bytes)) || (rc = p->logl.ensure(out_bytes))) return rc;
+  if ((rc = p->pin_in.ensure(in_bytes)) || (rc = p->pin_out.ensure(out_bytes))) return rc;
   cudaStream_t st = p->stream;
-  CU(cudaMemcpyAsync(p->hp.p, hp, (size_t)W * D.nh * sizeof(double), cudaMemcpyHostToDevice, st));
-  if (D.nm > 0) CU(cudaMemcpyAsync(p->modpar.p, modpar, (size_t)W * D.nm * sizeof(double), cudaMemcpyHostToDevice, st));
+  double* h_in = static_cast<double*>(p->pin_in.p);
+  memcpy(h_in, hp, n_hp * sizeof(double));
+  if (n_mp > 0) memcpy(h_in + n_hp, modpar, n_mp * sizeof(double));
+  double* d_hp = p->hp.as<double>();
+  double* d_mp = d_hp + n_hp;
+  double* d_logl = p->logl.as<double>();
+  int* d_status = reinterpret_cast<int*>(d_logl + W);
+  CU(cudaMemcpyAsync(d_hp, h_in, (n_hp + n_mp) * sizeof(double), cudaMemcpyHostToDevice, st));
   const double* d_model = nullptr;
   if (model_y) {
     if ((rc = p->model.ensure((size_t)W * D.N * sizeof(double)))) return rc;
     CU(cudaMemcpyAsync(p->model.p, model_y, (size_t)W * D.N * sizeof(double), cudaMemcpyHostToDevice, st));
     d_model = p->model.as<double>();
   }
-  if ((rc = run_logl(p, p->hp.as<double>(), p->modpar.as<double>(), d_model, W, to_ecc, p->logl.as<double>(),
-                     p->status.as<int>(), st)))
-    return rc;
-  CU(cudaMemcpyAsync(logL_out, p->logl.p, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(status_out, p->status.p, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if ((rc = run_logl(p, d_hp, d_mp, d_model, W, to_ecc, d_logl, d_status, st))) return rc;
+  CU(cudaMemcpyAsync(p->pin_out.p, d_logl, out_bytes, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
+  memcpy(logL_out, p->pin_out.p, (size_t)W * sizeof(double));
+  memcpy(status_out, static_cast<char*>(p->pin_out.p) + (size_t)W * sizeof(double), (size_t)W * sizeof(int));
   return 0;
 }
 
