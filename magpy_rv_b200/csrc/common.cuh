@@ -45,6 +45,9 @@ struct ProblemDesc {
 // 1042).  CovParams holds per-walker constants so the N^2/2 evaluations are a handful of fp64 ops
 // plus the transcendental calls.  Constants fold the reference's divisions into reciprocals
 // (<= 1 ulp change per entry, far inside the 1e-9 LogL tolerance) and the two QuasiPer exps into one.
+// The periodic terms use sinpi / cospi of d / per instead of sin / cos of pi d / per: the range reduction is
+// then exact (no Cody-Waite / Payne-Hanek step) and the evaluation 13 % cheaper (tools/micro/gen.cu: 1.08 ->
+// 0.94 SM-clocks at 16 warps per SM); the argument carries the same one-ulp rounding as the reference's.
 // ------------------------------------------------------------------------------------------------
 struct CovParams {
   int kind;      // kernel_id (Matern5 textbook -> 7)
@@ -60,7 +63,7 @@ __host__ __device__ inline CovParams make_cov_params(int kernel_id, int variant,
   switch (kernel_id) {
     case 0:  // Cosine: hp = amp, per
       p.a2 = hp[0] * hp[0];
-      p.c1 = 2.0 * MRV_PI / hp[1];
+      p.c1 = 2.0 / hp[1];          // cospi(c1 d)
       break;
     case 1:  // ExpSquared: amp, timescale
       p.a2 = hp[0] * hp[0];
@@ -69,13 +72,13 @@ __host__ __device__ inline CovParams make_cov_params(int kernel_id, int variant,
     case 2:  // ExpSinSquared: amp, timescale, per
       p.a2 = hp[0] * hp[0];
       p.c1 = -2.0 / (hp[1] * hp[1]);
-      p.c2 = MRV_PI / hp[2];
+      p.c2 = 1.0 / hp[2];          // sinpi(c2 d)
       break;
     case 3:  // QuasiPer: per, perlength, explength, amp
     case 4:  // JitterQuasiPer: + jit
       p.a2 = hp[3] * hp[3];
       p.c1 = -1.0 / (hp[2] * hp[2]);
-      p.c2 = MRV_PI / hp[0];
+      p.c2 = 1.0 / hp[0];          // sinpi(c2 d)
       p.c3 = -1.0 / (hp[1] * hp[1]);
       if (kernel_id == 4) p.jit2 = hp[4] * hp[4];
       break;
@@ -102,16 +105,16 @@ __host__ __device__ inline CovParams make_cov_params(int kernel_id, int variant,
 __device__ __forceinline__ double cov_from_dist(const CovParams& p, double d, double d2) {
   switch (p.kind) {
     case 0:
-      return p.a2 * cos(p.c1 * d);
+      return p.a2 * cospi(p.c1 * d);
     case 1:
       return p.a2 * exp(p.c1 * (d * d));
     case 2: {
-      double s = sin(p.c2 * d);
+      double s = sinpi(p.c2 * d);
       return p.a2 * exp(p.c1 * (s * s));
     }
     case 3:
     case 4: {
-      double s = sin(p.c2 * d);
+      double s = sinpi(p.c2 * d);
       return p.a2 * exp(p.c1 * d2 + p.c3 * (s * s));
     }
     case 5: {  // reference as coded (kernels.py:909)
@@ -139,7 +142,7 @@ __device__ __forceinline__ void cov_from_dist_n(const CovParams& p, const double
   switch (p.kind) {
     case 0:
 #pragma unroll
-      for (int e = 0; e < NV; ++e) out[e] = p.a2 * cos(p.c1 * d[e]);
+      for (int e = 0; e < NV; ++e) out[e] = p.a2 * cospi(p.c1 * d[e]);
       break;
     case 1:
 #pragma unroll
@@ -148,7 +151,7 @@ __device__ __forceinline__ void cov_from_dist_n(const CovParams& p, const double
     case 2: {
       double s[NV];
 #pragma unroll
-      for (int e = 0; e < NV; ++e) s[e] = sin(p.c2 * d[e]);
+      for (int e = 0; e < NV; ++e) s[e] = sinpi(p.c2 * d[e]);
 #pragma unroll
       for (int e = 0; e < NV; ++e) out[e] = p.a2 * exp(p.c1 * (s[e] * s[e]));
       break;
@@ -157,7 +160,7 @@ __device__ __forceinline__ void cov_from_dist_n(const CovParams& p, const double
     case 4: {
       double s[NV];
 #pragma unroll
-      for (int e = 0; e < NV; ++e) s[e] = sin(p.c2 * d[e]);
+      for (int e = 0; e < NV; ++e) s[e] = sinpi(p.c2 * d[e]);
 #pragma unroll
       for (int e = 0; e < NV; ++e) out[e] = p.a2 * exp(p.c1 * d2[e] + p.c3 * (s[e] * s[e]));
       break;
