@@ -324,14 +324,23 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
 // kernel attribute setup (opt-in shared memory sizes), once per process per device is enough but it
 // is cheap, so once per handle.
 // ------------------------------------------------------------------------------------------------
+// opt in to the largest dynamic shared memory a kernel can get: 227 KiB minus whatever it declares statically
+template <class K>
+static int allow_max_dynamic_smem(K kernel) {
+  cudaFuncAttributes fa;
+  CU(cudaFuncGetAttributes(&fa, kernel));
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - (int)fa.sharedSizeBytes));
+  return 0;
+}
+
 static int set_attrs(mrv_problem* p) {
   if (p->attrs_set) return 0;
-  CU(cudaFuncSetAttribute(fused_small_logl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(fused_small_blk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(fused_small_blk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(fused_small_blk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(mid_logl_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CU(cudaFuncSetAttribute(mid_logl_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (int rc = allow_max_dynamic_smem(fused_small_logl_kernel)) return rc;
+  if (int rc = allow_max_dynamic_smem(fused_small_blk_kernel<2>)) return rc;
+  if (int rc = allow_max_dynamic_smem(fused_small_blk_kernel<3>)) return rc;
+  if (int rc = allow_max_dynamic_smem(fused_small_blk_kernel<4>)) return rc;
+  if (int rc = allow_max_dynamic_smem(mid_logl_kernel<7>)) return rc;
+  if (int rc = allow_max_dynamic_smem(mid_logl_kernel<15>)) return rc;
   CU(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_BYTES));
   CU(cudaFuncSetAttribute(potrf_tile_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_BLK_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));

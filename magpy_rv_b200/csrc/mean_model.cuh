@@ -24,11 +24,27 @@ __device__ inline void convert_to_ecc(const ProblemDesc& D, double* phys, int to
   }
 }
 
+// Block-wide sum with ONE barrier per call (block_sum needs two): the warp partials go to scratch[buf][warp] and,
+// after the barrier, every thread adds them in warp order.  The caller alternates `buf`, so the writes of call
+// k + 2 are separated from the reads of call k by the barrier of call k + 1.  Fixed order => deterministic.
+__device__ __forceinline__ double block_sum_1bar(double v, double* scratch /* 2 x 32 doubles */, int buf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  double* s = scratch + 32 * buf;
+  if (lane == 0) s[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  for (int w = 0; w < nwarps; ++w) r += s[w];
+  return r;
+}
+
 // One Keplerian curve added into model[] (length N).  E is an N-double scratch array.
 __device__ inline void cta_keplerian(int N, const double* __restrict__ t, double P, double K, double ecc,
                                      double omega, double t0, double* model, double* E, double* red) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const double two_pi = 2.0 * MRV_PI;
+  __shared__ double kep_red[64];   // the Newton loop is a chain of up to 200 block-wide sums: one barrier each
+  (void)red;
   // M = 2*pi*(t - t0)/P, E0 = M (not reduced mod 2pi), models.py:686, 635-636
   for (int i = tid; i < N; i += nt) E[i] = __ddiv_rn(__dmul_rn(two_pi, __dsub_rn(t[i], t0)), P);
   __syncthreads();
@@ -45,7 +61,7 @@ __device__ inline void cta_keplerian(int N, const double* __restrict__ t, double
       E[i] = En;
       part += fabs(__dsub_rn(En, E0));
     }
-    const double l1 = block_sum(part, red);   // whole-vector ||E - E0||_1, models.py:643
+    const double l1 = block_sum_1bar(part, kep_red, it & 1);   // whole-vector ||E - E0||_1, models.py:643
     if (l1 <= 1.0e-10) break;                 // NaN compares false -> keeps iterating, as NumPy does
   }
   __syncthreads();
