@@ -33,9 +33,16 @@ __device__ __forceinline__ double block_sum_1bar(double v, double* scratch /* 2 
   double* s = scratch + 32 * buf;
   if (lane == 0) s[warp] = v;
   __syncthreads();
-  double r = 0.0;
-  for (int w = 0; w < nwarps; ++w) r += s[w];
-  return r;
+  // four interleaved partial sums (fixed association): the dependent-add chain is nwarps / 4 + 2 long instead of nwarps
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+  for (int w = 0; w + 3 < nwarps; w += 4) {
+    r0 += s[w];
+    r1 += s[w + 1];
+    r2 += s[w + 2];
+    r3 += s[w + 3];
+  }
+  for (int w = nwarps & ~3; w < nwarps; ++w) r0 += s[w];
+  return (r0 + r1) + (r2 + r3);
 }
 
 // One Keplerian curve added into model[] (length N).  E is an N-double scratch array.
