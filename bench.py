@@ -139,13 +139,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
+    vals, walls = [], []
     desc = ""
     per_step = max(5.0, args.cpu_budget_s)
     for i in range(args.warmup + args.steps):
-        v, desc, _ = cpu_sample(args.config, args.n, per_step if i >= args.warmup else min(per_step, 8.0))
+        v, desc, wall = cpu_sample(args.config, args.n, per_step if i >= args.warmup else min(per_step, 8.0))
         if i >= args.warmup:
             vals.append(v)
+            walls.append(wall)
     value = float(np.mean(vals))
     cores = host_threads()
     out = {
@@ -156,6 +157,9 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # ms_per_step is the time the whole step (walkers_per_gpu x gpus evaluations at N) would take at the sampled
+        # rate; the sample itself (what the wall clock around this run sees) took sample_wall_ms_per_step
+        "sample_wall_ms_per_step": 1e3 * float(np.mean(walls)),
     }
     print(json.dumps(out), flush=True)
 
