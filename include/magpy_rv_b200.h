@@ -174,6 +174,16 @@ int64_t mrv_stretch_scan(const double* u, int64_t n_u, int64_t chain_begin, int6
                          const double* dX_mod, double a, const int32_t* kepler_offsets, int32_t n_kepler,
                          int64_t* chains_done, double* z_out, double* new_hp, double* new_mod);
 
+/* One whole split of MCMC.split_step on the ensemble arrays (reference mcmc.py:343-394): chain c is walker
+ * own[c], stretches towards walker partner[c]; the proposal (own value where vary == 0) is stored at row
+ * dest[c] of hp_out [W, nh] / mod_out [W, nm], in chain order; z_out is [n_chains].  Same uniform-buffer
+ * protocol and return value as mrv_stretch_scan; returns -1 when nh or nm exceeds 64. */
+int64_t mrv_stretch_split(const double* u, int64_t n_u, int64_t chain_begin, int64_t n_chains, int32_t nh,
+                          int32_t nm, const double* hp0, const double* mod0, const int64_t* own,
+                          const int64_t* partner, const int64_t* dest, const uint8_t* hp_vary,
+                          const uint8_t* mod_vary, double a, const int32_t* kepler_offsets, int32_t n_kepler,
+                          int64_t* chains_done, double* z_out, double* hp_out, double* mod_out);
+
 /* Introspection / tuning (no reference counterpart). */
 enum { MRV_PATH_AUTO = 0, MRV_PATH_FUSED_SMEM = 1, MRV_PATH_BLOCKED = 2, MRV_PATH_MID = 3 };
 int mrv_set_option(mrv_problem* p, const char* key, int64_t value); /* "path", "wave_walkers", "panel_tiles" */

@@ -66,6 +66,11 @@ SIGNATURES = {
                                           ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_double, c_int32_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64),
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mrv_stretch_split": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double, c_int32_p,
+                                           ctypes.c_int32, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
     "mrv_set_option": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int64]),
     "mrv_get_info": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_char_p]),
     "mrv_device_count": (ctypes.c_int, []),

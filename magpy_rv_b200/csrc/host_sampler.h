@@ -66,3 +66,59 @@ extern "C" int64_t mrv_stretch_scan(const double* u, int64_t n_u, int64_t chain_
   *chains_done = c;
   return used;
 }
+
+// One whole split of the stretch move on the ensemble arrays themselves: chain c is walker own[c], stretches
+// towards walker partner[c] and is stored at row dest[c] of the proposal arrays (reference mcmc.py:343-394;
+// parameters with vary == False keep the chain's own value; rows are written in chain order, so a later
+// chain overwrites an earlier one with the same destination, as the reference's loop does).  Same scan,
+// refill protocol and arithmetic as mrv_stretch_scan; z_out is indexed by chain.
+extern "C" int64_t mrv_stretch_split(const double* u, int64_t n_u, int64_t chain_begin, int64_t n_chains, int32_t nh,
+                                     int32_t nm, const double* hp0, const double* mod0, const int64_t* own,
+                                     const int64_t* partner, const int64_t* dest, const uint8_t* hp_vary,
+                                     const uint8_t* mod_vary, double a, const int32_t* kepler_offsets,
+                                     int32_t n_kepler, int64_t* chains_done, double* z_out, double* hp_out,
+                                     double* mod_out) {
+  enum { MAXP = 64 };
+  if (nh > MAXP || nm > MAXP) return -1;
+  int64_t used = 0, c = chain_begin;
+  const double am1 = a - 1.0;
+  volatile double two = 2.0;
+  double hp[MAXP], md[MAXP], dh[MAXP], dm[MAXP];
+  for (; c < n_chains; ++c) {
+    const double* xk_h = hp0 + own[c] * nh;
+    const double* xj_h = hp0 + partner[c] * nh;
+    const double* xk_m = mod0 + own[c] * nm;
+    const double* xj_m = mod0 + partner[c] * nm;
+    for (int i = 0; i < nh; ++i) dh[i] = xk_h[i] - xj_h[i];
+    for (int i = 0; i < nm; ++i) dm[i] = xk_m[i] - xj_m[i];
+    int64_t pos = used;
+    bool ok = false;
+    while (pos < n_u) {
+      volatile double s = u[pos] * am1;
+      const double base = s + 1.0;
+      const double z = pow(base, two) / a;
+      ++pos;
+      for (int i = 0; i < nh; ++i) {
+        volatile double prod = dh[i] * z;
+        hp[i] = xj_h[i] + prod;
+      }
+      for (int i = 0; i < nm; ++i) {
+        volatile double prod = dm[i] * z;
+        md[i] = xj_m[i] + prod;
+      }
+      if (mrv_proposal_valid(hp, nh, md, kepler_offsets, n_kepler)) {
+        z_out[c] = z;
+        ok = true;
+        break;
+      }
+    }
+    if (!ok) break;
+    used = pos;
+    double* oh = hp_out + dest[c] * nh;
+    double* om = mod_out + dest[c] * nm;
+    for (int i = 0; i < nh; ++i) oh[i] = hp_vary[i] ? hp[i] : xk_h[i];
+    for (int i = 0; i < nm; ++i) om[i] = mod_vary[i] ? md[i] : xk_m[i];
+  }
+  *chains_done = c;
+  return used;
+}

@@ -12,6 +12,7 @@ and only log-probabilities and status words are all-gathered (``sharding.py``).
 """
 import os
 import random
+import sys
 import time
 
 import numpy as np
@@ -42,6 +43,37 @@ def _randint0(n):
 
 
 _randbelow = getattr(getattr(random, "_inst", None), "_randbelow", None) or (lambda n: random.randint(0, n - 1))
+# Random._randbelow_with_getrandbits spelled out (k = n.bit_length(); draw k bits until < n) saves two Python
+# calls per number; only when the module's hidden instance is the stock Mersenne Twister class
+_STOCK_RANDOM = type(getattr(random, "_inst", None)) is random.Random
+
+
+def _randints0(n, count):
+    """`count` successive random.randint(0, n - 1) values as an index array."""
+    if n <= 0 or not _STOCK_RANDOM:
+        return np.array([_randint0(n) for _ in range(count)], dtype=np.intp)
+    getrandbits, k, out = random.getrandbits, n.bit_length(), []
+    for _ in range(count):
+        r = getrandbits(k)
+        while r >= n:
+            r = getrandbits(k)
+        out.append(r)
+    return np.array(out, dtype=np.intp)
+
+
+def _shuffle(x):
+    """random.shuffle(x) for a list (Fisher-Yates from the top, one _randbelow(i + 1) per element)."""
+    if not _STOCK_RANDOM or sys.version_info < (3, 9):
+        random.shuffle(x)
+        return
+    getrandbits = random.getrandbits
+    for i in range(len(x) - 1, 0, -1):
+        n = i + 1
+        k = n.bit_length()
+        j = getrandbits(k)
+        while j >= n:
+            j = getrandbits(k)
+        x[i], x[j] = x[j], x[i]
 
 
 def _parameter_check_rows(rows, names, check_args=()):
@@ -246,7 +278,7 @@ class MCMC:
         # same RNG consumption and result as random.shuffle on the NumPy array, without the slow
         # element-wise array swaps
         inds = (np.arange(W) % n_splits).tolist()
-        random.shuffle(inds)
+        _shuffle(inds)
         inds = np.array(inds)
 
         self.hp = np.zeros_like(self.hp0)
@@ -259,42 +291,61 @@ class MCMC:
         # model parameter, keeping the LAST match (mcmc.py:378-381); same rule, O(W) instead of O(W^2)
         keys = list(zip(hp0[:, 0].tolist(), mod0[:, 0].tolist()))
         last_match = {k: o for o, k in enumerate(keys)}
-        hp_vary = np.array(self.hp_vary, dtype=bool)
-        mod_vary = np.array(self.modpar_vary, dtype=bool)
         check_args = (Rstar, Mstar) if (Rstar is not None and Mstar is not None) else ()
         a = float(a)
-
-        def stretch(u):
-            # pure Python-float arithmetic, exactly the reference's expression (np.random.rand()
-            # returns a Python float there, so `**2` is libm pow(x, 2.0), not x*x)
-            return (u * (a - 1) + 1) ** 2 / a
+        native = not check_args and self.hlen <= 64 and self.plen <= 64
+        if native:
+            hp0 = np.ascontiguousarray(hp0)
+            mod0 = np.ascontiguousarray(mod0)
+            # The Python `random` stream (one randint per chain) and the np.random stream (the uniforms) are
+            # independent, and every proposal is made from the snapshot, so the chains of all splits can be
+            # lined up -- split by split, in chain order -- and scanned in one native call: chain i consumes
+            # the next uniform and keeps consuming while its proposal is invalid, so the numbers a chain sees
+            # depend on every chain before it.  mrv_stretch_split (csrc/host_sampler.h) gathers the two walkers
+            # of each chain, scans over a buffer of pre-drawn uniforms sized so that it never overdraws, and
+            # scatters the proposals: the sequence of numbers each chain sees -- and the position of both
+            # streams afterwards -- is exactly the reference's.
+            own, partner = [], []
+            for split in range(n_splits):
+                in_s1 = inds == split
+                idx1, idx2 = np.nonzero(in_s1)[0], np.nonzero(~in_s1)[0]
+                if len(idx1) == 0:
+                    np.zeros((0, 1))[0]       # an empty first set is an IndexError in the reference too
+                own.append(idx1)
+                partner.append(idx2[_randints0(len(idx2), len(idx1))])
+            own = np.concatenate(own)
+            dest = np.array([last_match[keys[i]] for i in own.tolist()], dtype=np.int64)
+            z = self._split_native(hp0, mod0, own, np.concatenate(partner), dest, a)
+            # np.log over the array runs the same per-element routine as the reference's np.log(z) on one
+            # Python float (checked bit for bit); with duplicated destinations the last chain wins, as there
+            self.logz[dest] = np.log(z)
+            return
 
         for split in range(n_splits):
             in_s1 = inds == split
+            idx1 = np.nonzero(in_s1)[0]
+            N_chains1, N_chains2 = len(idx1), W - len(idx1)
+            if N_chains1 == 0:
+                np.zeros((0, 1))[0]
+            # Python `random` stream: one randint per chain, in chain order (independent of np.random)
+            rints = _randints0(N_chains2, N_chains1)
+            positions = [last_match[keys[i]] for i in idx1.tolist()]
+
+            def stretch(u):
+                # pure Python-float arithmetic, exactly the reference's expression (np.random.rand()
+                # returns a Python float there, so `**2` is libm pow(x, 2.0), not x*x)
+                return (u * (a - 1) + 1) ** 2 / a
+
+            hp_vary = np.array(self.hp_vary, dtype=bool)
+            mod_vary = np.array(self.modpar_vary, dtype=bool)
             S1_hp, S2_hp = hp0[in_s1], hp0[~in_s1]
             S1_mod, S2_mod = mod0[in_s1], mod0[~in_s1]
-            N_chains1, N_chains2 = len(S1_hp), len(S2_hp)
-            S1_hp[0]                      # an empty first set is an IndexError in the reference too
-            # Python `random` stream: one randint per chain, in chain order (independent of np.random)
-            rints = np.array([_randint0(N_chains2) for _ in range(N_chains1)], dtype=np.intp)
             Xj, Xj_mod = S2_hp[rints], S2_mod[rints]
             dX, dX_mod = S1_hp - Xj, S1_mod - Xj_mod
-
-            # np.random stream: chain i consumes the next uniform and keeps consuming while its proposal
-            # is invalid, so the numbers a chain sees depend on every chain before it.  The sequential
-            # scan runs in the native host helper mrv_stretch_scan (csrc/host_sampler.h) over a buffer
-            # of pre-drawn uniforms; surplus draws are handed back by rewinding the stream, so the
-            # sequence of numbers each chain sees -- and the stream position afterwards -- is exactly
-            # the reference's.
             z = np.empty(N_chains1)
             new_hp = np.empty_like(S1_hp)
             new_mod = np.empty_like(S1_mod)
-            if check_args:
-                self._scan_python(N_chains1, Xj, dX, Xj_mod, dX_mod, stretch, check_args, z, new_hp, new_mod)
-            else:
-                self._scan_native(N_chains1, Xj, dX, Xj_mod, dX_mod, a, z, new_hp, new_mod)
-
-            positions = [last_match[keys[i]] for i in np.nonzero(in_s1)[0].tolist()]
+            self._scan_python(N_chains1, Xj, dX, Xj_mod, dX_mod, stretch, check_args, z, new_hp, new_mod)
             out_hp = np.where(hp_vary, new_hp, S1_hp)
             out_mod = np.where(mod_vary, new_mod, S1_mod)
             logz = np.array([np.log(v) for v in z.tolist()])
@@ -305,6 +356,43 @@ class MCMC:
             else:   # duplicated keys: later chains overwrite earlier ones, as in the reference's loop
                 for c, pos in enumerate(positions):
                     self.hp[0, pos], self.modpar[0, pos], self.logz[pos] = out_hp[c], out_mod[c], logz[c]
+
+    def _split_native(self, hp0, mod0, own, partner, dest, a):
+        """One split through the C ABI host helper mrv_stretch_split (no GPU involved): gathers the two
+        walkers of every chain, runs the validity-redraw scan and stores the proposals in self.hp /
+        self.modpar.  Returns z per chain."""
+        import ctypes
+        from . import _native as nat
+        lib = nat.lib()
+        n_chains = len(own)
+        own = np.ascontiguousarray(own, dtype=np.int64)
+        partner = np.ascontiguousarray(partner, dtype=np.int64)
+        cache = getattr(self, "_split_consts", None)
+        if cache is None:
+            kep = self._kepler_offsets()
+            cache = self._split_consts = (kep, np.array(self.hp_vary, dtype=np.uint8), np.array(self.modpar_vary, dtype=np.uint8))
+        kep, hp_vary, mod_vary = cache
+        kep_p = kep.ctypes.data_as(nat.c_int32_p) if kep.size else None
+        z = np.empty(n_chains)
+        done = ctypes.c_int64(0)
+        p_done = ctypes.byref(done)
+        hp_out, mod_out = self.hp[0], self.modpar[0]
+        # Every chain that is not finished needs at least one more uniform, so drawing exactly
+        # (chains left) numbers per round never overdraws: the np.random stream ends where the
+        # reference leaves it without any get_state / set_state rewind.  Draws of a chain that ran
+        # dry in the middle of its redraws stay at the head of `buf` and are re-scanned.
+        buf = None
+        while done.value < n_chains:
+            fresh = np.random.rand(n_chains - done.value)
+            buf = fresh if buf is None or buf.size == 0 else np.concatenate([buf, fresh])
+            used = lib.mrv_stretch_split(buf.ctypes.data, buf.size, done.value, n_chains, self.hlen, self.plen,
+                                         hp0.ctypes.data, mod0.ctypes.data, own.ctypes.data, partner.ctypes.data,
+                                         dest.ctypes.data, hp_vary.ctypes.data, mod_vary.ctypes.data, a, kep_p,
+                                         int(kep.size), p_done, z.ctypes.data, hp_out.ctypes.data, mod_out.ctypes.data)
+            if used < 0:
+                raise RuntimeError("mrv_stretch_split rejected its arguments")
+            buf = buf[used:]
+        return z
 
     def _kepler_offsets(self):
         offs, o = [], 0
@@ -390,31 +478,25 @@ class MCMC:
         diff = self.logL[0, :, 0] - self.logL0[0, :, 0]
         accept = diff > 1
         reject = diff < -35.
-        middle = (diff >= -35.) & (diff <= 1.)
-        idx = np.nonzero(middle)[0]
+        idx = np.flatnonzero((diff >= -35.) & (diff <= 1.))
         if idx.size:
-            u = np.array([random.uniform(0, 1) for _ in range(idx.size)])
-            ok = u <= np.exp(diff[idx])
-            accept = accept.copy()
-            reject = reject.copy()
+            rnd = random.random     # random.uniform(0, 1) is 0 + (1 - 0) * random(): the same number, bit for bit
+            ok = np.array([rnd() for _ in range(idx.size)]) <= np.exp(diff[idx])
             accept[idx[ok]] = True
             reject[idx[~ok]] = True
 
-        hp_decision = np.zeros(shape=(1, W, self.hlen))
-        modpar_decision = np.zeros(shape=(1, W, self.plen))
-        logL_decision = np.zeros(shape=(1, W, 1))
+        # accepted rows take the proposal, rejected rows the current state, undecided (NaN) rows stay zero
+        acc_col = accept[:, None]
+        hp_decision = np.where(acc_col, self.hp[0], self.hp0[0])[None]
+        modpar_decision = np.where(acc_col, self.modpar[0], self.modpar0[0])[None]
+        logL_decision = np.where(acc_col, self.logL[0], self.logL0[0])[None]
+        self.mass_decision = np.where(acc_col, self.mass[0], self.mass0_list[0])[None]
         self.acceptance_chain = np.zeros(shape=(1, W, 1))
-        self.mass_decision = np.zeros_like(self.mass)
-
-        hp_decision[0, accept] = self.hp[0, accept]
-        modpar_decision[0, accept] = self.modpar[0, accept]
-        logL_decision[0, accept] = self.logL[0, accept]
-        self.mass_decision[0, accept] = self.mass[0, accept]
         self.acceptance_chain[0, accept, 0] = True
-        hp_decision[0, reject] = self.hp0[0, reject]
-        modpar_decision[0, reject] = self.modpar0[0, reject]
-        logL_decision[0, reject] = self.logL0[0, reject]
-        self.mass_decision[0, reject] = self.mass0_list[0, reject]
+        undecided = ~(accept | reject)
+        if undecided.any():
+            for arr in (hp_decision, modpar_decision, logL_decision, self.mass_decision):
+                arr[0, undecided] = 0.
 
         self._hist_logL.append(logL_decision)
         self._hist_mass.append(self.mass_decision)

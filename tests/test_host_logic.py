@@ -282,3 +282,61 @@ def test_native_stretch_scan_matches_python_scan(oracle_backend):
         for x, y in zip(out[0][:3], out[1][:3]):
             np.testing.assert_array_equal(x, y)
         assert out[0][3] == out[1][3], "np.random stream left at a different position"
+
+
+def test_native_stretch_split_matches_python_scan(oracle_backend):
+    """mrv_stretch_split (gather + scan + scatter on the ensemble arrays, all splits lined up in one call)
+    against the NumPy/Python formulation: same proposals at the same rows (non-varying parameters keep the
+    chain's own value, a later chain overwrites an earlier one with the same destination), same z, same
+    position of the np.random stream afterwards.  Walkers are valid, so z near 1 always ends a redraw loop."""
+    cfg = workloads.make_config("C3", W=24, N=20)
+    random.seed(3)
+    np.random.seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = mcmc.MCMC(cfg["t"], cfg["y"], cfg["yerr"], cfg["hparam0"], cfg["kernel"], cfg["model_par0"],
+                      cfg["model_list"], cfg["prior_list"], 24)
+    rng = np.random.default_rng(5)
+    redraws = 0
+    for trial in range(20):
+        W = int(rng.integers(6, 60))
+        a = float(rng.choice([2.0, 2.5, 1.3]))
+        hp0 = np.abs(rng.normal(0.6, 0.5, (W, 5))) + 1e-3
+        mod0 = np.column_stack([np.abs(rng.normal(2, 2, W)), np.abs(rng.normal(5, 5, W)), rng.uniform(-.6, .6, W),
+                                rng.uniform(-.6, .6, W), np.abs(rng.normal(3, 3, W))])
+        n = int(rng.integers(1, W + 1))
+        own = rng.permutation(W)[:n]
+        partner = rng.integers(0, W, n)
+        dest = own.copy()
+        if n > 3:
+            dest[-1] = dest[0]                      # duplicated destination: the last chain wins
+        m.hp_vary = [True, True, bool(trial % 2), True, True]
+        m.modpar_vary = [True, True, True, True, bool(trial % 3)]
+        m._split_consts = None
+
+        def stretch(u):
+            return (u * (a - 1) + 1) ** 2 / a
+
+        # NumPy / Python formulation
+        np.random.seed(2000 + trial)
+        Xj, Xjm = hp0[partner], mod0[partner]
+        dX, dXm = hp0[own] - Xj, mod0[own] - Xjm
+        z_ref, h, mm = np.empty(n), np.empty((n, 5)), np.empty((n, 5))
+        m._scan_python(n, Xj, dX, Xjm, dXm, stretch, (), z_ref, h, mm)
+        after_ref = np.random.rand()
+        hp_ref, mod_ref = np.zeros((1, W, 5)), np.zeros((1, W, 5))
+        for c in range(n):
+            hp_ref[0, dest[c]] = np.where(m.hp_vary, h[c], hp0[own[c]])
+            mod_ref[0, dest[c]] = np.where(m.modpar_vary, mm[c], mod0[own[c]])
+        # native
+        np.random.seed(2000 + trial)
+        m.hp, m.modpar = np.zeros((1, W, 5)), np.zeros((1, W, 5))
+        z = m._split_native(hp0, mod0, own, partner, dest.astype(np.int64), a)
+        after = np.random.rand()
+        np.testing.assert_array_equal(z, z_ref)
+        np.testing.assert_array_equal(m.hp, hp_ref)
+        np.testing.assert_array_equal(m.modpar, mod_ref)
+        assert after == after_ref, "np.random stream left at a different position"
+        np.random.seed(2000 + trial)
+        np.random.rand(n)
+        redraws += int(np.random.rand() != after_ref)
+    assert redraws > 5, "the test inputs should force redraws in most trials"
