@@ -174,6 +174,12 @@ struct mrv_problem {
   int substreams_opt = 0;  // 0 = auto (two half-waves on two streams up to 32 tile columns), 1 = one stream
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr};
+  // Keplerian mean models (tiled path): the Newton kernel runs on its own stream next to the generation of tile
+  // column 0, which does not need the residuals; the first diagonal-tile kernel waits for it
+  int mean_overlap_opt = 1;
+  bool mean_pending = false;
+  cudaStream_t mean_stream = nullptr;
+  cudaEvent_t ev_mean_fork = nullptr, ev_mean = nullptr;
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging (hp holds hp | modpar, logl holds logL | status)
   PinBuf pin_in, pin_out;
@@ -317,6 +323,9 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
     if (p->la_evO[i]) cudaEventDestroy(p->la_evO[i]);
   }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->mean_stream) cudaStreamDestroy(p->mean_stream);
+  if (p->ev_mean_fork) cudaEventDestroy(p->ev_mean_fork);
+  if (p->ev_mean) cudaEventDestroy(p->ev_mean);
   delete p;
 }
 
@@ -468,6 +477,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
                                                             hp_wave, A, walker_stride);
   p->prof.end(st);
   p->launches++;
+  if (p->mean_pending) CU(cudaStreamWaitEvent(st, p->ev_mean, 0));   // residuals are first read by the diagonal-tile kernel
   // part: 0 = every target tile of the columns, 1 = only the diagonal tile of column c0, 2 = column c0 without it
   auto launch_update = [&](int cat, int c0, int c1, int pb, int pe, cudaStream_t s, int part = 0) {
     g.mode = GEMM_UPDATE;
@@ -661,14 +671,25 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   CU(cudaMemsetAsync(p->logdet.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->quad.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->fstatus.p, 0, (size_t)W * sizeof(int), st));
-  p->prof.begin(CAT_MEAN, st, 0.0, 0.0);
-  mean_residual_kernel<<<(unsigned)W, mean_threads(D.N), 0, st>>>(D, p->d_t, so.given_is_resid ? nullptr : p->d_y, p->d_flags, d_modpar,
+  cudaStream_t mst = st;
+  p->mean_pending = p->has_kepler && d_model_given == nullptr && p->mean_overlap_opt != 0;
+  if (p->mean_pending) {
+    if (!p->mean_stream) CU(cudaStreamCreateWithFlags(&p->mean_stream, cudaStreamNonBlocking));
+    if (!p->ev_mean_fork) CU(cudaEventCreateWithFlags(&p->ev_mean_fork, cudaEventDisableTiming));
+    if (!p->ev_mean) CU(cudaEventCreateWithFlags(&p->ev_mean, cudaEventDisableTiming));
+    mst = p->mean_stream;
+    CU(cudaEventRecord(p->ev_mean_fork, st));      // after the parameter upload and the previous call's consumers
+    CU(cudaStreamWaitEvent(mst, p->ev_mean_fork, 0));
+  }
+  p->prof.begin(CAT_MEAN, mst, 0.0, 0.0);
+  mean_residual_kernel<<<(unsigned)W, mean_threads(D.N), 0, mst>>>(D, p->d_t, so.given_is_resid ? nullptr : p->d_y, p->d_flags, d_modpar,
                                                     d_model_given, to_ecc,
                                                     p->resid.as<double>(), p->n_pad, p->escratch.as<double>(),
                                                     p->phys.as<double>(), p->nonfinite.as<int>());
-  p->prof.end(st);
+  p->prof.end(mst);
   p->launches++;
   CU(cudaGetLastError());
+  if (p->mean_pending) CU(cudaEventRecord(p->ev_mean, mst));
   // Mid sizes: a wave is cut into two halves on two streams, so the latency-bound
   // diagonal-tile kernels and the small launches near the end of every tile column of one half overlap
   // with the GEMMs of the other (per-walker results do not depend on the split: nothing is shared).
@@ -1164,6 +1185,8 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {
     p->cs_store = (int)value;   // bit 0: streaming C stores; bit 1: L2 prefetch of the next C tile (persistent GEMM)
+  } else if (!strcmp(key, "mean_overlap")) {
+    p->mean_overlap_opt = (int)value;   // 0: Keplerian mean kernel on the main stream, 1: next to the column-0 generation
   } else if (!strcmp(key, "small_minb")) {
     p->small_minb_opt = (int)value;
   } else if (!strcmp(key, "small_blk_min")) {
