@@ -45,6 +45,43 @@ __device__ __forceinline__ double block_sum_1bar(double v, double* scratch /* 2 
   return (r0 + r1) + (r2 + r3);
 }
 
+// Newton loop of the eccentric anomaly with PPT points per thread held in registers (point i = tid + j * blockDim).
+// The per-thread partial of ||E - E0||_1 is accumulated in increasing j, as the strided loop of the generic path does.
+template <int PPT>
+__device__ __forceinline__ void kepler_newton_regs(int N, const double* __restrict__ t, double P, double ecc, double t0,
+                                                   double* E, double* kep_red) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double two_pi = 2.0 * MRV_PI;
+  double M[PPT], E0[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    const int i = tid + j * nt;
+    M[j] = i < N ? __ddiv_rn(__dmul_rn(two_pi, __dsub_rn(t[i], t0)), P) : 0.0;
+    E0[j] = M[j];
+  }
+  for (int it = 0; it < 200; ++it) {
+    double part = 0.0;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      if (tid + j * nt < N) {
+        double s, c;
+        sincos(E0[j], &s, &c);
+        const double f = __dsub_rn(__dsub_rn(E0[j], __dmul_rn(ecc, s)), M[j]);
+        const double fp = __dsub_rn(1.0, __dmul_rn(ecc, c));
+        const double En = __dsub_rn(E0[j], __ddiv_rn(f, fp));
+        part += fabs(__dsub_rn(En, E0[j]));
+        E0[j] = En;
+      }
+    }
+    const double l1 = block_sum_1bar(part, kep_red, it & 1);   // whole-vector ||E - E0||_1, models.py:643
+    if (l1 <= 1.0e-10) break;                 // NaN compares false -> keeps iterating, as NumPy does
+  }
+#pragma unroll
+  for (int j = 0; j < PPT; ++j)
+    if (tid + j * nt < N) E[tid + j * nt] = E0[j];
+  __syncthreads();
+}
+
 // One Keplerian curve added into model[] (length N).  E is an N-double scratch array.
 __device__ inline void cta_keplerian(int N, const double* __restrict__ t, double P, double K, double ecc,
                                      double omega, double t0, double* model, double* E, double* red) {
@@ -53,25 +90,32 @@ __device__ inline void cta_keplerian(int N, const double* __restrict__ t, double
   __shared__ double kep_red[64];   // the Newton loop is a chain of up to 200 block-wide sums: one barrier each
   (void)red;
   // M = 2*pi*(t - t0)/P, E0 = M (not reduced mod 2pi), models.py:686, 635-636
-  for (int i = tid; i < N; i += nt) E[i] = __ddiv_rn(__dmul_rn(two_pi, __dsub_rn(t[i], t0)), P);
-  __syncthreads();
-  for (int it = 0; it < 200; ++it) {
-    double part = 0.0;
-    for (int i = tid; i < N; i += nt) {
-      const double M = __ddiv_rn(__dmul_rn(two_pi, __dsub_rn(t[i], t0)), P);
-      const double E0 = E[i];
-      double s, c;
-      sincos(E0, &s, &c);
-      const double f = __dsub_rn(__dsub_rn(E0, __dmul_rn(ecc, s)), M);
-      const double fp = __dsub_rn(1.0, __dmul_rn(ecc, c));
-      const double En = __dsub_rn(E0, __ddiv_rn(f, fp));
-      E[i] = En;
-      part += fabs(__dsub_rn(En, E0));
+  if (N <= 4 * nt) {
+    // up to four points per thread: M and E stay in registers over the whole Newton loop (same operations, same order)
+    if (N <= nt) kepler_newton_regs<1>(N, t, P, ecc, t0, E, kep_red);
+    else if (N <= 2 * nt) kepler_newton_regs<2>(N, t, P, ecc, t0, E, kep_red);
+    else kepler_newton_regs<4>(N, t, P, ecc, t0, E, kep_red);
+  } else {   // generic path: E in the scratch array
+    for (int i = tid; i < N; i += nt) E[i] = __ddiv_rn(__dmul_rn(two_pi, __dsub_rn(t[i], t0)), P);
+    __syncthreads();
+    for (int it = 0; it < 200; ++it) {
+      double part = 0.0;
+      for (int i = tid; i < N; i += nt) {
+        const double M = __ddiv_rn(__dmul_rn(two_pi, __dsub_rn(t[i], t0)), P);
+        const double E0 = E[i];
+        double s, c;
+        sincos(E0, &s, &c);
+        const double f = __dsub_rn(__dsub_rn(E0, __dmul_rn(ecc, s)), M);
+        const double fp = __dsub_rn(1.0, __dmul_rn(ecc, c));
+        const double En = __dsub_rn(E0, __ddiv_rn(f, fp));
+        E[i] = En;
+        part += fabs(__dsub_rn(En, E0));
+      }
+      const double l1 = block_sum_1bar(part, kep_red, it & 1);   // whole-vector ||E - E0||_1, models.py:643
+      if (l1 <= 1.0e-10) break;                 // NaN compares false -> keeps iterating, as NumPy does
     }
-    const double l1 = block_sum_1bar(part, kep_red, it & 1);   // whole-vector ||E - E0||_1, models.py:643
-    if (l1 <= 1.0e-10) break;                 // NaN compares false -> keeps iterating, as NumPy does
+    __syncthreads();
   }
-  __syncthreads();
   const double fac = sqrt(__ddiv_rn(__dadd_rn(1.0, ecc), __dsub_rn(1.0, ecc)));
   const double ecw = __dmul_rn(ecc, cos(omega));
   for (int i = tid; i < N; i += nt) {

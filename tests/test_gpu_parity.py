@@ -86,6 +86,23 @@ def test_model_curves_match_reference(case):
         np.testing.assert_allclose(phys[w], want, rtol=1e-14, atol=1e-15)
 
 
+@pytest.mark.parametrize("N", [200, 256, 257, 512, 700, 1024, 1025, 1500])
+def test_keplerian_newton_loop_variants_match_oracle(N):
+    """mrv_model_eval launches 256 threads per walker: N <= 256 / 512 / 1024 run the Newton loop with 1 / 2 / 4
+    points per thread in registers, longer series through the scratch array; all must give the curve of the
+    oracle's whole-vector iteration (models.py:618-697), small-M regime where it converges."""
+    rng = np.random.default_rng(N)
+    t = np.sort(rng.uniform(0.0, 300.0, N))
+    W = 3
+    modpar = np.column_stack([rng.uniform(3.0, 40.0, W), rng.uniform(5.0, 60.0, W), rng.uniform(-0.5, 0.5, W),
+                              rng.uniform(-0.5, 0.5, W), rng.uniform(0.0, 20.0, W)])
+    y, phys = engine.model_eval(["Keplerian"], t, modpar, to_ecc=True)
+    for w in range(W):
+        want, want_phys = port.get_model(["Keplerian"], t, modpar[w], True, None)
+        np.testing.assert_allclose(y[w], want, rtol=0, atol=1e-10 * np.max(np.abs(want)))
+        np.testing.assert_allclose(phys[w], want_phys, rtol=1e-14, atol=1e-15)
+
+
 def test_covariance_matrices_match_reference():
     g = np.load(os.path.join(GOLD, "cov_cases.npz"))
     x, xp, xq, err = g["x"], g["xp"], g["xq"], g["err"]
