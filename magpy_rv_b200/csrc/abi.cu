@@ -370,7 +370,8 @@ static int effective_panel(const mrv_problem* p) {
 
 // one point per thread up to 512 points: the Keplerian Newton loop is a chain of up to 200 block-wide
 // reductions per walker, so fewer points per thread shortens every link
-static unsigned mean_threads(int N) { return N > 256 ? 512u : 256u; }
+static int g_mean_threads_opt = 0;   // option "mean_threads" (probe only): 0 = automatic
+static unsigned mean_threads(int N) { return g_mean_threads_opt ? (unsigned)g_mean_threads_opt : (N > 256 ? 512u : 256u); }
 
 static int choose_path(const mrv_problem* p, int64_t W = 0) {
   if (p->path_opt == MRV_PATH_FUSED_SMEM) return MRV_PATH_FUSED_SMEM;
@@ -1185,6 +1186,9 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {
     p->cs_store = (int)value;   // bit 0: streaming C stores; bit 1: L2 prefetch of the next C tile (persistent GEMM)
+  } else if (!strcmp(key, "mean_threads")) {
+    if (value != 0 && (value < 64 || value > 1024 || value % 32)) return fail(-1, "mean_threads must be 0 or a multiple of 32 in 64..1024");
+    g_mean_threads_opt = (int)value;
   } else if (!strcmp(key, "mean_overlap")) {
     p->mean_overlap_opt = (int)value;   // 0: Keplerian mean kernel on the main stream, 1: next to the column-0 generation
   } else if (!strcmp(key, "small_minb")) {
