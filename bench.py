@@ -274,6 +274,8 @@ def run_ours(args):
     a, b = partition(Wtot, n_gpus)[rank]
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["model_list"], cfg["prior_list"],
                                     flags=cfg["flags"], device=local_rank, kernel_variant=cfg["kernel_variant"])
+    if world > 1:
+        prob.set_option("ensemble_walkers", Wtot)     # kernel choices by the whole ensemble: results independent of N GPUs
     if args.panel:
         prob.set_option("panel_tiles", args.panel)
     if args.wave:

@@ -164,6 +164,9 @@ struct mrv_problem {
   int band_opt = 0;    // UPDATE rasterisation band (tile rows), 0 = default
   int panel_inner_opt = 0;  // inner panel width of the two-level scheme, 0 = default (8)
   int cs_store = 1;    // streaming stores for updated C tiles
+  int64_t ensemble_opt = 0; // option "ensemble_walkers": size of the WHOLE ensemble when this handle evaluates one shard of it --
+                            // the size-dependent kernel choices below then do not depend on the number of shards, so a walker's
+                            // log L is bitwise the same on 1, 2, 4 or 8 GPUs (0 = the batch is the ensemble)
   int small_minb_opt = 0;   // 2 / 3 / 4 forces the register-cap variant of the fused kernel (0 = by shared memory)
   int small_blk_min = 32;   // below this the rank-1 shared-memory kernel is used (option "small_blk_min"); measured:
                             // the packed blocked sweep wins from N = 32 up (tools/small_probe.py), equal at 16
@@ -562,7 +565,8 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   CU(cudaSetDevice(p->device));
   if (int rc = set_attrs(p)) return rc;
   const ProblemDesc& D = p->desc;
-  const int path = choose_path(p, W);
+  const int64_t Wsel = p->ensemble_opt > 0 ? std::max<int64_t>(p->ensemble_opt, W) : W;
+  const int path = choose_path(p, Wsel);
   p->last_path = path;
   if (path == MRV_PATH_FUSED_SMEM) {
     if (D.N > SMALL_N_MAX) return fail(-1, "fused shared-memory path needs N <= %d (N=%d)", SMALL_N_MAX, D.N);
@@ -574,7 +578,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
       // as many resident CTAs as the shared memory allows (1 KiB reserved per CTA), register cap to match
       const int fit = (int)((227 * 1024) / (smem + 1024));
       // ... but no tighter than the ensemble needs: a single round of CTAs runs fastest with the loosest cap
-      const int rounds = (int)((W + p->num_sms - 1) / p->num_sms);
+      const int rounds = (int)((Wsel + p->num_sms - 1) / p->num_sms);
       const int minb = p->small_minb_opt > 0 ? p->small_minb_opt : std::max(2, std::min(4, std::min(fit, rounds)));
       auto kern = minb >= 4 ? fused_small_blk_kernel<4> : (minb == 3 ? fused_small_blk_kernel<3> : fused_small_blk_kernel<2>);
       kern<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar,
@@ -1186,6 +1190,9 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {
     p->cs_store = (int)value;   // bit 0: streaming C stores; bit 1: L2 prefetch of the next C tile (persistent GEMM)
+  } else if (!strcmp(key, "ensemble_walkers")) {
+    if (value < 0) return fail(-1, "ensemble_walkers must be >= 0");
+    p->ensemble_opt = value;
   } else if (!strcmp(key, "mean_threads")) {
     if (value != 0 && (value < 64 || value > 1024 || value % 32)) return fail(-1, "mean_threads must be 0 or a multiple of 32 in 64..1024");
     g_mean_threads_opt = (int)value;

@@ -84,6 +84,11 @@ class ShardedEvaluator:
         import torch
         rank, world = dist.get_rank(), dist.get_world_size()
         a, b = partition(W, world)[rank]
+        if self.problem is not None and getattr(self, "_ensemble_hint", None) != W:
+            # kernel selection by the size of the whole ensemble, not of this rank's block: a walker's log L is
+            # then bitwise the same for every number of shards
+            self.problem.set_option("ensemble_walkers", W)
+            self._ensemble_hint = W
         if self.problem is not None and torch.cuda.is_available():
             # device path: kernels write the rank's block, NCCL gathers on the same stream
             dev = torch.device("cuda", self.problem.device)

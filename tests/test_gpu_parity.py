@@ -103,6 +103,26 @@ def test_keplerian_newton_loop_variants_match_oracle(N):
         np.testing.assert_allclose(phys[w], want_phys, rtol=1e-14, atol=1e-15)
 
 
+@pytest.mark.parametrize("name,N,W,shards", [("C3", 500, 256, 2), ("C1", 100, 600, 4), ("C2", 384, 512, 8)])
+def test_shard_count_does_not_change_a_walkers_logl(name, N, W, shards):
+    """A rank that evaluates one block of the ensemble selects its kernels by the size of the WHOLE ensemble
+    (option ensemble_walkers, set by sharding.ShardedEvaluator), so log L of a walker is bitwise the same for every
+    number of shards although the size rules (fused / streamed panel / tiled, register-cap variant) depend on W."""
+    cfg = workloads.make_config(name, W=W, N=N)
+    prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["model_list"], cfg["prior_list"],
+                                    flags=cfg["flags"])
+    whole, st = prob.logl(cfg["hp"], cfg["modpar"])
+    path_whole = prob.info("path")
+    assert np.all(st == 0)
+    prob.set_option("ensemble_walkers", W)
+    step = W // shards
+    for a in range(0, W, step):
+        part, st = prob.logl(cfg["hp"][a:a + step], cfg["modpar"][a:a + step])
+        assert prob.info("path") == path_whole
+        np.testing.assert_array_equal(part, whole[a:a + step])
+    prob.close()
+
+
 def test_covariance_matrices_match_reference():
     g = np.load(os.path.join(GOLD, "cov_cases.npz"))
     x, xp, xq, err = g["x"], g["xp"], g["xq"], g["err"]
