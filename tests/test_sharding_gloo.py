@@ -55,6 +55,24 @@ def _worker(rank, world, port_no, q):
         full, _ = _oracle_eval(cfg)(cfg["hp"], cfg["modpar"])
         ok = bool(np.array_equal(logl, full) and status.dtype == np.int32 and np.all(status == 0))
 
+        # a rank tells its problem handle the size of the WHOLE ensemble (kernel selection must not depend on
+        # the number of shards) before it evaluates its own block
+        class FakeProblem:
+            device = 0
+            options = []
+
+            def set_option(self, key, value):
+                self.options.append((key, value))
+
+            def logl(self, hp, modpar, to_ecc=True):
+                assert self.options and self.options[-1] == ("ensemble_walkers", 13)
+                return _oracle_eval(cfg)(hp, modpar)
+        ev2 = ShardedEvaluator(None, None, None, None, None, None, None, None, local_eval=lambda *a: None)
+        ev2._local_eval, ev2.problem = None, FakeProblem()
+        logl2, _ = ev2.logl(cfg["hp"], cfg["modpar"])
+        ev2.logl(cfg["hp"], cfg["modpar"])
+        ok = ok and bool(np.array_equal(logl2, full)) and FakeProblem.options == [("ensemble_walkers", 13)]
+
         # the sampler on top of the sharded evaluator: same chain as a single process
         class Backend:
             def __init__(self, *a):
