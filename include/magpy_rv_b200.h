@@ -119,6 +119,13 @@ int mrv_model_eval(int device, const double* t, const double* flags, int64_t N,
                    const mrv_model_op* ops, int n_ops, int nm, const double* modpar, int64_t W,
                    int to_ecc, double* model_out, double* modpar_phys_out);
 
+/* Keplerian.ecc_anomaly(M, ecc, max_itr) (models.py:618-650): Newton iteration of Kepler's equation on the
+ * whole vector M [N] with the reference's stopping rule ||E - E0||_1 <= 1e-10; E_out [N]. */
+int mrv_kepler_anomaly(int device, const double* M, int64_t N, double ecc, int max_itr, double* E_out);
+
+/* Keplerian.true_anomaly(E, ecc) (models.py:653-669): nu = 2 atan(sqrt((1 + ecc) / (1 - ecc)) tan(E / 2)). */
+int mrv_true_anomaly(int device, const double* E, int64_t N, double ecc, double* nu_out);
+
 /* Dense covariance K [n1, n2] row-major between two time vectors: GPLikelihood.compute_kernel
  * (gp_likelihood.py:173-230) = compute_distances (kernels.py:51-78) + compute_covmatrix.
  * diag_mode bit 0: add gp_jit^2 (JitterQuasiPer / Matern3, kernels.py:778-783, 1044-1050) on

@@ -62,6 +62,8 @@ SIGNATURES = {
     "mrv_gelman_rubin": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                         ctypes.c_int64, c_double_p]),
     # host-only helper called twice per MCMC iteration: raw addresses (c_void_p) keep the ctypes overhead low
+    "mrv_kepler_anomaly": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.c_int64, ctypes.c_double, ctypes.c_int, c_double_p]),
+    "mrv_true_anomaly": (ctypes.c_int, [ctypes.c_int, c_double_p, ctypes.c_int64, ctypes.c_double, c_double_p]),
     "mrv_stretch_scan": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32,
                                           ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                           ctypes.c_double, c_int32_p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64),

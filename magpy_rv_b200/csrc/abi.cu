@@ -949,6 +949,36 @@ extern "C" int mrv_model_eval(int device, const double* t, const double* flags, 
   return 0;
 }
 
+// Keplerian.ecc_anomaly / true_anomaly on caller-supplied vectors (reference models.py:618-669).
+static int kepler_vector_op(int device, const double* in, int64_t N, double ecc, int max_itr, double* out, bool anomaly) {
+  if (!in || !out) return fail(-1, "null argument");
+  if (N < 0 || N > (int64_t)1 << 30) return fail(-1, "bad length %lld", (long long)N);
+  if (int rc = require_device(device)) return rc;
+  if (N == 0) return 0;
+  double *d_in = nullptr, *d_out = nullptr;
+  int rc = upload(&d_in, in, (size_t)N);
+  if (rc) return rc;
+  cudaError_t e = cudaMalloc((void**)&d_out, (size_t)N * sizeof(double));
+  if (e == cudaSuccess) {
+    if (anomaly) kepler_anomaly_kernel<<<1, 512>>>(d_in, (int)N, ecc, max_itr, d_out);
+    else true_anomaly_kernel<<<(unsigned)std::min<int64_t>((N + 255) / 256, 1184), 256>>>(d_in, (int)N, ecc, d_out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_in);
+  cudaFree(d_out);
+  if (e != cudaSuccess) return fail(-2, "kepler vector op: %s", cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int mrv_kepler_anomaly(int device, const double* M, int64_t N, double ecc, int max_itr, double* E_out) {
+  return kepler_vector_op(device, M, N, ecc, max_itr, E_out, true);
+}
+
+extern "C" int mrv_true_anomaly(int device, const double* E, int64_t N, double ecc, double* nu_out) {
+  return kepler_vector_op(device, E, N, ecc, 0, nu_out, false);
+}
+
 static int dense_cov(int device, int kernel_id, int variant, const double* hp, int nh, const double* x1, const double* x2,
                      const double* dist_e, const double* dist_se, int64_t n1, int64_t n2, int diag_mode,
                      const double* diag_add, double* K_out) {

@@ -216,3 +216,34 @@ __global__ void mean_residual_kernel(ProblemDesc D, const double* __restrict__ t
     if (tid == 0) nonfinite[w] = bad;
   }
 }
+
+// Keplerian.ecc_anomaly(M, ecc, max_itr) for a caller-supplied mean-anomaly vector (reference models.py:618-650):
+// the same whole-vector Newton iteration as cta_keplerian, one CTA, E_out is the working array.
+__global__ void kepler_anomaly_kernel(const double* __restrict__ M, int N, double ecc, int max_itr, double* E) {
+  __shared__ double red[64];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < N; i += nt) E[i] = M[i];
+  __syncthreads();
+  for (int it = 0; it < max_itr; ++it) {
+    double part = 0.0;
+    for (int i = tid; i < N; i += nt) {
+      const double E0 = E[i];
+      double s, c;
+      sincos(E0, &s, &c);
+      const double f = __dsub_rn(__dsub_rn(E0, __dmul_rn(ecc, s)), M[i]);
+      const double fp = __dsub_rn(1.0, __dmul_rn(ecc, c));
+      const double En = __dsub_rn(E0, __ddiv_rn(f, fp));
+      E[i] = En;
+      part += fabs(__dsub_rn(En, E0));
+    }
+    const double l1 = block_sum_1bar(part, red, it & 1);
+    if (l1 <= 1.0e-10) break;
+  }
+}
+
+// Keplerian.true_anomaly(E, ecc) = 2 atan(sqrt((1 + ecc) / (1 - ecc)) tan(E / 2)) (reference models.py:653-669).
+__global__ void true_anomaly_kernel(const double* __restrict__ E, int N, double ecc, double* nu) {
+  const double fac = sqrt(__ddiv_rn(__dadd_rn(1.0, ecc), __dsub_rn(1.0, ecc)));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x)
+    nu[i] = __dmul_rn(2.0, atan(__dmul_rn(fac, tan(__ddiv_rn(E[i], 2.0)))));
+}

@@ -270,6 +270,28 @@ def model_eval_ops(ops, nm, t, modpar, to_ecc=False, flags=None, device=None):
     return out, phys
 
 
+def kepler_anomaly(M, ecc, max_itr=200, device=None):
+    """Eccentric anomaly of a mean-anomaly vector -- see mrv_kepler_anomaly (reference models.py:618-650)."""
+    M = np.asarray(M, dtype=np.float64)
+    flat = np.ascontiguousarray(M.ravel())
+    out = np.empty_like(flat)
+    device = nat.default_device() if device is None else device
+    rc = nat.lib().mrv_kepler_anomaly(device, nat.dptr(flat), flat.shape[0], float(ecc), int(max_itr), nat.dptr(out))
+    nat.check(rc, "mrv_kepler_anomaly")
+    return out.reshape(M.shape)
+
+
+def true_anomaly(E, ecc, device=None):
+    """True anomaly of an eccentric-anomaly vector -- see mrv_true_anomaly (reference models.py:653-669)."""
+    E = np.asarray(E, dtype=np.float64)
+    flat = np.ascontiguousarray(E.ravel())
+    out = np.empty_like(flat)
+    device = nat.default_device() if device is None else device
+    rc = nat.lib().mrv_true_anomaly(device, nat.dptr(flat), flat.shape[0], float(ecc), nat.dptr(out))
+    nat.check(rc, "mrv_true_anomaly")
+    return out.reshape(E.shape)
+
+
 def predict_reduce(V, z, Kss, full_cov=False, device=None):
     """(mean [Np], cov [Np, Np] or var [Np]) -- see mrv_predict_reduce."""
     V = nat.as_f64(V)

@@ -219,6 +219,17 @@ class Keplerian(Model):
         names = ["P", "K", "Sk", "Ck", "t0"] if SkCk is True else ["P", "K", "ecc", "omega", "t0"]
         return _numbered(names, model_num, plotting)
 
+    def ecc_anomaly(self, M, ecc, max_itr=200):
+        """Eccentric anomaly by Newton iteration on the whole vector M, stopping when ||E - E0||_1 <= 1e-10
+        (reference models.py:618-650), on the GPU."""
+        E = engine.kepler_anomaly(M, ecc, max_itr)
+        return E if np.ndim(M) else E[()]
+
+    def true_anomaly(self, E, ecc):
+        """nu = 2 arctan(sqrt((1 + ecc) / (1 - ecc)) tan(E / 2)) (reference models.py:653-669), on the GPU."""
+        nu = engine.true_anomaly(E, ecc)
+        return nu if np.ndim(E) else nu[()]
+
     def model(self):
         out, _ = engine.model_eval(["kep"], self.time, [self.P, self.K, self.ecc, self.omega, self.t0], to_ecc=False)
         return out[0]

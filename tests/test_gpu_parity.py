@@ -123,6 +123,30 @@ def test_shard_count_does_not_change_a_walkers_logl(name, N, W, shards):
     prob.close()
 
 
+def test_keplerian_anomaly_methods_match_oracle():
+    """Keplerian.ecc_anomaly / true_anomaly as public methods (reference models.py:618-669): same iterates as
+    the oracle's whole-vector Newton loop in the converging regime, scalars in -> scalars out, max_itr honoured."""
+    rng = np.random.default_rng(8)
+    mp0 = mod.mod_create(["Keplerian"])
+    for name, v in zip(mp0, (4.2, 50.0, 0.1, 1.0, 0.5)):
+        mp0[name] = par.parameter(value=v, error=0.1, vary=True)
+    k = mod.Keplerian(np.linspace(0.0, 10.0, 5), mp0)
+    for N, ecc in ((1, 0.3), (40, 0.0), (700, 0.45), (1500, 0.8)):
+        M = rng.uniform(-20.0, 60.0, N)
+        E = k.ecc_anomaly(M, ecc)
+        want = port.ecc_anomaly(M, ecc)
+        np.testing.assert_allclose(E, want, rtol=0, atol=1e-9)      # a stop one iteration apart moves E by < 1e-10
+        np.testing.assert_allclose(E - ecc * np.sin(E), M, rtol=0, atol=1e-9)      # Kepler's equation holds
+        nu = k.true_anomaly(E, ecc)
+        np.testing.assert_allclose(nu, 2. * np.arctan(np.sqrt((1. + ecc) / (1. - ecc)) * np.tan(E / 2.)),
+                                   rtol=1e-12, atol=1e-12)
+    np.testing.assert_array_equal(k.ecc_anomaly(M, 0.4, max_itr=0), M)
+    one = k.ecc_anomaly(M, 0.4, max_itr=1)
+    np.testing.assert_allclose(one, M - (M - 0.4 * np.sin(M) - M) / (1. - 0.4 * np.cos(M)), rtol=1e-13, atol=1e-13)
+    assert np.ndim(k.ecc_anomaly(0.7, 0.2)) == 0 and np.ndim(k.true_anomaly(0.7, 0.2)) == 0
+    assert abs(float(k.ecc_anomaly(0.7, 0.2)) - float(port.ecc_anomaly(np.array([0.7]), 0.2)[0])) < 1e-12
+
+
 def test_covariance_matrices_match_reference():
     g = np.load(os.path.join(GOLD, "cov_cases.npz"))
     x, xp, xq, err = g["x"], g["xp"], g["xq"], g["err"]
