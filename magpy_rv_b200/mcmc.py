@@ -277,7 +277,10 @@ class MCMC:
         W = self.numb_chains
         # same RNG consumption and result as random.shuffle on the NumPy array, without the slow
         # element-wise array swaps
-        inds = (np.arange(W) % n_splits).tolist()
+        base = getattr(self, "_inds_base", None)
+        if base is None or base[0] != (W, n_splits):
+            base = self._inds_base = ((W, n_splits), (np.arange(W) % n_splits).tolist())
+        inds = list(base[1])
         _shuffle(inds)
         inds = np.array(inds)
 
@@ -289,8 +292,12 @@ class MCMC:
         mod0 = self.modpar0[0]
         # the reference locates each walker again by matching the first hyper-parameter and first
         # model parameter, keeping the LAST match (mcmc.py:378-381); same rule, O(W) instead of O(W^2)
-        keys = list(zip(hp0[:, 0].tolist(), mod0[:, 0].tolist()))
-        last_match = {k: o for o, k in enumerate(keys)}
+        first_hp = hp0[:, 0].tolist()
+        distinct = len(set(first_hp)) == W        # the usual case: every walker is its own (last) match
+        keys = last_match = None
+        if not distinct:
+            keys = list(zip(first_hp, mod0[:, 0].tolist()))
+            last_match = dict(zip(keys, range(W)))
         check_args = (Rstar, Mstar) if (Rstar is not None and Mstar is not None) else ()
         a = float(a)
         native = not check_args and self.hlen <= 64 and self.plen <= 64
@@ -314,7 +321,7 @@ class MCMC:
                 own.append(idx1)
                 partner.append(idx2[_randints0(len(idx2), len(idx1))])
             own = np.concatenate(own)
-            dest = np.array([last_match[keys[i]] for i in own.tolist()], dtype=np.int64)
+            dest = own.astype(np.int64) if distinct else np.fromiter(map(last_match.__getitem__, keys), np.int64, W)[own]
             z = self._split_native(hp0, mod0, own, np.concatenate(partner), dest, a)
             # np.log over the array runs the same per-element routine as the reference's np.log(z) on one
             # Python float (checked bit for bit); with duplicated destinations the last chain wins, as there
@@ -329,7 +336,7 @@ class MCMC:
                 np.zeros((0, 1))[0]
             # Python `random` stream: one randint per chain, in chain order (independent of np.random)
             rints = _randints0(N_chains2, N_chains1)
-            positions = [last_match[keys[i]] for i in idx1.tolist()]
+            positions = idx1.tolist() if distinct else [last_match[keys[i]] for i in idx1.tolist()]
 
             def stretch(u):
                 # pure Python-float arithmetic, exactly the reference's expression (np.random.rand()
@@ -491,8 +498,7 @@ class MCMC:
         modpar_decision = np.where(acc_col, self.modpar[0], self.modpar0[0])[None]
         logL_decision = np.where(acc_col, self.logL[0], self.logL0[0])[None]
         self.mass_decision = np.where(acc_col, self.mass[0], self.mass0_list[0])[None]
-        self.acceptance_chain = np.zeros(shape=(1, W, 1))
-        self.acceptance_chain[0, accept, 0] = True
+        self.acceptance_chain = accept.astype(np.float64).reshape(1, W, 1)
         undecided = ~(accept | reject)
         if undecided.any():
             for arr in (hp_decision, modpar_decision, logL_decision, self.mass_decision):
@@ -507,11 +513,11 @@ class MCMC:
     def reset(self):
         """Accepted proposals become the new current state (reference mcmc.py:540-567); returns
         (logL_list, hparameter_list, model_parameter_list, accepted, mass_list)."""
-        acc = self.acceptance_chain[0, :, 0] == True  # noqa: E712
-        self.logL0[0, acc] = self.logL[0, acc]
-        self.hp0[0, acc] = self.hp[0, acc]
-        self.modpar0[0, acc] = self.modpar[0, acc]
-        self.mass0_list[0, acc] = self.mass[0, acc]
+        acc = (self.acceptance_chain[0, :, 0] == True)[:, None]  # noqa: E712
+        np.copyto(self.logL0[0], self.logL[0], where=acc)
+        np.copyto(self.hp0[0], self.hp[0], where=acc)
+        np.copyto(self.modpar0[0], self.modpar[0], where=acc)
+        np.copyto(self.mass0_list[0], self.mass[0], where=acc)
         return self.logL_list, self.hparameter_list, self.model_parameter_list, self.accepted, self.mass_list
 
     # -- device-resident loop (opt-in, non-parity) ----------------------------------------------------------

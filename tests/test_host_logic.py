@@ -340,3 +340,46 @@ def test_native_stretch_split_matches_python_scan(oracle_backend):
         np.random.rand(n)
         redraws += int(np.random.rand() != after_ref)
     assert redraws > 5, "the test inputs should force redraws in most trials"
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("fixed_first", [False, True])
+def test_split_step_matches_reference_live(oracle_backend, fixed_first):
+    """split_step against the live reference under the same two RNG seeds, three proposals in a row: with
+    distinct first hyper-parameters (every walker is its own match) and with a first hyper-parameter of zero
+    error and no mean model, where the reference's position search (mcmc.py:378-381) sends every chain to the
+    LAST walker and leaves all other rows zero."""
+    ref = ref_loader.load()
+    cfg = workloads.make_config("C1", W=14, N=25)
+
+    def make(par_mod, mcmc_mod):
+        hp = par_mod.par_create("QuasiPer")
+        vals = {"gp_per": (20., 2.), "gp_perlength": (0.5, 0.1), "gp_explength": (40., 5.), "gp_amp": (8., 1.)}
+        for i, k in enumerate(hp):
+            v, e = vals[k]
+            first = fixed_first and i == 0
+            hp[k] = par_mod.parameter(value=v, error=0. if first else e, vary=not first)
+        random.seed(11)
+        np.random.seed(11)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return mcmc_mod.MCMC(cfg["t"], cfg["y"], cfg["yerr"], hp, "QuasiPer",
+                                 {"no": par_mod.parameter(value=0., error=0., vary=False)}, ["no"], [], 14)
+
+    a = make(ref.par, ref.mcmc)
+    b = make(par, mcmc)
+    np.testing.assert_array_equal(a.hp0, b.hp0)
+    for rep in range(3):
+        random.seed(100 + rep)
+        np.random.seed(100 + rep)
+        a.split_step()
+        ra, na = random.random(), np.random.rand()
+        random.seed(100 + rep)
+        np.random.seed(100 + rep)
+        b.split_step()
+        rb, nb = random.random(), np.random.rand()
+        np.testing.assert_array_equal(a.hp, b.hp)
+        np.testing.assert_array_equal(a.modpar, b.modpar)
+        np.testing.assert_array_equal(a.logz, b.logz)
+        assert (ra, na) == (rb, nb), "RNG streams left at different positions"
+    if fixed_first:
+        assert np.count_nonzero(b.hp[0].any(axis=1)) == 1 and b.hp[0, -1].any()
