@@ -383,3 +383,22 @@ def test_split_step_matches_reference_live(oracle_backend, fixed_first):
         assert (ra, na) == (rb, nb), "RNG streams left at different positions"
     if fixed_first:
         assert np.count_nonzero(b.hp[0].any(axis=1)) == 1 and b.hp[0, -1].any()
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) runs without a GPU and prints one
+    JSON line with the contract's keys, the same metric / unit / config naming as the GPU arm."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--npoints", "200",
+                          "--walkers-per-gpu", "16", "--steps", "1", "--warmup", "1", "--cpu-budget-s", "1"],
+                         capture_output=True, text=True, timeout=240, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "gp_logl_evals_per_sec" and line["unit"] == "evals/s"
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 1
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["N"] == 200 and "workload" in line["config"] and line["gpu_launches"] == 0
