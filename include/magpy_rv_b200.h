@@ -11,7 +11,8 @@
  *   - per-walker `status` follows LAPACK potrf `info`: 0 ok, k > 0 = the leading minor of order k
  *     is not positive definite (the reference raises numpy.linalg.LinAlgError from cho_factor,
  *     gp_likelihood.py:271), -1 = non-finite covariance / residual input (cho_factor
- *     check_finite=True raises ValueError).
+ *     check_finite=True raises ValueError), -3 = internal error (the dataflow factorisation kernel gave up
+ *     waiting for a tile dependency; never produced by valid input -- the Python shim raises RuntimeError).
  *   - host-pointer entry points copy in/out synchronously; *_device entry points take device
  *     pointers and enqueue on `stream` (a cudaStream_t passed as void*, NULL = default stream).
  *   - a handle is bound to one CUDA device and is not thread safe.
@@ -205,6 +206,10 @@ int mrv_abi_version(void);
 double mrv_fp64_mma_peak(int device, int iters);
 /* Same for the vector FP64 pipe (DFMA), for comparison. */
 double mrv_fp64_fma_peak(int device, int iters);
+/* Covariance evaluations per second of kernel `kernel_id` (kernels.py:229...1042 bodies, 8 evaluations in flight per
+ * thread, 16 warps per SM): bench.py states the generation cost of one matrix entry as vector-pipe peak / this rate
+ * (FP64 flop-equivalents per entry) in the small-N roofline.  < 0 on error. */
+double mrv_cov_eval_rate(int device, int kernel_id, int kernel_variant, const double* hp, int nh);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,7 @@ SIGNATURES = {
     "mrv_abi_version": (ctypes.c_int, []),
     "mrv_fp64_mma_peak": (ctypes.c_double, [ctypes.c_int, ctypes.c_int]),
     "mrv_fp64_fma_peak": (ctypes.c_double, [ctypes.c_int, ctypes.c_int]),
+    "mrv_cov_eval_rate": (ctypes.c_double, [ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, ctypes.c_int]),
 }
 
 _lib = None

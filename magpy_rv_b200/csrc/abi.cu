@@ -13,9 +13,9 @@
 
 #include "../../include/magpy_rv_b200.h"
 #include "blocked.cuh"
+#include "dag.cuh"
 #include "common.cuh"
 #include "dense_ops.cuh"
-#include "gemm_persist.cuh"
 #include "mean_model.cuh"
 #include "small_logl.cuh"
 #include "mid_logl.cuh"
@@ -88,8 +88,8 @@ struct PinBuf {
 };
 
 // Optional per-category kernel timing with CUDA events on the launching stream (bench.py roofline).
-enum { CAT_GEN = 0, CAT_POTRF, CAT_TRSM, CAT_UPDATE_PANEL, CAT_UPDATE_MID, CAT_UPDATE_TRAIL, CAT_MEAN, CAT_FINAL, CAT_FUSED, CAT_COUNT };
-static const char* const kCatNames[CAT_COUNT] = {"gen", "potrf", "trsm", "update_panel", "update_mid", "update_trail", "mean", "final", "fused"};
+enum { CAT_GEN = 0, CAT_POTRF, CAT_TRSM, CAT_UPDATE_PANEL, CAT_UPDATE_MID, CAT_UPDATE_TRAIL, CAT_MEAN, CAT_FINAL, CAT_FUSED, CAT_DAG, CAT_COUNT };
+static const char* const kCatNames[CAT_COUNT] = {"gen", "potrf", "trsm", "update_panel", "update_mid", "update_trail", "mean", "final", "fused", "dag"};
 struct ProfRec {
   int cat;
   cudaEvent_t e0, e1;
@@ -158,9 +158,9 @@ struct mrv_problem {
   int path_opt = MRV_PATH_AUTO;
   int64_t wave_opt = 0;
   int panel_opt = 0;
-  int gemm_impl = 0;  // 0 = one tile per CTA, bulk-copy/mbarrier ring (default); 1 = persistent variant; 2 = cp.async
   int num_sms = 148;
   int potrf_impl = 0;  // 0 = blocked rank-16 sweep with DMMA trailing updates, 1 = rank-1 sweep
+  int tiled_impl = 0;  // tiled path: 0 = automatic, 1 = one launch per tile column and kernel (run_wave), 2 = persistent dataflow kernel
   int band_opt = 0;    // UPDATE rasterisation band (tile rows), 0 = default
   int panel_inner_opt = 0;  // inner panel width of the two-level scheme, 0 = default (8)
   int cs_store = 1;    // streaming stores for updated C tiles
@@ -186,7 +186,7 @@ struct mrv_problem {
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging (hp holds hp | modpar, logl holds logL | status)
   PinBuf pin_in, pin_out;
-  DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter, midws;
+  DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter, midws, zcols, rowdone;
   int64_t wave_cur = 0;
   int64_t launches = 0;
   int last_path = 0;
@@ -310,7 +310,8 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
   cudaFree(p->d_yerr);
   cudaFree(p->d_flags);
   DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
-                    &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter, &p->midws};
+                    &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter, &p->midws,
+                    &p->zcols, &p->rowdone};
   for (DevBuf* b : bufs) b->release();
   p->pin_in.release();
   p->pin_out.release();
@@ -355,9 +356,8 @@ static int set_attrs(mrv_problem* p) {
   if (int rc = allow_max_dynamic_smem(mid_logl_kernel<15>)) return rc;
   CU(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_SMEM_BYTES));
   CU(cudaFuncSetAttribute(potrf_tile_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTRF_BLK_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(gemm_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(gemm_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TMA_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(gemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TMA_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TMA_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(tile_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DAG_SMEM_BYTES));
   CU(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, p->device));
   p->attrs_set = true;
   return 0;
@@ -444,7 +444,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   // latency-bound diagonal-tile kernel (one CTA per walker, ~60 us) leaves the critical path.
   // measured on top of the two half-waves (tools/substream_probe.py): +5 % at N = 1024 x 128 walkers, +0..1 % for
   // other small waves, -2 % at 640 x 512 -- so only (sub-)waves of at most 64 walkers use it (option 2 forces it)
-  const bool la = p->gemm_impl == 0 && nt <= 64 && (p->lookahead_opt == 2 || (p->lookahead_opt == 1 && B <= 64));
+  const bool la = nt <= 64 && (p->lookahead_opt == 2 || (p->lookahead_opt == 1 && B <= 64));
   cudaStream_t aux = nullptr;
   if (la) {
     if (!p->la_stream[sub]) CU(cudaStreamCreateWithFlags(&p->la_stream[sub], cudaStreamNonBlocking));
@@ -453,16 +453,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
     aux = p->la_stream[sub];
   }
   auto launch_gemm = [&](dim3 grid, cudaStream_t st) {
-    if (p->gemm_impl == 1) {
-      const long long total = (long long)grid.x * grid.y;
-      const unsigned ctas = (unsigned)std::min<long long>(total, p->num_sms);
-      cudaMemsetAsync(p->counter.p, 0, sizeof(int), st);
-      gemm_persist_kernel<<<ctas, GEMM_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g, (int)grid.x, (int)total, p->counter.as<int>());
-    } else if (p->gemm_impl == 0) {
-      gemm_tile_kernel<true><<<grid, GEMM_TMA_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g);
-    } else {
-      gemm_tile_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(g);
-    }
+    gemm_tile_kernel<<<grid, GEMM_TMA_THREADS, GEMM_TMA_SMEM_BYTES, st>>>(g);
   };
   const double T3 = (double)TILE * TILE * TILE;
   // algorithmic / executed FLOPs of an UPDATE launch over target columns [c0, c1) with np operand columns
@@ -553,6 +544,60 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
     }
     if (P1 < nt) launch_update(CAT_UPDATE_TRAIL, P1, nt, P0, P1, st);
   }
+  CU(cudaGetLastError());
+  return 0;
+}
+
+// Tiled path as ONE persistent dataflow kernel per wave (dag.cuh).  Measured against the launch-per-column loop
+// above (tools/sweep_c5.py, profiles/README.md) it wins wherever the wave does not fill many rounds of CTAs per
+// launch, i.e. up to N = 4096; above that the right-looking panels of run_wave re-use operands better.
+static bool use_dag(const mrv_problem* p) {
+  if (p->tiled_impl == 1) return false;
+  if (p->tiled_impl == 2) return p->nt <= 128;
+  return p->nt <= DAG_AUTO_MAX_TILES;
+}
+
+static int run_wave_dag(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so) {
+  const ProblemDesc& D = p->desc;
+  const int nt = p->nt;
+  DagArgs g;
+  memset(&g, 0, sizeof g);
+  g.N = D.N;
+  g.nt = nt;
+  g.B = (int)B;
+  g.kernel_id = D.kernel_id;
+  g.variant = D.variant;
+  g.nh = D.nh;
+  const long long total = (long long)B * nt * (nt + 1) / 2;
+  if (total > 0x7fffffffLL) return fail(-1, "wave of %lld walkers x %d tile columns has too many tile tasks", (long long)B, nt);
+  g.total_tasks = (int)total;
+  g.Abase = p->factor.as<double>();
+  g.walker_stride = tile_index(nt - 1, nt - 1) * TILE_ELEMS + TILE_ELEMS;
+  g.t = p->d_t;
+  g.yerr = p->d_yerr;
+  g.hp_wave = d_hp + (size_t)w0 * D.nh;
+  g.resid = p->resid.as<double>() + (size_t)w0 * p->n_pad;
+  g.ldr = p->n_pad;
+  g.zcols = p->zcols.as<double>();
+  g.rowdone = p->rowdone.as<int>();
+  g.counter = p->counter.as<int>();
+  g.acc_logdet = p->logdet.as<double>() + w0;
+  g.acc_quad = p->quad.as<double>() + w0;
+  g.status = p->fstatus.as<int>() + w0;
+  g.zout = so.z ? so.z + (size_t)w0 * so.ldz : nullptr;
+  g.ldz = so.ldz;
+  CU(cudaMemsetAsync(p->rowdone.p, 0, (size_t)B * nt * sizeof(int), st));
+  CU(cudaMemsetAsync(p->counter.p, 0, sizeof(int), st));     // task counter; [1] = abort flag, cleared once per batch
+  const unsigned grid = (unsigned)std::min<long long>(total, p->num_sms);
+  const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)B;
+  const double T3 = (double)TILE * TILE * TILE;
+  // executed: every tile (i,k) runs k full tile products, off-diagonal tiles one more for the solve (5/8 of it issued)
+  double ex = 0.0;
+  for (int k = 0; k < nt; ++k) ex += (double)(nt - k) * 2.0 * T3 * k + (double)(nt - k - 1) * 2.0 * T3 * 0.625 + 1.5 * T3;
+  p->prof.begin(CAT_DAG, st, fl, ex * (double)B);
+  tile_dag_kernel<<<grid, DAG_THREADS, DAG_SMEM_BYTES, st>>>(g);
+  p->prof.end(st);
+  p->launches++;
   CU(cudaGetLastError());
   return 0;
 }
@@ -672,12 +717,18 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   if ((rc = p->zbuf.ensure((size_t)B * TILE * sizeof(double)))) return rc;
   if ((rc = p->counter.ensure(64))) return rc;
   if ((rc = p->factor.ensure((size_t)B * walker_bytes))) return rc;
+  const bool dag = use_dag(p);
+  if (dag) {
+    if ((rc = p->zcols.ensure((size_t)B * nt * TILE * sizeof(double)))) return rc;
+    if ((rc = p->rowdone.ensure((size_t)B * nt * sizeof(int)))) return rc;
+    CU(cudaMemsetAsync(p->counter.p, 0, 4 * sizeof(int), st));
+  }
 
   CU(cudaMemsetAsync(p->logdet.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->quad.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->fstatus.p, 0, (size_t)W * sizeof(int), st));
   cudaStream_t mst = st;
-  p->mean_pending = p->has_kepler && d_model_given == nullptr && p->mean_overlap_opt != 0;
+  p->mean_pending = p->has_kepler && d_model_given == nullptr && p->mean_overlap_opt != 0 && !dag;
   if (p->mean_pending) {
     if (!p->mean_stream) CU(cudaStreamCreateWithFlags(&p->mean_stream, cudaStreamNonBlocking));
     if (!p->ev_mean_fork) CU(cudaEventCreateWithFlags(&p->ev_mean_fork, cudaEventDisableTiming));
@@ -704,7 +755,6 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   // occasionally lose 10..40 %), so the automatic choice is two streams exactly where they were a robust win
   int nsub = p->substreams_opt > 0 ? p->substreams_opt : (((nt <= 16 && B >= 16) || (nt <= 64 && B >= 16 && B <= 64)) ? 2 : 1);
   nsub = std::max(1, std::min(nsub, 4));
-  if (p->gemm_impl == 1) nsub = 1;   // the persistent GEMM variant shares one tile counter
   if (nsub > 1) {
     if (!p->ev_fork) CU(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
     for (int i = 0; i < nsub - 1; ++i) {
@@ -715,7 +765,9 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   for (int64_t w0 = 0; w0 < W; w0 += B) {
     const int64_t Bw = std::min<int64_t>(B, W - w0);
     const int parts = (int)std::min<int64_t>(nsub, Bw);
-    if (parts > 1) {
+    if (dag) {
+      if ((rc = run_wave_dag(p, d_hp, w0, Bw, st, so))) return rc;
+    } else if (parts > 1) {
       CU(cudaEventRecord(p->ev_fork, st));
       int64_t off = 0;
       for (int i = 0; i < parts; ++i) {
@@ -737,7 +789,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   finalize_logl_kernel<<<(unsigned)((W + 127) / 128), 128, 0, st>>>(D, (int)W, d_hp, p->phys.as<double>(),
                                                                     p->logdet.as<double>(), p->quad.as<double>(),
                                                                     p->nonfinite.as<int>(), p->fstatus.as<int>(), d_logl,
-                                                                    d_status, so.logdet);
+                                                                    d_status, so.logdet, dag ? p->counter.as<int>() + 1 : nullptr);
   p->prof.end(st);
   p->launches++;
   CU(cudaGetLastError());
@@ -1211,15 +1263,12 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->wave_opt = value;
   } else if (!strcmp(key, "panel_tiles")) {
     p->panel_opt = (int)value;
-  } else if (!strcmp(key, "gemm_impl")) {
-    if (value < 0 || value > 2) return fail(-1, "gemm_impl must be 0 (bulk copy per tile), 1 (persistent) or 2 (cp.async)");
-    p->gemm_impl = (int)value;
   } else if (!strcmp(key, "panel_inner")) {
     p->panel_inner_opt = (int)value;
   } else if (!strcmp(key, "update_band")) {
     p->band_opt = (int)value;
   } else if (!strcmp(key, "cs_store")) {
-    p->cs_store = (int)value;   // bit 0: streaming C stores; bit 1: L2 prefetch of the next C tile (persistent GEMM)
+    p->cs_store = (int)value;   // 1: streaming (evict-first) stores of updated C tiles
   } else if (!strcmp(key, "ensemble_walkers")) {
     if (value < 0) return fail(-1, "ensemble_walkers must be >= 0");
     p->ensemble_opt = value;
@@ -1236,6 +1285,9 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->lookahead_opt = (int)value;
   } else if (!strcmp(key, "substreams")) {
     p->substreams_opt = (int)value;
+  } else if (!strcmp(key, "tiled_impl")) {
+    if (value < 0 || value > 2) return fail(-1, "tiled_impl must be 0 (automatic), 1 (launch per tile column) or 2 (persistent dataflow kernel)");
+    p->tiled_impl = (int)value;
   } else if (!strcmp(key, "potrf_impl")) {
     if (value < 0 || value > 1) return fail(-1, "potrf_impl must be 0 (blocked DMMA sweep) or 1 (rank-1 sweep)");
     p->potrf_impl = (int)value;
@@ -1254,6 +1306,7 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "path")) return p->last_path ? p->last_path : choose_path(p);
   if (!strcmp(key, "launches")) return p->launches;
   if (!strcmp(key, "wave_walkers")) return p->wave_cur;
+  if (!strcmp(key, "tiled_impl")) return use_dag(p) ? 2 : 1;
   if (!strcmp(key, "n_pad")) return p->n_pad;
   if (!strcmp(key, "panel_tiles")) return effective_panel(p);
   if (!strcmp(key, "small_n_max")) return SMALL_N_MAX;
@@ -1292,7 +1345,8 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "workspace_bytes")) {
     int64_t s = 0;
     DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
-                      &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter, &p->midws};
+                      &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter, &p->midws,
+                      &p->zcols, &p->rowdone};
     for (DevBuf* b : bufs) s += (int64_t)b->bytes;
     return s;
   }
@@ -1363,6 +1417,56 @@ static double time_peak(int variant, int iters) {
     if (variant == 0) flops = 2.0 * 16 * 8 * 16 * 8.0 * iters * (256 / 32) * blocks;
     else flops = 2.0 * 16.0 * iters * 256 * blocks;
     const double rate = flops / (ms * 1e-3);
+    if (rep > 0) best = std::max(best, rate);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return best;
+}
+
+// Covariance-evaluation rate: every thread keeps 8 independent evaluations of k(d) in flight (the ILP the
+// factorisation kernels use), 16 warps per SM.  bench.py turns the rate into the cost of one matrix entry in
+// FP64 flop-equivalents (vector-pipe peak / rate) for the small-N roofline.
+__global__ void __launch_bounds__(512) cov_rate_kernel(CovParams cp, int iters, double* sink) {
+  double d[8], d2[8], o[8], acc = 0.0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) d[e] = 0.37 * (threadIdx.x + 1) + 1.3 * e + 1e-3 * blockIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      d[e] += 0.0131;
+      d2[e] = d[e] * d[e];
+    }
+    cov_from_dist_n<8>(cp, d, d2, o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += o[e];
+  }
+  if (acc == 123.456) sink[0] = acc;
+}
+
+extern "C" double mrv_cov_eval_rate(int device, int kernel_id, int kernel_variant, const double* hp, int nh) {
+  if (require_device(device)) return -1.0;
+  if (!hp || kernel_nh(kernel_id) < 0 || nh != kernel_nh(kernel_id)) return -1.0;
+  const CovParams cp = make_cov_params(kernel_id, kernel_variant, hp);
+  double* sink = nullptr;
+  if (cudaMalloc((void**)&sink, 8) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const int blocks = 148 * 4, iters = 2000;
+  double best = -1.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0);
+    cov_rate_kernel<<<blocks, 512>>>(cp, iters, sink);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) {
+      best = -1.0;
+      break;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double rate = 8.0 * iters * 512.0 * blocks / (ms * 1e-3);
     if (rep > 0) best = std::max(best, rate);
   }
   cudaEventDestroy(e0);

@@ -28,7 +28,6 @@
 #define SLICE_ELEMS (TILE * KSLICE)       // 2048 doubles = 16 KiB
 #define SLICES_PER_TILE (TILE / KSLICE)   // 8
 #define GEMM_THREADS 256
-#define GEMM_STAGES 3
 
 __host__ __device__ __forceinline__ size_t tile_index(int i, int j) { return (size_t)i * (i + 1) / 2 + j; }
 __host__ __device__ __forceinline__ int tile_off(int r, int c) {
@@ -56,14 +55,6 @@ __device__ __forceinline__ void dmma_1684(double (&d)[4], double a0, double a1, 
       : "+d"(d[0]), "+d"(d[1]), "+d"(d[2]), "+d"(d[3])
       : "d"(a0), "d"(a1), "d"(b0));
 }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ------------------------------------------------------------------------------------------------
 // Covariance value of global element (gi, gj) of the padded matrix.
@@ -565,10 +556,9 @@ potrf_tile_blk_kernel(int k, int N, double* __restrict__ Abase, size_t walker_st
 // ------------------------------------------------------------------------------------------------
 // DMMA tile GEMM: acc(128x128) = sum over operand tile pairs of A_p * B_p^T, K = 128 per pair.
 // 8 warps as 2 (m) x 4 (n): warp tile 64 x 32 = 4 m16-fragments x 4 n8-fragments.
-// 3-stage cp.async pipeline over k16 slices (16 KiB of A + 16 KiB of B per stage).
+// 4-stage bulk-copy / mbarrier ring over k16 slices (16 KiB of A + 16 KiB of B per stage).
 // ------------------------------------------------------------------------------------------------
 #define GEMM_STAGE_DOUBLES (2 * SLICE_ELEMS)
-#define GEMM_SMEM_BYTES ((size_t)GEMM_STAGES * GEMM_STAGE_DOUBLES * sizeof(double) + (2 * TILE + 4 * TILE + TILE) * sizeof(double))
 
 enum { GEMM_TRSM = 0, GEMM_UPDATE = 1 };
 
@@ -594,17 +584,6 @@ struct GemmArgs {
   int ldr;
   const double* zbuf;  // [wave, 128]
 };
-
-__device__ __forceinline__ void load_slice(double* stage, const double* __restrict__ Asrc,
-                                           const double* __restrict__ Bsrc, int tid) {
-  // 2048 doubles each; 256 threads x 4 x 16 B per operand
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int off = (j * 256 + tid) * 2;
-    cp_async16(stage + off, Asrc + off);
-    cp_async16(stage + SLICE_ELEMS + off, Bsrc + off);
-  }
-}
 
 // ---- mbarrier / bulk-copy (TMA engine, 1-D) primitives -------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -671,17 +650,14 @@ __device__ __forceinline__ void decode_update_tile(const GemmArgs& g, int x, int
   ti = tj = g.nt - 1;  // unreachable for a correctly sized grid
 }
 
-// One kernel body, two operand-feed variants:
-//   TMA = true : one elected lane streams the k16 operand slices with
-//                1-D bulk copies (cp.async.bulk, the TMA engine) into a 4-stage ring guarded by
-//                full/empty mbarriers; the 8 consumer warps never meet at a CTA-wide barrier and
-//                fetch the first fragments of slice q+1 while the last MMAs of slice q issue.
-//   TMA = false: all 256 threads issue 16-byte cp.async (LDGSTS) into a 3-stage ring with one
-//                __syncthreads per slice (kept as an A/B reference, option "gemm_impl" = 1).
-template <bool TMA>
-__global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm_tile_kernel(GemmArgs g) {
+// Operand feed: one elected lane streams the k16 operand slices with 1-D bulk copies (cp.async.bulk, the TMA
+// engine) into a 4-stage ring guarded by full/empty mbarriers; the 8 consumer warps never meet at a CTA-wide
+// barrier and fetch the first fragments of slice q+1 while the last MMAs of slice q issue.  (A 16-byte cp.async
+// ring with one __syncthreads per slice and a persistent multi-tile variant were measured 25 % / 0-4 % slower
+// in round 1 and removed.)
+__global__ void __launch_bounds__(GEMM_TMA_THREADS, 1) gemm_tile_kernel(GemmArgs g) {
   extern __shared__ double smem[];
-  constexpr int NST = TMA ? GEMM_TMA_STAGES : GEMM_STAGES;
+  constexpr int NST = GEMM_TMA_STAGES;
   double* stages = smem;
   double* tis = smem + NST * GEMM_STAGE_DOUBLES;  // 128: t of the tile rows
   double* tjs = tis + TILE;                       // 128: t of the tile cols
@@ -725,7 +701,7 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
     return Aw + tix * TILE_ELEMS + s * SLICE_ELEMS;
   };
 
-  if (TMA) {
+  {
     if (tid == 0) {
       for (int s = 0; s < GEMM_TMA_STAGES; ++s) {
         mbar_init(&full_bar[s], 1);   // one arrive (the producer's expect_tx) + 32 KiB of bytes
@@ -745,12 +721,6 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
         bulk_g2s(dst, a_src(q), SLICE_ELEMS * sizeof(double), &full_bar[q]);
         bulk_g2s(dst + SLICE_ELEMS, b_src(q), SLICE_ELEMS * sizeof(double), &full_bar[q]);
       }
-    }
-  } else {
-#pragma unroll
-    for (int s = 0; s < GEMM_STAGES - 1; ++s) {
-      if (s < nslices) load_slice(stages + s * GEMM_STAGE_DOUBLES, a_src(s), b_src(s), tid);
-      cp_async_commit();
     }
   }
 
@@ -833,7 +803,7 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
   const int a_lane = ((wm * 8) << 5) + lane;
   const int b_lane = ((wn * 4) << 5) + lane;
   double af[2][8], bf[2][4];
-  if (TMA) {
+  {
     mbar_wait(&full_bar[0], 0u);
     const double* As = stages + a_lane;
     const double* Bs = stages + SLICE_ELEMS + b_lane;
@@ -844,7 +814,7 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
   }
   for (int q = 0; q < nslices; ++q) {
     const int st = q % NST;
-    if (TMA) {
+    {
       // refill: slice q+2 goes into the stage consumed two iterations ago (one full iteration of
       // slack, so the wait on its empty barrier is normally already satisfied)
       const int qn = q + 2;
@@ -858,21 +828,8 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
       }
       __syncwarp();
     }
-    if (!TMA) {
-      cp_async_wait<GEMM_STAGES - 2>();
-      __syncthreads();
-      const int qn = q + GEMM_STAGES - 1;
-      if (qn < nslices) load_slice(stages + (qn % GEMM_STAGES) * GEMM_STAGE_DOUBLES, a_src(qn), b_src(qn), tid);
-      cp_async_commit();
-    }
     const double* As = stages + st * GEMM_STAGE_DOUBLES + a_lane;
     const double* Bs = stages + st * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
-    if (!TMA) {
-#pragma unroll
-      for (int v = 0; v < 8; ++v) af[0][v] = As[v << 5];
-#pragma unroll
-      for (int v = 0; v < 4; ++v) bf[0][v] = Bs[v << 5];
-    }
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const int cur = kk & 1, nxt = cur ^ 1;
@@ -881,7 +838,7 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
         for (int v = 0; v < 8; ++v) af[nxt][v] = As[(((kk + 1) * 16 + v) << 5)];
 #pragma unroll
         for (int v = 0; v < 4; ++v) bf[nxt][v] = Bs[(((kk + 1) * 16 + v) << 5)];
-      } else if (TMA && q + 1 < nslices) {
+      } else if (q + 1 < nslices) {
         // first fragments of the next slice (its stage was filled by the producer long ago)
         const int sn = (q + 1) % NST;
         mbar_wait(&full_bar[sn], (unsigned)(((q + 1) / NST) & 1));
@@ -899,13 +856,10 @@ __global__ void __launch_bounds__(TMA ? GEMM_TMA_THREADS : GEMM_THREADS, 1) gemm
           for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
       }
     }
-    if (TMA) {
-      // this warp has read everything it needs from stage `st`: hand it back to the producer
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[st]);
-    }
+    // this warp has read everything it needs from stage `st`: hand it back to the producer
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[st]);
   }
-  if (!TMA) cp_async_wait<0>();
 
   // epilogue ------------------------------------------------------------------------------------
   // element (R, C): R = wm*64 + mi*16 + gq + 8*v1, C = wn*32 + ni*8 + 2*tig + v0
@@ -969,13 +923,15 @@ __global__ void finalize_logl_kernel(ProblemDesc D, int W, const double* __restr
                                      const double* __restrict__ phys, const double* __restrict__ acc_logdet,
                                      const double* __restrict__ acc_quad, const int* __restrict__ nonfinite,
                                      const int* __restrict__ fact_status, double* __restrict__ logl_out,
-                                     int* __restrict__ status_out, double* __restrict__ logdet_out) {
+                                     int* __restrict__ status_out, double* __restrict__ logdet_out,
+                                     const int* __restrict__ abort_flag) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= W) return;
   double v = -((double)D.N / 2.0) * log(2.0 * MRV_PI) - 0.5 * acc_logdet[w] - 0.5 * acc_quad[w];
   v = add_priors(D, hp + (size_t)w * D.nh, phys + (size_t)w * D.nm, v);
   int st = fact_status[w];
   if (nonfinite[w]) st = -1;
+  if (abort_flag != nullptr && *abort_flag != 0) st = MRV_STATUS_INTERNAL;   // the dataflow kernel gave up on a dependency
   logl_out[w] = v;
   status_out[w] = st;
   if (logdet_out != nullptr) logdet_out[w] = acc_logdet[w];

@@ -10,6 +10,7 @@
 #define MRV_MAX_OPS 16
 #define MRV_MAX_MODPAR 48
 #define MRV_MAX_PRIORS 48
+#define MRV_STATUS_INTERNAL (-3)   // per-walker status: internal error (a dataflow dependency never arrived); never from valid input
 
 struct ModelOp {
   int type;

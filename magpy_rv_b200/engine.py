@@ -225,6 +225,9 @@ def raise_for_status(status):
         return
     w = int(bad[0])
     s = int(status[w])
+    if s == -3:
+        raise RuntimeError("magpy_rv_b200 internal error: the dataflow factorisation kernel gave up waiting for a tile "
+                           "dependency (walker %d); no result was produced" % w)
     if s > 0:
         raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite (walker %d)" % (s, w))
     raise ValueError("array must not contain infs or NaNs (walker %d)" % w)

@@ -12,6 +12,11 @@ Outputs (all small):
     tests/golden/cov_cases.npz       compute_covmatrix outputs (square, rectangular, as-coded Matern5)
     tests/golden/chain_C*.npz        seeded run_MCMC chains (random.seed(s); np.random.seed(s))
     tests/golden/predict_cases.npz   GPLikelihood.predict means / std / full covariances
+    tests/golden/big_cases.json      LogL scalars at the benchmark sizes (group "big"; "big16k" adds N = 16384):
+                                     C5 QuasiPer N = 8192 / 16384 one walker, C4 at N = 4096 with two Offsets and
+                                     Uniform / Jeffrey / Gaussian priors (2 walkers), C4M textbook Matern 5/2 at
+                                     N = 4096 (NumPy restatement through the same slogdet / cho_solve, F1).  Inputs
+                                     are regenerated from workloads.make_config (seeded); checksums guard them.
 """
 import contextlib
 import io
@@ -297,6 +302,40 @@ def make_predict(ref):
     np.savez_compressed(os.path.join(GOLD, "predict_cases.npz"), **out)
 
 
+def _checksum(cfg, rows):
+    return float(np.sum(cfg["t"]) + np.sum(cfg["y"]) + np.sum(cfg["yerr"]) + np.sum(cfg["hp"][rows]) + np.sum(cfg["modpar"][rows]))
+
+
+def make_big(ref, with_16k=False):
+    """Reference LogL at the sizes bench.py runs (parity above N = 4096 was only checked by scaling
+    identities).  One evaluation at N = 8192 takes ~1 min here, at N = 16384 ~6 min and ~15 GiB."""
+    import time
+    import workloads
+    from oracle import logl_port as port
+    path = os.path.join(GOLD, "big_cases.json")
+    out = json.load(open(path)) if os.path.exists(path) else {}
+    plan = [("c4_4096", "C4", 4096, [0, 1], "reference"), ("c4m_4096", "C4M", 4096, [0, 1], "port_textbook_matern5"),
+            ("c5_8192", "C5", 8192, [1], "reference")]
+    if with_16k:
+        plan = [("c5_16384", "C5", 16384, [1], "reference")]
+    for key, name, N, rows, how in plan:
+        cfg = workloads.make_config(name, W=2, N=N)
+        prior_list = [ref.par.pri_create(a, b, [d[x] for x in d]) for a, b, d in cfg["prior_list"]]
+        vals = []
+        t0 = time.time()
+        for w in rows:
+            if how == "reference":
+                v, _ = ref_logl_walker(ref, cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["hp"][w], cfg["model_list"],
+                                       cfg["modpar"][w], prior_list, cfg["flags"])
+            else:
+                v = port.logL_one(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["hp"][w], cfg["model_list"],
+                                  cfg["modpar"][w], cfg["prior_list"], cfg["flags"], textbook_matern5=True)
+            vals.append(float(v))
+        out[key] = dict(config=name, N=N, rows=rows, logL=vals, source=how, checksum=_checksum(cfg, rows))
+        print("big %-10s N=%5d rows=%s logL=%s  (%.1f s)" % (key, N, rows, vals, time.time() - t0))
+        json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+
+
 def main(argv):
     groups = set(argv) or {"kat", "cases", "cov", "chains", "predict", "options"}
     os.makedirs(GOLD, exist_ok=True)
@@ -313,6 +352,10 @@ def main(argv):
         make_predict(ref)
     if "options" in groups:
         make_chain_options(ref)
+    if "big" in groups:
+        make_big(ref)
+    if "big16k" in groups:
+        make_big(ref, with_16k=True)
 
 
 if __name__ == "__main__":

@@ -1,15 +1,17 @@
 """Import the UNMODIFIED reference package under matplotlib/seaborn stubs.
 
 TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  The reference lives at /root/reference (read
-only, build container only).  ``load()`` returns a namespace with the reference modules or raises
-``ReferenceUnavailable`` when the tree is absent (e.g. on the GPU box).
+only, build container only); ``oracle/stage_ref.py`` installs its unmodified wheel under
+``oracle/_ref/`` (git-ignored, travels to the GPU box with the snapshot).  ``load()`` returns a
+namespace with the reference modules from whichever of the two is present, or raises
+``ReferenceUnavailable``.
 """
 import importlib
 import os
 import sys
 import types
 
-REF_SRC_CANDIDATES = ("/root/reference/src",)
+REF_SRC_CANDIDATES = ("/root/reference/src", os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref"))
 
 
 class ReferenceUnavailable(RuntimeError):
@@ -33,7 +35,7 @@ def load():
     """Return a SimpleNamespace(par, ker, mod, gp, mcmc, mcmcx, aux) of reference modules."""
     src = next((p for p in REF_SRC_CANDIDATES if os.path.isdir(os.path.join(p, "magpy_rv"))), None)
     if src is None:
-        raise ReferenceUnavailable("reference tree not found (expected /root/reference/src)")
+        raise ReferenceUnavailable("reference package not found (expected /root/reference/src or oracle/_ref)")
     # gp_likelihood.py:14 and mcmc.py:19-20 import matplotlib.pyplot / seaborn at module top;
     # neither is installed here and neither is touched unless plotting is requested.
     for name in ("matplotlib", "matplotlib.pyplot", "seaborn"):

@@ -286,6 +286,82 @@ def test_blocked_path_invariances_and_large_n():
     prob.close()
 
 
+def test_big_goldens_from_the_reference():
+    """LogL at the sizes bench.py runs, against scalars the REAL reference produced in the build container
+    (oracle/make_golden.py big / big16k -> tests/golden/big_cases.json): C5 QuasiPer at N = 8192 and 16384 (one walker,
+    LU slogdet + cho_solve, gp_likelihood.py:265-275), C4 at its named N = 4096 with two Offsets and Uniform / Jeffrey /
+    Gaussian priors, and C4M = textbook Matern 5/2 at N = 4096 (NumPy restatement through the same slogdet / cho_solve,
+    since the reference's as-coded Matern 5/2 is not positive definite)."""
+    big = json.load(open(os.path.join(GOLD, "big_cases.json")))
+    assert set(big) >= {"c4_4096", "c4m_4096", "c5_8192", "c5_16384"}
+    for key in ("c4_4096", "c4m_4096", "c5_8192", "c5_16384"):
+        g = big[key]
+        cfg = workloads.make_config(g["config"], W=2, N=g["N"])
+        rows = g["rows"]
+        chk = float(np.sum(cfg["t"]) + np.sum(cfg["y"]) + np.sum(cfg["yerr"]) + np.sum(cfg["hp"][rows]) + np.sum(cfg["modpar"][rows]))
+        assert abs(chk - g["checksum"]) <= 1e-12 * abs(g["checksum"]), "workload generator drifted from the golden inputs"
+        prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["model_list"], cfg["prior_list"],
+                                        flags=cfg["flags"], kernel_variant=cfg["kernel_variant"])
+        got, st = prob.logl(cfg["hp"][rows], cfg["modpar"][rows])
+        err = relerr(got, g["logL"])
+        print("%s N=%d path=%d: max rel err vs %s = %.2e" % (key, g["N"], prob.info("path"), g["source"], err))
+        assert np.all(st == 0) and err < RTOL
+        prob.close()
+
+
+def test_non_default_kernel_variants_match_goldens():
+    """Every code path reachable through mrv_set_option is exercised against the reference goldens: the rank-1
+    diagonal-tile kernel (potrf_impl = 1, also the rank-1 fused small-N kernel), two-level panels (panel_inner), plain
+    (non-streaming) C stores, forced look-ahead / sub-streams and the dataflow / launch-per-column variants of the tiled
+    path (option "tiled_impl")."""
+    names = ("size_256", "size_500", "size_1000_exps", "combo", "kern_QuasiPer")
+    for case in [c for c in CASES if c["name"] in names]:
+        for opts in ({"potrf_impl": 1}, {"panel_tiles": 4, "panel_inner": 2}, {"panel_tiles": 3, "panel_inner": 1},
+                     {"cs_store": 0}, {"lookahead": 2, "substreams": 2}, {"substreams": 3, "lookahead": 0},
+                     {"tiled_impl": 1}, {"tiled_impl": 2}):
+            prob = make_problem(case)
+            prob.set_option("path", 2)
+            for k, v in opts.items():
+                prob.set_option(k, v)
+            got, st = prob.logl(case["hp"], case["modpar"], to_ecc=True)
+            assert np.all(st == 0) and relerr(got, case["logL"]) < RTOL, (case["name"], opts, relerr(got, case["logL"]))
+            prob.close()
+        if case["N"] <= 144:      # rank-1 variant of the fused shared-memory kernel
+            prob = make_problem(case)
+            prob.set_option("path", 1)
+            prob.set_option("potrf_impl", 1)
+            got, st = prob.logl(case["hp"], case["modpar"], to_ecc=True)
+            assert np.all(st == 0) and relerr(got, case["logL"]) < RTOL
+            prob.close()
+
+
+@pytest.mark.parametrize("name,N,W", [("C5", 700, 40), ("C3", 500, 300), ("C4", 1300, 9), ("C5", 2100, 5), ("C4M", 1024, 3)])
+def test_dataflow_kernel_is_bitwise_the_launch_per_column_path(name, N, W):
+    """The persistent dataflow kernel (csrc/dag.cuh, tiled_impl = 2) sums every element in the order of the
+    launch-per-column loop (tiled_impl = 1): log L and status must be bitwise identical, for ensembles larger and smaller
+    than the number of SMs, with mean models / priors, padding (N not a multiple of 128) and several waves."""
+    cfg = workloads.make_config(name, W=W, N=N)
+    out = {}
+    for impl in (1, 2):
+        prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["model_list"], cfg["prior_list"],
+                                        flags=cfg["flags"], kernel_variant=cfg["kernel_variant"])
+        prob.set_option("path", 2)
+        prob.set_option("tiled_impl", impl)
+        out[impl] = prob.logl(cfg["hp"], cfg["modpar"])
+        assert prob.info("tiled_impl") == impl
+        if impl == 2:
+            prob.set_option("wave_walkers", max(1, W // 3))          # several waves through the same workspace
+            again = prob.logl(cfg["hp"], cfg["modpar"])
+            np.testing.assert_array_equal(again[0], out[2][0])
+        prob.close()
+    assert np.all(out[1][1] == 0)
+    np.testing.assert_array_equal(out[1][0], out[2][0])
+    np.testing.assert_array_equal(out[1][1], out[2][1])
+    want = port.logL_batch(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["hp"][:2], cfg["model_list"], cfg["modpar"][:2],
+                           cfg["prior_list"], cfg["flags"], textbook_matern5=bool(cfg["kernel_variant"]))
+    assert relerr(out[2][0][:2], want) < RTOL
+
+
 def test_streamed_panel_path_persistent_slots():
     """More walkers than resident CTAs on the one-CTA-per-walker path (N = 200: two 8-warp CTAs per SM;
     N = 330: one 16-warp CTA per SM): every slot's workspace and barrier ring is reused across walkers;
@@ -394,14 +470,34 @@ def test_predict_matches_reference():
             xp = g["xpred_" + gname]
             want_mean, want_std, want_cov = g["%s__%s__mean" % (kk, gname)], g["%s__%s__std" % (kk, gname)], g["%s__%s__cov" % (kk, gname)]
             scale = max(1.0, float(np.max(np.abs(want_cov))))
-            mean, std = gp.GPLikelihood(x, y, err, hp, kern, model_y, mp).predict(xp)
+            with np.errstate(invalid="ignore"):      # np.sqrt of a negative variance: NaN + RuntimeWarning, as in the reference
+                mean, std = gp.GPLikelihood(x, y, err, hp, kern, model_y, mp).predict(xp)
             mean2, cov = gp.GPLikelihood(x, y, err, hp, kern, model_y, mp).predict(xp, FullCov=True)
             np.testing.assert_allclose(mean, want_mean, rtol=1e-9, atol=1e-9)
             np.testing.assert_allclose(mean2, want_mean, rtol=1e-9, atol=1e-9)
             np.testing.assert_allclose(cov, want_cov, rtol=1e-8, atol=1e-9 * scale)
-            safe = np.diag(want_cov) > 1e-6 * scale          # sqrt of a round-off-level variance is noise
-            np.testing.assert_allclose(std[safe], want_std[safe], rtol=1e-6)
             assert mean.shape == want_mean.shape and std.shape == want_std.shape and cov.shape == want_cov.shape
+            # The reference returns NaN standard deviations (gp_likelihood.py:478, sqrt of a negative variance) in two
+            # situations, and so do we:
+            #  (i) a genuinely negative variance -- one prediction point with a jitter kernel: the 1 x 1 Kss block is
+            #      "square" and receives jit^2, Ks does not (kernels.py:780-783) -> NaN at exactly the same indices;
+            #  (ii) xpred == x: the whole predictive covariance is round-off (|v| ~ 1e-14) and the SIGN of each entry is
+            #      noise, in the reference (23-31 of 60 entries NaN) as here -> no index-wise statement is possible;
+            #      what holds is that our variance is also round-off there and that NaN appears iff OUR variance < 0.
+            var_ref, var = np.diag(want_cov), np.diag(cov)
+            floor = 1e-9 * scale
+            real = np.abs(var_ref) > floor
+            np.testing.assert_array_equal(np.isnan(std[real]), np.isnan(want_std[real]))
+            np.testing.assert_array_equal(np.isnan(std[real]), var_ref[real] < 0)
+            ok = real & ~np.isnan(want_std)
+            np.testing.assert_allclose(std[ok], want_std[ok], rtol=1e-6)
+            assert np.all(np.abs(var[~real]) <= 2 * floor)
+            tiny = ~real
+            assert np.all(np.isnan(std[tiny]) | (std[tiny] <= np.sqrt(2 * floor)))
+            if gname == "single" and kern in ("JitterQuasiPer", "Matern3/2"):
+                assert np.isnan(want_std).all() and np.isnan(std).all()          # case (i) is really exercised
+            if gname == "same":
+                assert np.isnan(want_std).any() and not real.any()               # case (ii) is really exercised
 
 
 def test_solve_batch_blocked_and_fused_agree():
@@ -474,13 +570,14 @@ def test_status_words_on_both_paths():
     status -1, on the fused, the streamed-panel and the blocked path; healthy walkers in the same batch
     unaffected."""
     rng = np.random.default_rng(5)
-    for N, path in ((60, 0), (300, 0), (300, 2), (60, 3), (700, 0)):
+    for N, path, impl in ((60, 0, 0), (300, 0, 0), (300, 2, 1), (300, 2, 2), (60, 3, 0), (700, 0, 1), (700, 0, 2)):
         t = np.sort(rng.uniform(0, 100, N))
         y = rng.normal(0, 1, N)
         e = rng.uniform(0.5, 1.0, N)
         # as-coded Matern 5/2 is indefinite (SURVEY.md F1)
         prob = engine.LikelihoodProblem(t, y, e, "Matern5/2")
         prob.set_option("path", path)
+        prob.set_option("tiled_impl", impl)
         _, st = prob.logl([[5.0, 12.0], [4.0, 9.0]], np.zeros((2, 1)))
         K = port.compute_kernel("Matern5/2", [5.0, 12.0], t, t, t, e)
         with pytest.raises(np.linalg.LinAlgError):
@@ -490,6 +587,7 @@ def test_status_words_on_both_paths():
         # NaN hyper-parameter in one walker only
         prob = engine.LikelihoodProblem(t, y, e, "QuasiPer")
         prob.set_option("path", path)
+        prob.set_option("tiled_impl", impl)
         hp = np.array([[20., .5, 30., 4.], [np.nan, .5, 30., 4.], [21., .6, 28., 3.]])
         got, st = prob.logl(hp, np.zeros((3, 1)))
         want = port.logL_batch(t, y, e, "QuasiPer", hp[[0, 2]], ["no"], np.zeros((2, 1)))

@@ -392,13 +392,20 @@ def test_bench_reference_arm_prints_the_contract_line():
     import subprocess
     import sys
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--npoints", "200",
-                          "--walkers-per-gpu", "16", "--steps", "1", "--warmup", "1", "--cpu-budget-s", "1"],
+                          "--walkers-per-gpu", "16", "--steps", "2", "--warmup", "1", "--cpu-budget-s", "1", "--only-configs", "C1"],
                          capture_output=True, text=True, timeout=240, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "gp_logl_evals_per_sec" and line["unit"] == "evals/s"
-    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 1 and line["warmup"] == 1
+    assert line["higher_is_better"] is True and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] == 1
     assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # the staged unmodified reference (oracle/_ref) when present, else the oracle port
+    from oracle import ref_loader
+    assert line["cpu_baseline"]["kind"] == ("reference" if ref_loader.available() else "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["measured_at_full_size"] is True and line["ms_per_step"] > 0
+    c1 = line["configs"][0]
+    assert c1["label"] == "C1" and c1["value"] > 0 and c1["cpu_baseline"]["kind"] == line["cpu_baseline"]["kind"]
+    if ref_loader.available():
+        assert c1["run_mcmc"]["evals"] == 51 * 100 and c1["run_mcmc"]["evals_per_s"] > 0
     assert line["config"]["N"] == 200 and "workload" in line["config"] and line["gpu_launches"] == 0

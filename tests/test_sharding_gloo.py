@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 
 import workloads
 from magpy_rv_b200 import mcmc
-from magpy_rv_b200.sharding import ShardedEvaluator, partition
+from magpy_rv_b200.sharding import RankDesync, ShardedEvaluator, partition
 from oracle import logl_port as port
 
 
@@ -54,6 +54,18 @@ def _worker(rank, world, port_no, q):
         logl, status = ev.logl(cfg["hp"], cfg["modpar"])
         full, _ = _oracle_eval(cfg)(cfg["hp"], cfg["modpar"])
         ok = bool(np.array_equal(logl, full) and status.dtype == np.int32 and np.all(status == 0))
+
+        # ranks whose host RNG streams diverged generate different proposals: the checksum riding in the gathered
+        # record makes EVERY rank raise instead of stitching log L values of different proposals together
+        hp_bad = cfg["hp"].copy()
+        if rank == 1:
+            hp_bad[3, 1] += 1e-9
+        try:
+            ev.logl(hp_bad, cfg["modpar"])
+            raised = False
+        except RankDesync:
+            raised = True
+        ok = ok and raised
 
         # a rank tells its problem handle the size of the WHOLE ensemble (kernel selection must not depend on
         # the number of shards) before it evaluates its own block

@@ -17,9 +17,8 @@ for N, W in sizes:
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"])
     if path_opt:
         prob.set_option("path", path_opt)
-    for panel, impl in (((8, 0),) if N > 168 else ((1, 0),)):
+    for panel, impl in (((0, 0),) if N > 168 else ((1, 0),)):
         prob.set_option("panel_tiles", panel)
-        prob.set_option("gemm_impl", impl)
         prob.logl(cfg["hp"], cfg["modpar"])
         torch.cuda.synchronize()
         t0 = time.perf_counter()
