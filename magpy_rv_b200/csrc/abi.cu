@@ -40,7 +40,7 @@ static int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(-2, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
   } while (0)
 
-#define SMALL_N_MAX 168
+#define SMALL_N_MAX 166   // largest N whose (N + 1) x N matrix + 4 N point / residual doubles fit 227 KB of shared memory
 
 struct DevBuf {
   void* p = nullptr;
@@ -186,7 +186,7 @@ struct mrv_problem {
   // workspace
   DevBuf hp, modpar, model, logl, status;                      // host-API staging (hp holds hp | modpar, logl holds logL | status)
   PinBuf pin_in, pin_out;
-  DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter, midws, zcols, rowdone;
+  DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter, midws, zcols, rowdone, phase, cpar;
   int64_t wave_cur = 0;
   int64_t launches = 0;
   int last_path = 0;
@@ -259,8 +259,10 @@ static int fill_desc(ProblemDesc& D, int64_t N, int kernel_id, int variant, int 
   return 0;
 }
 
-static int upload(double** dst, const double* src, size_t n) {
-  CU(cudaMalloc((void**)dst, std::max<size_t>(n, 1) * sizeof(double)));
+static int upload(double** dst, const double* src, size_t n, size_t n_alloc = 0) {
+  n_alloc = std::max<size_t>(std::max(n, n_alloc), 1);   // n_alloc > n: zero padded (whole 128-point tiles can be copied)
+  CU(cudaMalloc((void**)dst, n_alloc * sizeof(double)));
+  if (n_alloc > n) CU(cudaMemset(*dst, 0, n_alloc * sizeof(double)));
   CU(cudaMemcpy(*dst, src, n * sizeof(double), cudaMemcpyHostToDevice));
   return 0;
 }
@@ -287,8 +289,9 @@ extern "C" int mrv_problem_create(mrv_problem** out, int device, const double* t
   }
   p->nt = (int)((N + TILE - 1) / TILE);
   p->n_pad = p->nt * TILE;
+  p->desc.t_ref = t[N / 2];   // phase origin of the periodic covariance terms: phases stay small for any time offset (BJD ...)
   int rc = 0;
-  if ((rc = upload(&p->d_t, t, N)) || (rc = upload(&p->d_y, y, N)) || (rc = upload(&p->d_yerr, yerr, N)) ||
+  if ((rc = upload(&p->d_t, t, N, p->n_pad)) || (rc = upload(&p->d_y, y, N)) || (rc = upload(&p->d_yerr, yerr, N)) ||
       (flags && (rc = upload(&p->d_flags, flags, N)))) {
     mrv_problem_destroy(p);
     return rc;
@@ -311,7 +314,7 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
   cudaFree(p->d_flags);
   DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
                     &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter, &p->midws,
-                    &p->zcols, &p->rowdone};
+                    &p->zcols, &p->rowdone, &p->phase, &p->cpar};
   for (DevBuf* b : bufs) b->release();
   p->pin_in.release();
   p->pin_out.release();
@@ -425,6 +428,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   g.t = p->d_t;
   g.yerr = p->d_yerr;
   g.hp_wave = hp_wave;
+  g.ph_wave = p->phase.as<double>() + (size_t)w0 * 2 * p->n_pad;
   g.resid = resid;
   g.ldr = p->n_pad;
   g.zbuf = zbuf;
@@ -469,7 +473,7 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   };
   p->prof.begin(CAT_GEN, st, 0.0, 0.0);
   gen_column_kernel<<<dim3(nt, (unsigned)B), 256, 0, st>>>(N, nt, 0, D.kernel_id, D.variant, D.nh, p->d_t, p->d_yerr,
-                                                            hp_wave, A, walker_stride);
+                                                            hp_wave, g.ph_wave, A, walker_stride);
   p->prof.end(st);
   p->launches++;
   if (p->mean_pending) CU(cudaStreamWaitEvent(st, p->ev_mean, 0));   // residuals are first read by the diagonal-tile kernel
@@ -565,9 +569,10 @@ static int run_wave_dag(mrv_problem* p, const double* d_hp, int64_t w0, int64_t 
   g.N = D.N;
   g.nt = nt;
   g.B = (int)B;
-  g.kernel_id = D.kernel_id;
-  g.variant = D.variant;
-  g.nh = D.nh;
+  {
+    const double hp0[MRV_MAX_HP] = {1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0};
+    g.kind = make_cov_params(D.kernel_id, D.variant, hp0).kind;
+  }
   const long long total = (long long)B * nt * (nt + 1) / 2;
   if (total > 0x7fffffffLL) return fail(-1, "wave of %lld walkers x %d tile columns has too many tile tasks", (long long)B, nt);
   g.total_tasks = (int)total;
@@ -575,7 +580,8 @@ static int run_wave_dag(mrv_problem* p, const double* d_hp, int64_t w0, int64_t 
   g.walker_stride = tile_index(nt - 1, nt - 1) * TILE_ELEMS + TILE_ELEMS;
   g.t = p->d_t;
   g.yerr = p->d_yerr;
-  g.hp_wave = d_hp + (size_t)w0 * D.nh;
+  g.ph_wave = p->phase.as<double>() + (size_t)w0 * 2 * p->n_pad;
+  g.cpar_wave = p->cpar.as<double>() + (size_t)w0 * 8;
   g.resid = p->resid.as<double>() + (size_t)w0 * p->n_pad;
   g.ldr = p->n_pad;
   g.zcols = p->zcols.as<double>();
@@ -724,6 +730,13 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
     CU(cudaMemsetAsync(p->counter.p, 0, 4 * sizeof(int), st));
   }
 
+  if ((rc = p->phase.ensure((size_t)W * 2 * p->n_pad * sizeof(double)))) return rc;
+  if ((rc = p->cpar.ensure((size_t)W * 8 * sizeof(double)))) return rc;
+  p->prof.begin(CAT_GEN, st, 0.0, 0.0);
+  phase_table_kernel<<<dim3((unsigned)std::min(8, (p->n_pad + 255) / 256), (unsigned)W), 256, 0, st>>>(
+      D.N, p->n_pad, D.t_ref, D.kernel_id, D.variant, D.nh, p->d_t, d_hp, p->phase.as<double>(), p->cpar.as<double>());
+  p->prof.end(st);
+  p->launches++;
   CU(cudaMemsetAsync(p->logdet.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->quad.p, 0, (size_t)W * sizeof(double), st));
   CU(cudaMemsetAsync(p->fstatus.p, 0, (size_t)W * sizeof(int), st));
@@ -1311,6 +1324,19 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "panel_tiles")) return effective_panel(p);
   if (!strcmp(key, "small_n_max")) return SMALL_N_MAX;
   if (!strcmp(key, "mid_n_max")) return MID_N_MAX;
+  if (!strncmp(key, "dag_t", 5)) {   // phase timers of the dataflow kernel (only with -DDAG_TIMING); index 16 resets
+    unsigned long long v[16];
+    cudaSetDevice(p->device);
+    if (cudaMemcpyFromSymbol(v, g_dag_timing, sizeof v) != cudaSuccess) return -1;
+    const int i = atoi(key + 5);
+    if (i < 0 || i > 16) return -1;
+    if (i == 16) {
+      memset(v, 0, sizeof v);
+      cudaMemcpyToSymbol(g_dag_timing, v, sizeof v);
+      return 0;
+    }
+    return (int64_t)v[i];
+  }
   if (!strncmp(key, "mid_t", 5)) {   // phase timers of the streamed-panel kernel (only with -DMID_TIMING); reading resets
     long long v[32];
     cudaSetDevice(p->device);
@@ -1346,7 +1372,7 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
     int64_t s = 0;
     DevBuf* bufs[] = {&p->hp, &p->modpar, &p->model, &p->logl, &p->status, &p->resid, &p->escratch, &p->phys,
                       &p->nonfinite, &p->logdet, &p->quad, &p->fstatus, &p->zbuf, &p->factor, &p->counter, &p->midws,
-                      &p->zcols, &p->rowdone};
+                      &p->zcols, &p->rowdone, &p->phase, &p->cpar};
     for (DevBuf* b : bufs) s += (int64_t)b->bytes;
     return s;
   }
@@ -1445,20 +1471,46 @@ __global__ void __launch_bounds__(512) cov_rate_kernel(CovParams cp, int iters, 
   if (acc == 123.456) sink[0] = acc;
 }
 
+// Same through the fast per-point evaluation the factorisation kernels use (cov_pair_n).
+template <bool LOCKSTEP>
+__global__ void __launch_bounds__(512) cov_pair_rate_kernel(CovParams cp, int iters, double* sink) {
+  double ti[8], ci[8], si[8], tj[8], cj[8], sj[8], o[8], acc = 0.0;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    ti[e] = 0.37 * (threadIdx.x + 1) + 1.3 * e + 1e-3 * blockIdx.x;
+    tj[e] = 0.11 * e;
+    cov_point_phase(cp, ti[e], ci[e], si[e]);
+    cov_point_phase(cp, tj[e], cj[e], sj[e]);
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      ti[e] += 0.0131;
+      ci[e] = fma(ci[e], 0.999999, 1e-7 * si[e]);   // keeps the inputs changing without leaving [-1, 1]
+    }
+    cov_pair_n<8, LOCKSTEP>(cp, ti, ci, si, tj, cj, sj, o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += o[e];
+  }
+  if (acc == 123.456) sink[0] = acc;
+}
+
 extern "C" double mrv_cov_eval_rate(int device, int kernel_id, int kernel_variant, const double* hp, int nh) {
   if (require_device(device)) return -1.0;
   if (!hp || kernel_nh(kernel_id) < 0 || nh != kernel_nh(kernel_id)) return -1.0;
-  const CovParams cp = make_cov_params(kernel_id, kernel_variant, hp);
+  const CovParams cp = make_cov_params(kernel_id, kernel_variant % 100, hp);   // variant + 100: the library-function form
   double* sink = nullptr;
   if (cudaMalloc((void**)&sink, 8) != cudaSuccess) return -1.0;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const int blocks = 148 * 4, iters = 2000;
+  const int blocks = 148, iters = 8000;   // one 16-warp block per SM for both forms (equal occupancy)
   double best = -1.0;
   for (int rep = 0; rep < 4; ++rep) {
     cudaEventRecord(e0);
-    cov_rate_kernel<<<blocks, 512>>>(cp, iters, sink);
+    if (kernel_variant >= 200) cov_pair_rate_kernel<true><<<blocks, 512>>>(cp, iters, sink);    // per-point form, lock-step exp (tile kernels)
+    else if (kernel_variant >= 100) cov_rate_kernel<<<blocks, 512>>>(cp, iters, sink);          // library sinpi / exp on distances
+    else cov_pair_rate_kernel<false><<<blocks, 512>>>(cp, iters, sink);                         // per-point form, library exp
     cudaEventRecord(e1);
     if (cudaEventSynchronize(e1) != cudaSuccess) {
       best = -1.0;

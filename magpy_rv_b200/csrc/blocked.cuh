@@ -57,29 +57,88 @@ __device__ __forceinline__ void dmma_1684(double (&d)[4], double a0, double a1, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Covariance value of global element (gi, gj) of the padded matrix.
+// Covariance fragments of the padded matrix, generated from per-point data in shared memory:
+// point i of an array `p` with stride `st` is (t, C, S) = (p[i], p[i + st], p[i + 2 st]) -- the time stamp and the
+// cosine / sine of its phase (common.cuh: cov_pair_n, cov_point_phase).
+// (deliberately not inlined: the callers have 8..16 unrolled sites and the covariance switch with its fp64 exp
+// expansions would otherwise be replicated at each of them)
 // ------------------------------------------------------------------------------------------------
-// (deliberately not inlined: the GEMM epilogue calls it from 64 unrolled sites and the covariance
-// switch with its fp64 sin/exp expansions would otherwise be replicated 64 times)
-__device__ __noinline__ double gen_element(const CovParams& cp, int N, int gi, int gj, double ti, double tj,
-                                           const double* __restrict__ yerr) {
-  if (gi < N && gj < N) return (gi == gj) ? cov_diag(cp, yerr[gi]) : cov_eval(cp, ti, tj);
-  return (gi == gj) ? 1.0 : 0.0;
-}
+struct Cov4 { double v0, v1, v2, v3; };
+struct Cov8 { double v0, v1, v2, v3, v4, v5, v6, v7; };
 
-// Four elements of one accumulator fragment at once: rows gi0, gi0+8; columns gj0, gj0+1 (order of
-// the DMMA accumulator registers c[0..3]).  One call site per fragment, ILP 4 inside.
-__device__ __noinline__ void gen_fragment4(const CovParams& cp, int N, int gi0, int gj0, double ti0, double ti1,
-                                           double tj0, double tj1, const double* __restrict__ yerr, double (&out)[4]) {
-  const double tis4[4] = {ti0, ti0, ti1, ti1}, tjs4[4] = {tj0, tj1, tj0, tj1};
-  double d[4], d2[4];
+// INTERIOR fragments (no diagonal element, nothing in the padding): everything by value and the result in
+// registers.  The general versions below take the output array by reference, which routes every value through
+// local memory and adds per-element diagonal / padding tests.  Almost every fragment is interior.
+// Accumulator order: rows R, R + 8 x columns C, C + 1 (then C + 8, C + 9 for the 8-entry form).
+__device__ __noinline__ Cov4 gen_interior4(int kind, double a2, double c1, double c2, double c3, const double* __restrict__ pr,
+                                           int sr, int R, const double* __restrict__ pc, int sc, int C) {
+  CovParams p;
+  p.kind = kind; p.a2 = a2; p.c1 = c1; p.c2 = c2; p.c3 = c3; p.jit2 = 0.0; p.cph = 0.0;
+  double ti[4], ci[4], si[4], tj[4], cj[4], sj[4], o[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const double dt = tis4[e] - tjs4[e];
-    d[e] = fabs(dt);
-    d2[e] = dt * dt;
+    const int r = R + 8 * (e >> 1), c = C + (e & 1);
+    ti[e] = pr[r]; ci[e] = pr[r + sr]; si[e] = pr[r + 2 * sr];
+    tj[e] = pc[c]; cj[e] = pc[c + sc]; sj[e] = pc[c + 2 * sc];
   }
-  cov_from_dist_n<4>(cp, d, d2, out);
+  cov_pair_n<4, true>(p, ti, ci, si, tj, cj, sj, o);
+  Cov4 r;
+  r.v0 = o[0]; r.v1 = o[1]; r.v2 = o[2]; r.v3 = o[3];
+  return r;
+}
+__device__ __noinline__ Cov8 gen_interior8(int kind, double a2, double c1, double c2, double c3, const double* __restrict__ pr,
+                                           int sr, int R, const double* __restrict__ pc, int sc, int C) {
+  CovParams p;
+  p.kind = kind; p.a2 = a2; p.c1 = c1; p.c2 = c2; p.c3 = c3; p.jit2 = 0.0; p.cph = 0.0;
+  double ti[8], ci[8], si[8], tj[8], cj[8], sj[8], o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int r = R + 8 * ((e >> 1) & 1), c = C + 8 * (e >> 2) + (e & 1);
+    ti[e] = pr[r]; ci[e] = pr[r + sr]; si[e] = pr[r + 2 * sr];
+    tj[e] = pc[c]; cj[e] = pc[c + sc]; sj[e] = pc[c + 2 * sc];
+  }
+  cov_pair_n<8, true>(p, ti, ci, si, tj, cj, sj, o);
+  Cov8 r;
+  r.v0 = o[0]; r.v1 = o[1]; r.v2 = o[2]; r.v3 = o[3]; r.v4 = o[4]; r.v5 = o[5]; r.v6 = o[6]; r.v7 = o[7];
+  return r;
+}
+
+// The same 8 interior entries INLINE for a kernel kind known at compile time, negated straight into two accumulator
+// fragments: no call, no switch, and the compiler interleaves the exp chains of neighbouring sites.  Used for the
+// QuasiPer kinds (every BASELINE configuration but the Matern one); values are bitwise those of gen_interior8.
+template <int KIND>
+__device__ __forceinline__ void gen_interior8_inline(const CovParams& cp, const double* __restrict__ pr, int R,
+                                                     const double* __restrict__ pc, int C, double (&f0)[4], double (&f1)[4]) {
+  CovParams p = cp;
+  p.kind = KIND;
+  double ti[8], ci[8], si[8], tj[8], cj[8], sj[8], o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int r = R + 8 * ((e >> 1) & 1), c = C + 8 * (e >> 2) + (e & 1);
+    ti[e] = pr[r]; ci[e] = pr[r + TILE]; si[e] = pr[r + 2 * TILE];
+    tj[e] = pc[c]; cj[e] = pc[c + TILE]; sj[e] = pc[c + 2 * TILE];
+  }
+  cov_pair_n<8, true>(p, ti, ci, si, tj, cj, sj, o);
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    f0[v] = -o[v];
+    f1[v] = -o[4 + v];
+  }
+}
+
+// General fragments: global element (gi0 + 8 (e >> 1), gj0 + (e & 1)) etc.; diagonal elements get cov_diag, elements
+// in the padding the identity.
+__device__ __noinline__ void gen_fragment4(const CovParams& cp, int N, int gi0, int gj0, const double* __restrict__ pr, int sr,
+                                           int R, const double* __restrict__ pc, int sc, int C,
+                                           const double* __restrict__ yerr, double (&out)[4]) {
+  double ti[4], ci[4], si[4], tj[4], cj[4], sj[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int r = R + 8 * (e >> 1), c = C + (e & 1);
+    ti[e] = pr[r]; ci[e] = pr[r + sr]; si[e] = pr[r + 2 * sr];
+    tj[e] = pc[c]; cj[e] = pc[c + sc]; sj[e] = pc[c + 2 * sc];
+  }
+  cov_pair_n<4, true>(cp, ti, ci, si, tj, cj, sj, out);
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const int gi = gi0 + 8 * (e >> 1), gj = gj0 + (e & 1);
@@ -87,62 +146,17 @@ __device__ __noinline__ void gen_fragment4(const CovParams& cp, int N, int gi0, 
     else if (gi == gj) out[e] = cov_diag(cp, yerr[gi]);
   }
 }
-
-// INTERIOR fragments (no diagonal element, nothing in the padding): everything by value and the result in
-// registers.  The general versions above / below take the output array by reference, which routes every
-// value through local memory and adds per-element diagonal / padding tests: measured 3.8 SM-clocks per
-// covariance evaluation in the streamed-panel kernel against 1.1 for the bare evaluation at the same
-// occupancy (tools/micro/gen.cu).  Almost every fragment is interior.
-struct Cov4 { double v0, v1, v2, v3; };
-struct Cov8 { double v0, v1, v2, v3, v4, v5, v6, v7; };
-__device__ __noinline__ Cov4 gen_interior4(int kind, double a2, double c1, double c2, double c3, double ti0, double ti1,
-                                           double tj0, double tj1) {
-  CovParams p;
-  p.kind = kind; p.a2 = a2; p.c1 = c1; p.c2 = c2; p.c3 = c3; p.jit2 = 0.0;
-  const double dt[4] = {ti0 - tj0, ti0 - tj1, ti1 - tj0, ti1 - tj1};
-  double d[4], d2[4], o[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    d[e] = fabs(dt[e]);
-    d2[e] = dt[e] * dt[e];
-  }
-  cov_from_dist_n<4>(p, d, d2, o);
-  Cov4 r;
-  r.v0 = o[0]; r.v1 = o[1]; r.v2 = o[2]; r.v3 = o[3];
-  return r;
-}
-__device__ __noinline__ Cov8 gen_interior8(int kind, double a2, double c1, double c2, double c3, double ti0, double ti1,
-                                           double tj0, double tj1, double tj8, double tj9) {
-  CovParams p;
-  p.kind = kind; p.a2 = a2; p.c1 = c1; p.c2 = c2; p.c3 = c3; p.jit2 = 0.0;
-  const double dt[8] = {ti0 - tj0, ti0 - tj1, ti1 - tj0, ti1 - tj1, ti0 - tj8, ti0 - tj9, ti1 - tj8, ti1 - tj9};
-  double d[8], d2[8], o[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    d[e] = fabs(dt[e]);
-    d2[e] = dt[e] * dt[e];
-  }
-  cov_from_dist_n<8>(p, d, d2, o);
-  Cov8 r;
-  r.v0 = o[0]; r.v1 = o[1]; r.v2 = o[2]; r.v3 = o[3]; r.v4 = o[4]; r.v5 = o[5]; r.v6 = o[6]; r.v7 = o[7];
-  return r;
-}
-
-// Two adjacent accumulator fragments (columns gj0, gj0+1 and gj0+8, gj0+9; rows gi0, gi0+8) in one call:
-// 8 independent exp / sin chains in flight per lane.  The GEMM runs 8 warps per SM, where 4 chains per
-// lane left the FP64 pipe waiting on its own latency during the first-touch generation.
-__device__ __noinline__ void gen_fragment8(const CovParams& cp, int N, int gi0, int gj0, double ti0, double ti1,
-                                           double tj0, double tj1, double tj8, double tj9,
+__device__ __noinline__ void gen_fragment8(const CovParams& cp, int N, int gi0, int gj0, const double* __restrict__ pr, int sr,
+                                           int R, const double* __restrict__ pc, int sc, int C,
                                            const double* __restrict__ yerr, double (&out)[8]) {
-  const double tjs[4] = {tj0, tj1, tj8, tj9};
-  double d[8], d2[8];
+  double ti[8], ci[8], si[8], tj[8], cj[8], sj[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const double dt = (((e >> 1) & 1) ? ti1 : ti0) - tjs[2 * (e >> 2) + (e & 1)];
-    d[e] = fabs(dt);
-    d2[e] = dt * dt;
+    const int r = R + 8 * ((e >> 1) & 1), c = C + 8 * (e >> 2) + (e & 1);
+    ti[e] = pr[r]; ci[e] = pr[r + sr]; si[e] = pr[r + 2 * sr];
+    tj[e] = pc[c]; cj[e] = pc[c + sc]; sj[e] = pc[c + 2 * sc];
   }
-  cov_from_dist_n<8>(cp, d, d2, out);
+  cov_pair_n<8, true>(cp, ti, ci, si, tj, cj, sj, out);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int gi = gi0 + 8 * ((e >> 1) & 1), gj = gj0 + 8 * (e >> 2) + (e & 1);
@@ -151,19 +165,49 @@ __device__ __noinline__ void gen_fragment8(const CovParams& cp, int N, int gi0, 
   }
 }
 
+// Per-walker phase table for the tiled paths: ph[w][0][i] = cospi(2 u), ph[w][1][i] = sinpi(2 u), u = cph_w (t_i - t_ref);
+// N sincospi per walker.  Padding points get (1, 0); they are never used (padding entries are the identity).
+// Also writes the walker's covariance constants (a2, c1, c2, c3, jit2, 0, 0, 0) for the dataflow kernel, which
+// fetches them with the points instead of recomputing the reciprocals in every tile task.
+__global__ void __launch_bounds__(256)
+phase_table_kernel(int N, int n_pad, double t_ref, int kernel_id, int variant, int nh, const double* __restrict__ t,
+                   const double* __restrict__ hp_all, double* __restrict__ ph, double* __restrict__ cpar) {
+  const int w = blockIdx.y;
+  const CovParams cp = make_cov_params(kernel_id, variant, hp_all + (size_t)w * nh);
+  if (blockIdx.x == 0 && threadIdx.x < 8) {
+    const double v[8] = {cp.a2, cp.c1, cp.c2, cp.c3, cp.jit2, 0.0, 0.0, 0.0};
+    cpar[(size_t)w * 8 + threadIdx.x] = v[threadIdx.x];
+  }
+  double* dst = ph + (size_t)w * 2 * n_pad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+    double c = 1.0, s = 0.0;
+    if (i < N) cov_point_phase(cp, t[i] - t_ref, c, s);
+    dst[i] = c;
+    dst[n_pad + i] = s;
+  }
+}
+
+// Points of one tile (128 consecutive indices from `first`) into shared memory: p[0..127] = t, p[128..] = C, p[256..] = S.
+__device__ __forceinline__ void load_tile_points(double* p, int first, int lane128, int N, int n_pad, const double* __restrict__ t,
+                                                 const double* __restrict__ ph_w) {
+  const int gi = first + lane128;
+  p[lane128] = gi < N ? t[gi] : 0.0;
+  p[TILE + lane128] = ph_w[gi];
+  p[2 * TILE + lane128] = ph_w[n_pad + gi];
+}
+
 // Write the covariance tiles of tile-column `col` for every walker of the wave (needed before
 // potrf/trsm touch a column that no UPDATE has generated yet, i.e. column 0).
 __global__ void __launch_bounds__(256)
 gen_column_kernel(int N, int nt, int col, int kernel_id, int variant, int nh, const double* __restrict__ t,
-                  const double* __restrict__ yerr, const double* __restrict__ hp_wave, double* __restrict__ Abase,
-                  size_t walker_stride) {
-  __shared__ double ti_s[TILE], tj_s[TILE];
+                  const double* __restrict__ yerr, const double* __restrict__ hp_wave, const double* __restrict__ ph_wave,
+                  double* __restrict__ Abase, size_t walker_stride) {
+  __shared__ double pi_s[3 * TILE], pj_s[3 * TILE];
   const int i = col + blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-  if (tid < TILE) {
-    const int gi = i * TILE + tid, gj = col * TILE + tid;
-    ti_s[tid] = gi < N ? t[gi] : 0.0;
-    tj_s[tid] = gj < N ? t[gj] : 0.0;
-  }
+  const int n_pad = nt * TILE;
+  const double* ph_w = ph_wave + (size_t)b * 2 * n_pad;
+  if (tid < TILE) load_tile_points(pi_s, i * TILE, tid, N, n_pad, t, ph_w);
+  else load_tile_points(pj_s, col * TILE, tid - TILE, N, n_pad, t, ph_w);
   __syncthreads();
   const CovParams cp = make_cov_params(kernel_id, variant, hp_wave + (size_t)b * nh);
   double* tile = Abase + (size_t)b * walker_stride + tile_index(i, col) * TILE_ELEMS;
@@ -172,14 +216,13 @@ gen_column_kernel(int N, int nt, int col, int kernel_id, int variant, int nh, co
     const int e = e4 * 4;
     const int kg = e >> 9, m8 = (e >> 5) & 15, g = (e >> 2) & 7;
     const int R = m8 * 8 + g, C = kg * 4;
-    double d[4], d2[4], out[4];
+    double ti[4], ci[4], si[4], tj[4], cj[4], sj[4], out[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const double dt = ti_s[R] - tj_s[C + u];
-      d[u] = fabs(dt);
-      d2[u] = dt * dt;
+      ti[u] = pi_s[R]; ci[u] = pi_s[TILE + R]; si[u] = pi_s[2 * TILE + R];
+      tj[u] = pj_s[C + u]; cj[u] = pj_s[TILE + C + u]; sj[u] = pj_s[2 * TILE + C + u];
     }
-    cov_from_dist_n<4>(cp, d, d2, out);
+    cov_pair_n<4, true>(cp, ti, ci, si, tj, cj, sj, out);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int gi = i * TILE + R, gj = col * TILE + C + u;
@@ -340,9 +383,38 @@ __host__ __device__ inline size_t sweep_packed_doubles(int ld, int n_cols) {
   return (size_t)16 * nb * ld - (size_t)128 * nb * (nb - 1);
 }
 
+// Phase timers of the dataflow kernel (only with -DDAG_TIMING; thread 0 of a CTA accumulates clock64 deltas in
+// registers, tools/dag_timing.py reads the per-phase totals).  Without the flag every call is empty.
+struct PhaseTimer {
+#ifdef DAG_TIMING
+  long long* a;   // shared memory: 16 accumulators + the last time stamp (only thread 0 touches them)
+  __device__ __forceinline__ void init(void* smem17) {
+    a = reinterpret_cast<long long*>(smem17);
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 16; ++i) a[i] = 0;
+      a[16] = clock64();
+    }
+  }
+  __device__ __forceinline__ void mark(int slot) {
+    if (threadIdx.x == 0) {
+      const long long now = clock64();
+      a[slot] += now - a[16];
+      a[16] = now;
+    }
+  }
+  __device__ __forceinline__ void count(int slot) {
+    if (threadIdx.x == 0) a[slot] += 1;
+  }
+#else
+  __device__ __forceinline__ void init(void*) {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void count(int) {}
+#endif
+};
+
 template <bool WITH_INV, int NWARPS, bool PACKED = false>
 __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, double* PA, const int pa_ld, double* PB,
-                                       const int pb_ld, double* D, double* wv) {
+                                       const int pb_ld, double* D, double* wv, PhaseTimer* ptm = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tig = lane & 3;
   const int n_rows = n_cols + 1;                 // + residual row
@@ -379,6 +451,7 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
       if (in_blk && c < r) D[r * PB_D_LD + c] = v * wv[c];
       __syncthreads();
     }
+    if (ptm) ptm->mark(8);
     // ---- 2. panel rows ----------------------------------------------------------------------
     if (tid < ld) {
       const int rho = tid;
@@ -412,6 +485,7 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
       }
     }
     __syncthreads();
+    if (ptm) ptm->mark(9);
     // ---- 3. trailing update on the tensor pipe -------------------------------------------------
     const int c_begin = k0 + PB_NB;
     const int n_m16 = (n_cols - c_begin) / 16;
@@ -469,6 +543,7 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
       }
     }
     __syncthreads();
+    if (ptm) ptm->mark(10);
   }
 }
 
@@ -580,6 +655,7 @@ struct GemmArgs {
   const double* t;
   const double* yerr;
   const double* hp_wave;
+  const double* ph_wave;   // [wave, 2, nt * 128] phase cosines / sines of the points (phase_table_kernel)
   double* resid;     // [wave, ldr]
   int ldr;
   const double* zbuf;  // [wave, 128]
@@ -621,7 +697,7 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;
 #define GEMM_TMA_STAGES 4
 #define GEMM_TMA_THREADS GEMM_THREADS
 #define GEMM_TMA_SMEM_BYTES \
-  ((size_t)GEMM_TMA_STAGES * GEMM_STAGE_DOUBLES * sizeof(double) + (2 * TILE + 4 * TILE + TILE) * sizeof(double) + 2 * GEMM_TMA_STAGES * sizeof(unsigned long long))
+  ((size_t)GEMM_TMA_STAGES * GEMM_STAGE_DOUBLES * sizeof(double) + (6 * TILE + 4 * TILE + TILE) * sizeof(double) + 2 * GEMM_TMA_STAGES * sizeof(unsigned long long))
 
 // L2-aware rasterisation of an UPDATE launch.  Target tiles (ti, tj), col_begin <= tj < col_end,
 // ti >= tj, are walked in horizontal BANDS of UPDATE_BAND tile rows, column by column inside a band:
@@ -659,9 +735,9 @@ __global__ void __launch_bounds__(GEMM_TMA_THREADS, 1) gemm_tile_kernel(GemmArgs
   extern __shared__ double smem[];
   constexpr int NST = GEMM_TMA_STAGES;
   double* stages = smem;
-  double* tis = smem + NST * GEMM_STAGE_DOUBLES;  // 128: t of the tile rows
-  double* tjs = tis + TILE;                       // 128: t of the tile cols
-  double* part = tjs + TILE;                      // 4 x 128 GEMV partials
+  double* tis = smem + NST * GEMM_STAGE_DOUBLES;  // 3 x 128: t, phase cosine, phase sine of the tile rows
+  double* tjs = tis + 3 * TILE;                   // 3 x 128: the same of the tile cols
+  double* part = tjs + 3 * TILE;                  // 4 x 128 GEMV partials
   double* zs = part + 4 * TILE;                   // 128: z_k
   unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(zs + TILE);
   unsigned long long* empty_bar = full_bar + GEMM_TMA_STAGES;
@@ -725,13 +801,9 @@ __global__ void __launch_bounds__(GEMM_TMA_THREADS, 1) gemm_tile_kernel(GemmArgs
   }
 
   if (g.mode == GEMM_UPDATE && g.gen) {
-    if (tid < TILE) {
-      const int gi = ti * TILE + tid;
-      tis[tid] = gi < g.N ? g.t[gi] : 0.0;
-    } else {
-      const int gj = tj * TILE + (tid - TILE);
-      tjs[tid - TILE] = gj < g.N ? g.t[gj] : 0.0;
-    }
+    const double* ph_w = g.ph_wave + (size_t)b * 2 * g.nt * TILE;
+    if (tid < TILE) load_tile_points(tis, ti * TILE, tid, g.N, g.nt * TILE, g.t, ph_w);
+    else load_tile_points(tjs, tj * TILE, tid - TILE, g.N, g.nt * TILE, g.t, ph_w);
   }
   if (g.mode == GEMM_TRSM && tid < TILE) zs[tid] = g.zbuf[(size_t)b * TILE + tid];
 
@@ -758,15 +830,20 @@ __global__ void __launch_bounds__(GEMM_TMA_THREADS, 1) gemm_tile_kernel(GemmArgs
     consumer_sync();  // tis / tjs
     const CovParams cp = make_cov_params(g.kernel_id, g.variant, g.hp_wave + (size_t)b * g.nh);
     const bool interior = ti > tj && (ti + 1) * TILE <= g.N;   // off-diagonal tile, no padding rows
-    if (interior) {
+    if (interior && (cp.kind == 3 || cp.kind == 4)) {
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int np2 = 0; np2 < 2; ++np2)
+          gen_interior8_inline<3>(cp, tis, wm * 64 + mi * 16 + gq, tjs, wn * 32 + np2 * 16 + 2 * tig, acc[mi][2 * np2], acc[mi][2 * np2 + 1]);
+    } else if (interior) {
 #pragma unroll
       for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
         for (int np2 = 0; np2 < 2; ++np2) {
           const int R = wm * 64 + mi * 16 + gq;
           const int C = wn * 32 + np2 * 16 + 2 * tig;
-          const Cov8 f = gen_interior8(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, tis[R], tis[R + 8], tjs[C], tjs[C + 1], tjs[C + 8],
-                                       tjs[C + 9]);
+          const Cov8 f = gen_interior8(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, tis, TILE, R, tjs, TILE, C);
           acc[mi][2 * np2][0] = -f.v0; acc[mi][2 * np2][1] = -f.v1; acc[mi][2 * np2][2] = -f.v2; acc[mi][2 * np2][3] = -f.v3;
           acc[mi][2 * np2 + 1][0] = -f.v4; acc[mi][2 * np2 + 1][1] = -f.v5; acc[mi][2 * np2 + 1][2] = -f.v6;
           acc[mi][2 * np2 + 1][3] = -f.v7;
@@ -780,8 +857,7 @@ __global__ void __launch_bounds__(GEMM_TMA_THREADS, 1) gemm_tile_kernel(GemmArgs
           const int R = wm * 64 + mi * 16 + gq;
           const int C = wn * 32 + np2 * 16 + 2 * tig;
           double frag[8];
-          gen_fragment8(cp, g.N, ti * TILE + R, tj * TILE + C, tis[R], tis[R + 8], tjs[C], tjs[C + 1], tjs[C + 8],
-                        tjs[C + 9], g.yerr, frag);
+          gen_fragment8(cp, g.N, ti * TILE + R, tj * TILE + C, tis, TILE, R, tjs, TILE, C, g.yerr, frag);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             acc[mi][2 * np2][v] = -frag[v];

@@ -37,6 +37,7 @@ struct ProblemDesc {
   int variant;       // 0 reference-as-coded, 1 textbook Matern5
   int nh, nm;        // hyper-parameters / model parameters per walker
   int n_ops, n_priors;
+  double t_ref;      // phase origin of the periodic covariance terms (a time stamp from the middle of the series)
   ModelOp ops[MRV_MAX_OPS];
   PriorSpec priors[MRV_MAX_PRIORS];
 };
@@ -55,16 +56,18 @@ struct CovParams {
   double a2;     // amp^2
   double c1, c2, c3;
   double jit2;   // jitter^2 (0 when the kernel has none)
+  double cph;    // periodic kernels: 1 / per (phase of a point = cph * (t - t_ref), in periods), else 0
 };
 
 __host__ __device__ inline CovParams make_cov_params(int kernel_id, int variant, const double* hp) {
   CovParams p;
   p.kind = kernel_id;
-  p.a2 = p.c1 = p.c2 = p.c3 = p.jit2 = 0.0;
+  p.a2 = p.c1 = p.c2 = p.c3 = p.jit2 = p.cph = 0.0;
   switch (kernel_id) {
     case 0:  // Cosine: hp = amp, per
       p.a2 = hp[0] * hp[0];
       p.c1 = 2.0 / hp[1];          // cospi(c1 d)
+      p.cph = 1.0 / hp[1];
       break;
     case 1:  // ExpSquared: amp, timescale
       p.a2 = hp[0] * hp[0];
@@ -74,6 +77,7 @@ __host__ __device__ inline CovParams make_cov_params(int kernel_id, int variant,
       p.a2 = hp[0] * hp[0];
       p.c1 = -2.0 / (hp[1] * hp[1]);
       p.c2 = 1.0 / hp[2];          // sinpi(c2 d)
+      p.cph = p.c2;
       break;
     case 3:  // QuasiPer: per, perlength, explength, amp
     case 4:  // JitterQuasiPer: + jit
@@ -81,6 +85,7 @@ __host__ __device__ inline CovParams make_cov_params(int kernel_id, int variant,
       p.c1 = -1.0 / (hp[2] * hp[2]);
       p.c2 = 1.0 / hp[0];          // sinpi(c2 d)
       p.c3 = -1.0 / (hp[1] * hp[1]);
+      p.cph = p.c2;
       if (kernel_id == 4) p.jit2 = hp[4] * hp[4];
       break;
     case 5:  // Matern5/2: amp, timescale
@@ -190,6 +195,152 @@ __device__ __forceinline__ void cov_from_dist_n(const CovParams& p, const double
     default:
 #pragma unroll
       for (int e = 0; e < NV; ++e) out[e] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast evaluation for the factorisation kernels (the N^2 / 2 entries of every walker): periodic terms by the
+// angle-difference identity on PER-POINT phases.  With u_i = (t_i - t_ref) / per, C_i = cospi(2 u_i),
+// S_i = sinpi(2 u_i) (N sincospi per walker instead of N^2 / 2 sinpi),
+//        cos(2 pi d / per) = C_i C_j + S_i S_j,       sin^2(pi d / per) = (1 - cos(2 pi d / per)) / 2.
+// The periodic term enters the QuasiPer / ExpSinSquared entries only through the EXPONENT, where an absolute error
+// of ~1e-16 is a relative error of ~1e-16 of the entry; the phase of a point carries the rounding of u_i (|u_i| eps
+// periods, i.e. a shift of the time stamp by 1 ulp of t - t_ref), the same size as the rounding of pi d / per in the
+// reference for far-apart pairs.  Measured (tools/cov_rate_probe.py): QuasiPer 98 -> 44 FP64 flop-equivalents per entry.
+// The dense per-object API (mrv_covmatrix*) and the diagonal keep the distance form above, which follows the
+// reference's formula literally.
+// ------------------------------------------------------------------------------------------------
+// exp of NV values in LOCK STEP, branch-free: the library exp carries a rare-path branch per call, which cuts the
+// NV evaluations into NV basic blocks that the compiler cannot interleave -- in the 8-warp tile kernels the exp chains
+// then run one after the other at the latency of a dependent DFMA chain (ncu: the exp line was 12.5 % of all stall
+// samples of the dataflow kernel, reason "wait"; generation 9.6 us per 128 x 128 tile against ~3 us of FP64 issue time).
+// Range reduction by ln 2 (hi / lo), degree-11 polynomial (Chebyshev interpolant of exp on |r| <= ln 2 / 2, relative
+// truncation error 4.2e-18; measured against expl: <= 1.5e-16 relative over [-700, 1]), scaling by 2^t built in the
+// exponent field.  Arguments are clamped to [-700, 700]: the result below 1e-304 is not flushed to zero, and +700
+// is only reachable with negative time scales (whose covariance is not positive definite either way); NaN passes through.
+template <int NV>
+__device__ __forceinline__ void exp_lockstep(double (&x)[NV]) {
+  const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: the rounded integer sits in the low word
+  double t[NV], p[NV];
+  int ti[NV];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) x[e] = (x[e] < -700.0) ? -700.0 : x[e];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) x[e] = (x[e] > 700.0) ? 700.0 : x[e];
+#pragma unroll
+  for (int e = 0; e < NV; ++e) t[e] = fma(x[e], 1.4426950408889634074, MAGIC);
+#pragma unroll
+  for (int e = 0; e < NV; ++e) ti[e] = __double2loint(t[e]);
+#pragma unroll
+  for (int e = 0; e < NV; ++e) t[e] -= MAGIC;
+#pragma unroll
+  for (int e = 0; e < NV; ++e) x[e] = fma(t[e], -6.93147180369123816490e-01, x[e]);
+#pragma unroll
+  for (int e = 0; e < NV; ++e) x[e] = fma(t[e], -1.90821492927058770002e-10, x[e]);
+#pragma unroll
+  for (int e = 0; e < NV; ++e) p[e] = fma(2.5110037605963777712e-8, x[e], 2.7632639639041029749e-7);
+#define MRV_EXP_STEP(c)                \
+  _Pragma("unroll") for (int e = 0; e < NV; ++e) p[e] = fma(p[e], x[e], c);
+  MRV_EXP_STEP(2.7557240918578969823e-6)
+  MRV_EXP_STEP(2.4801485482328492419e-5)
+  MRV_EXP_STEP(1.9841269890047113707e-4)
+  MRV_EXP_STEP(1.3888888952314774652e-3)
+  MRV_EXP_STEP(8.3333333333196006109e-3)
+  MRV_EXP_STEP(4.1666666666488095495e-2)
+  MRV_EXP_STEP(1.6666666666666680806e-1)
+  MRV_EXP_STEP(5.0000000000000183855e-1)
+  MRV_EXP_STEP(1.0)
+  MRV_EXP_STEP(1.0)
+#undef MRV_EXP_STEP
+#pragma unroll
+  for (int e = 0; e < NV; ++e) x[e] = p[e] * __hiloint2double((1023 + ti[e]) << 20, 0);
+}
+
+// NV entries k(t_i, t_j) from per-point data: ti / tj times, (ci, si) / (cj, sj) the points' phase cosines / sines.
+// LOCKSTEP: the exponentials through exp_lockstep (tile kernels: few warps, latency-bound) instead of the library exp
+// (kernels with 16+ warps per SM, where the library function's shorter instruction count wins).
+template <int NV, bool LOCKSTEP = false>
+__device__ __forceinline__ void cov_pair_n(const CovParams& p, const double (&ti)[NV], const double (&ci)[NV],
+                                           const double (&si)[NV], const double (&tj)[NV], const double (&cj)[NV],
+                                           const double (&sj)[NV], double (&out)[NV]) {
+  double arg[NV];
+  switch (p.kind) {
+    case 0:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) out[e] = p.a2 * fma(ci[e], cj[e], si[e] * sj[e]);
+      return;
+    case 1:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const double dt = ti[e] - tj[e];
+        arg[e] = p.c1 * (dt * dt);
+      }
+      break;
+    case 2:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) arg[e] = p.c1 * fma(-0.5, fma(ci[e], cj[e], si[e] * sj[e]), 0.5);
+      break;
+    case 3:
+    case 4:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const double dt = ti[e] - tj[e];
+        const double s2 = fma(-0.5, fma(ci[e], cj[e], si[e] * sj[e]), 0.5);
+        arg[e] = fma(p.c1, dt * dt, p.c3 * s2);
+      }
+      break;
+    case 5:
+    case 6:
+    case 7:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) arg[e] = -(p.c1 * fabs(ti[e] - tj[e]));
+      break;
+    default:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) out[e] = 0.0;
+      return;
+  }
+  if (LOCKSTEP) exp_lockstep<NV>(arg);
+  else {
+#pragma unroll
+    for (int e = 0; e < NV; ++e) arg[e] = exp(arg[e]);
+  }
+  switch (p.kind) {
+    case 5:   // reference as coded (kernels.py:909)
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const double dt = ti[e] - tj[e], d2 = dt * dt;
+        const double x = p.c1 * fabs(dt);
+        out[e] = p.a2 * (1.0 + x + ((5.0 * (d2 * d2)) / 3.0 * p.c2) * arg[e]);
+      }
+      break;
+    case 7:   // textbook Matern 5/2
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const double dt = ti[e] - tj[e];
+        const double x = p.c1 * fabs(dt);
+        out[e] = p.a2 * (1.0 + x + p.c2 * (dt * dt)) * arg[e];
+      }
+      break;
+    case 6:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) {
+        const double x = p.c1 * fabs(ti[e] - tj[e]);
+        out[e] = p.a2 * (1.0 + x) * arg[e];
+      }
+      break;
+    default:
+#pragma unroll
+      for (int e = 0; e < NV; ++e) out[e] = p.a2 * arg[e];
+  }
+}
+
+// Phase of one point (only the periodic kernels read it).
+__device__ __forceinline__ void cov_point_phase(const CovParams& p, double t_shifted, double& c, double& s) {
+  if (p.cph != 0.0 || p.kind == 0 || (p.kind >= 2 && p.kind <= 4)) sincospi(2.0 * (p.cph * t_shifted), &s, &c);
+  else {
+    c = 1.0;
+    s = 0.0;
   }
 }
 

@@ -2,17 +2,18 @@
 //
 // The launch-per-tile-column host loop of abi.cu:run_wave pays, per column, a serial chain
 //     in-panel UPDATE -> diagonal-tile kernel (latency-bound, one CTA per walker) -> TRSM
-// whose launches each end in a partially filled last round of CTAs; at N = 1024 x 128 walkers the tensor pipe idles
-// more than half of the time (round 1: 44 % of the DMMA peak).  Here ONE kernel of one CTA per SM runs the whole
+// whose launches each end in a partially filled last round of CTAs.  Here ONE kernel of one CTA per SM runs the whole
 // factorisation of a wave as a list of TILE TASKS pulled from an atomic counter; the dependencies between tasks
 // are per-walker, per-tile-row progress counters in global memory (release / acquire), so different walkers sit in
 // different tile columns at the same time and nothing waits for the slowest CTA of a launch.
 //
 // Left-looking by tiles, same storage (lower-triangular 128 x 128 tiles in operand order, blocked.cuh):
-//   O(b, i, k), i > k   acc = -K(i,k) generated from t (first and only touch) + sum_{p<k} L(i,p) L(k,p)^T  (DMMA, operands
-//                       streamed through the bulk-copy / mbarrier ring; the k tiles of a row are contiguous in memory);
-//                       C = -acc goes to the workspace; once the diagonal tile of column k is done: X = C inv(L_kk)^T
-//                       (DMMA, triangular skip as in TRSM), L(i,k) = X stored, r_i -= X z_k.
+//   O(b, i, k), i > k   acc = -K(i,k) generated from the points (first and only touch) + sum_{p<k} L(i,p) L(k,p)^T  (DMMA,
+//                       operands streamed through the bulk-copy / mbarrier ring; the k tiles of a row are contiguous in
+//                       memory); C = -acc goes to SHARED memory in operand order (it never visits HBM); once the
+//                       diagonal tile of column k is done: X = C inv(L_kk)^T (DMMA, A fragments straight from the C tile,
+//                       inv(L_kk) streamed through a second small ring, triangular skip as in TRSM), L(i,k) = X stored,
+//                       r_i -= X z_k.
 //   D(b, k)             acc = -K(k,k) + sum_{p<k} L(k,p) L(k,p)^T; the 128 x 128 block goes to shared memory and is swept
 //                       by cta_block_sweep (pivots, inv(L_kk), z_k = L_kk^-1 r_k, log det, status) exactly as
 //                       potrf_tile_blk_kernel does.
@@ -20,24 +21,29 @@
 // rowdone[b][k] >= k for its update and rowdone[b][k] >= k + 1 (diagonal tile done) for its solve.
 //
 // Task order (any order that keeps a walker's dependencies earlier in the list is deadlock-free: the grid is
-// co-resident, tasks are taken in list order, so everything a task waits for is already running or done):
-//     D(.,0) | O(.,1,0)  D(.,1)  O(.,i>=2,0) | O(.,2,1)  D(.,2)  O(.,i>=3,1) | ...
-// i.e. the tile that the NEXT diagonal task needs is finished first and the next diagonal tasks overlap with the
-// rest of the column (look-ahead).  Summation order per element is the order of the launch-per-column path
-// (p ascending, k16 slices ascending; storing C = -acc and reloading acc = -C is exact), so results are bitwise
-// identical to it.
+// co-resident, tasks are taken in list order -- one task ahead at most --, so the smallest unfinished task is always
+// running and everything it waits for is done):
+//     D(.,0) | O(.,1,0)  O(.,2,0)  D(.,1)  O(.,i>=3,0) | O(.,2,1)  O(.,3,1)  D(.,2)  O(.,i>=4,1) | ...
+// i.e. per column s first the two tiles that the next diagonal task and the next column's first task need, then
+// the next diagonal tasks (look-ahead: they overlap with the rest of the column), then the rest walker-major (so
+// that co-running CTAs share L(s, .) in L2).  A task's inputs that no task produces -- the time stamps / phases of
+// its 2 x 128 points and the walker's covariance constants -- are fetched by bulk copies issued during the PREVIOUS
+// task of the CTA (double-buffered), so no task starts with a global-memory round trip.
+// Summation order per element is the order of the launch-per-column path (p ascending, k16 slices ascending;
+// storing C = -acc and reloading it is exact), so results are bitwise identical to it.
 #pragma once
 #include "blocked.cuh"
 
 struct DagArgs {
   int N, nt, B;
-  int kernel_id, variant, nh;
+  int kind;                // CovParams::kind of the problem (kernel id, Matern5 textbook -> 7)
   int total_tasks;
   double* Abase;
   size_t walker_stride;
-  const double* t;
+  const double* t;         // [nt * 128] time stamps, zero padded
   const double* yerr;
-  const double* hp_wave;   // [B, nh]
+  const double* ph_wave;   // [B, 2, nt * 128] phase cosines / sines of the points (phase_table_kernel)
+  const double* cpar_wave; // [B, 8] covariance constants a2, c1, c2, c3, jit2 (phase_table_kernel)
   double* resid;           // [B, ldr]
   int ldr;
   double* zcols;           // [B, nt, 128]  z_k per tile column
@@ -52,9 +58,15 @@ struct DagArgs {
 
 #define DAG_THREADS 256
 #define DAG_AUTO_MAX_TILES 0          // automatic choice: tile columns up to which the dataflow kernel replaces run_wave
+#define DAG_BSTAGES 3                 // ring of inv(L_kk) k16 slices for the solve phase
 #define DAG_SWEEP_DOUBLES (PB_LD * TILE + PB_NB * PB_PA_LD + PB_NB * PB_PB_LD + PB_NB * PB_D_LD + PB_NB + 64 + TILE)
-#define DAG_AUX_DOUBLES (2 * TILE + 4 * TILE + TILE)
-#define DAG_SMEM_BYTES ((size_t)(DAG_SWEEP_DOUBLES + DAG_AUX_DOUBLES) * sizeof(double) + 2 * GEMM_TMA_STAGES * sizeof(unsigned long long) + 16 * sizeof(int))
+#define DAG_R1_OFFSET (GEMM_TMA_STAGES * GEMM_STAGE_DOUBLES)   // doubles: end of the update ring / C tile
+#define DAG_SOLVE_DOUBLES (DAG_R1_OFFSET + DAG_BSTAGES * SLICE_ELEMS)
+#define DAG_MAIN_DOUBLES (DAG_SWEEP_DOUBLES > DAG_SOLVE_DOUBLES ? DAG_SWEEP_DOUBLES : DAG_SOLVE_DOUBLES)
+#define DAG_PTS_DOUBLES (6 * TILE + 8)                          // one buffer of point data + covariance constants
+#define DAG_AUX_DOUBLES (2 * DAG_PTS_DOUBLES + 4 * TILE + TILE)
+#define DAG_NBARS (2 * GEMM_TMA_STAGES + 2 * DAG_BSTAGES + 2)
+#define DAG_SMEM_BYTES ((size_t)(DAG_MAIN_DOUBLES + DAG_AUX_DOUBLES) * sizeof(double) + DAG_NBARS * sizeof(unsigned long long) + 16 * sizeof(int) + 17 * sizeof(long long))
 #define DAG_SPIN_LIMIT (1ll << 33)   // ~4 s of SM clocks: a dependency that takes longer means a lost task, not a slow one
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -84,6 +96,14 @@ __device__ __forceinline__ bool dag_wait(const int* p, int need, int* abort_flag
 
 enum { DAG_TASK_EXIT = 0, DAG_TASK_DIAG = 1, DAG_TASK_OFF = 2 };
 
+// -DDAG_TIMING: SM clocks per phase summed over all CTAs (thread 0 of each), and task counts.
+//  0 task fetch + dependency wait   1 generation (+ first bulk copies)   2 update main loop   3 C tile -> shared memory
+//  4 wait for the diagonal tile     5 solve main loop                    6 solve epilogue + release
+//  7 diagonal: acc -> S + residual  8 sweep: pivot blocks  9 sweep: panel rows  10 sweep: trailing DMMA update
+// 11 pivots / log det / z           12 inv(L) write-back + release       13 # diagonal tasks  14 # off-diagonal tasks
+// 15 end-of-task barrier
+__device__ unsigned long long g_dag_timing[16];
+
 __device__ __forceinline__ void dag_decode(const DagArgs& g, int tsk, int& type, int& b, int& i, int& k) {
   const int B = g.B, nt = g.nt;
   if (tsk < B) {
@@ -98,28 +118,119 @@ __device__ __forceinline__ void dag_decode(const DagArgs& g, int tsk, int& type,
     ++s;
   }
   k = s;
-  if (r < B) {                 // the tile the next diagonal task needs
-    type = DAG_TASK_OFF;
+  type = DAG_TASK_OFF;
+  if (r < B) {                                 // the tile the next diagonal task needs
     b = r;
     i = s + 1;
-  } else if (r < 2 * B) {      // next diagonal tile (look-ahead)
+    return;
+  }
+  r -= B;
+  if (s + 2 < nt) {                            // the tile the next column's first task needs
+    if (r < B) {
+      b = r;
+      i = s + 2;
+      return;
+    }
+    r -= B;
+  }
+  if (r < B) {                                 // next diagonal tile (look-ahead)
     type = DAG_TASK_DIAG;
-    b = r - B;
+    b = r;
     i = k = s + 1;
-  } else {                     // rest of column s, walker-major so that co-running CTAs share L(s, .) in L2
-    r -= 2 * B;
-    const int per = nt - s - 2;
-    type = DAG_TASK_OFF;
-    b = r / per;
-    i = s + 2 + r % per;
+    return;
+  }
+  r -= B;                                      // rest of column s, walker-major
+  const int per = nt - s - 3;
+  b = r / per;
+  i = s + 3 + r % per;
+}
+
+// k16-slice main loop of a tile task.  UPDATE (SOLVE = false): A | B slice pairs through the 4-stage ring R0.
+// SOLVE: A fragments straight from the resident C tile in R0 (slice q at q * SLICE_ELEMS), inv(L_kk) slices through the
+// 3-stage ring R1; the warp owning output columns [32 wn, 32 wn + 32) stops issuing after slice q_last = 2 wn + 1
+// (inv(L) is lower triangular).  `q0` is the ring's running slice counter (stage and barrier phase persist across tasks).
+template <bool SOLVE>
+__device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices, unsigned q0, const double* ringA,
+                                             const double* ringB, unsigned long long* fbar, unsigned long long* ebar,
+                                             const double* __restrict__ Asrc, const double* __restrict__ Bsrc, int a_lane,
+                                             int b_lane, int q_last, int tid, int lane) {
+  constexpr unsigned NSTG = SOLVE ? DAG_BSTAGES : GEMM_TMA_STAGES;
+  constexpr unsigned slice_bytes = SLICE_ELEMS * sizeof(double);
+  auto a_ptr = [&](int q, unsigned st) -> const double* {
+    return SOLVE ? ringA + (size_t)q * SLICE_ELEMS + a_lane : ringA + st * GEMM_STAGE_DOUBLES + a_lane;
+  };
+  auto b_ptr = [&](unsigned st) -> const double* {
+    return SOLVE ? ringB + st * SLICE_ELEMS + b_lane : ringA + st * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
+  };
+  double af[2][8], bf[2][4];
+  {
+    const unsigned st0 = q0 % NSTG;
+    mbar_wait(&fbar[st0], (q0 / NSTG) & 1);
+    const double* As = a_ptr(0, st0);
+    const double* Bs = b_ptr(st0);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) af[0][v] = As[v << 5];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) bf[0][v] = Bs[v << 5];
+  }
+  for (int q = 0; q < nslices; ++q) {
+    const unsigned qa = q0 + q, st = qa % NSTG;
+    {
+      // refill: slice q + 2 goes into the stage consumed two (one, for the 3-stage ring) iterations ago
+      const int qn = q + 2;
+      if (tid == 0 && qn < nslices) {
+        const unsigned qq = q0 + qn, sn = qq % NSTG, u = qq / NSTG;
+        if (u > 0) mbar_wait(&ebar[sn], (u - 1) & 1);
+        if (SOLVE) {
+          mbar_expect_tx(&fbar[sn], slice_bytes);
+          bulk_g2s(const_cast<double*>(ringB) + sn * SLICE_ELEMS, Bsrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
+        } else {
+          double* dst = const_cast<double*>(ringA) + sn * GEMM_STAGE_DOUBLES;
+          mbar_expect_tx(&fbar[sn], 2 * slice_bytes);
+          bulk_g2s(dst, Asrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
+          bulk_g2s(dst + SLICE_ELEMS, Bsrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
+        }
+      }
+      __syncwarp();
+    }
+    const double* As = a_ptr(q, st);
+    const double* Bs = b_ptr(st);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int cur = kk & 1, nxt = cur ^ 1;
+      if (kk < 3) {
+#pragma unroll
+        for (int v = 0; v < 8; ++v) af[nxt][v] = As[(((kk + 1) * 16 + v) << 5)];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bf[nxt][v] = Bs[(((kk + 1) * 16 + v) << 5)];
+      } else if (q + 1 < nslices) {
+        const unsigned qn1 = qa + 1, sn = qn1 % NSTG;
+        mbar_wait(&fbar[sn], (qn1 / NSTG) & 1);
+        const double* An = a_ptr(q + 1, sn);
+        const double* Bn = b_ptr(sn);
+#pragma unroll
+        for (int v = 0; v < 8; ++v) af[nxt][v] = An[v << 5];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bf[nxt][v] = Bn[v << 5];
+      }
+      if (!SOLVE || q <= q_last) {   // warp-uniform
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ebar[st]);
   }
 }
 
 __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
   extern __shared__ double smem[];
   constexpr int NST = GEMM_TMA_STAGES;
-  double* stages = smem;                          // operand ring, 4 x 32 KiB -- aliased by the sweep matrix S
+  double* stages = smem;                          // R0: operand ring, 4 x 32 KiB | C tile of the solve phase | S
   double* S = smem;
+  double* bring = smem + DAG_R1_OFFSET;           // R1 (behind the C tile): inv(L_kk) slices of the solve phase | rest of S, PA ...
   double* PA = S + (size_t)PB_LD * TILE;
   double* PBm = PA + PB_NB * PB_PA_LD;
   double* Dm = PBm + PB_NB * PB_PB_LD;
@@ -127,226 +238,254 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
   double* red = wv + PB_NB;
   int* ired = (int*)(red + 32);
   double* isd_s = red + 64;
-  double* tis = smem + DAG_SWEEP_DOUBLES;         // never aliased
-  double* tjs = tis + TILE;
-  double* part = tjs + TILE;
+  double* pts = smem + DAG_MAIN_DOUBLES;          // never aliased: 2 x (rows t, C, S | cols t, C, S | constants)
+  double* part = pts + 2 * DAG_PTS_DOUBLES;
   double* zs = part + 4 * TILE;
   unsigned long long* full_bar = reinterpret_cast<unsigned long long*>(zs + TILE);
   unsigned long long* empty_bar = full_bar + NST;
-  int* s_task = reinterpret_cast<int*>(empty_bar + NST);
+  unsigned long long* fullB = empty_bar + NST;
+  unsigned long long* emptyB = fullB + DAG_BSTAGES;
+  unsigned long long* pt_bar = emptyB + DAG_BSTAGES;
+  int* s_task = reinterpret_cast<int*>(pt_bar + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp >> 2) & 1;
   const int gq = lane >> 2, tig = lane & 3;
   int* abort_flag = g.counter + 1;
+  const int n_pad = g.nt * TILE;
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 8);
     }
+    for (int s = 0; s < DAG_BSTAGES; ++s) {
+      mbar_init(&fullB[s], 1);
+      mbar_init(&emptyB[s], 8);
+    }
+    mbar_init(&pt_bar[0], 1);
+    mbar_init(&pt_bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     fence_proxy_async();
   }
   __syncthreads();
 
-  unsigned qg = 0;   // slices streamed through the ring so far (uniform across the CTA)
+  unsigned qg = 0;        // k16 slices streamed through the update ring so far (uniform across the CTA)
+  unsigned qb = 0;        // inv(L) slices streamed through the solve ring so far
+  unsigned n_local = 0;   // tasks this CTA has started: point buffer = n_local & 1
+  PhaseTimer tm;
+  tm.init(s_task + 16);
+
+  // Point data of task `tsk` (thread 0): six 1 KiB bulk copies + the walker's constants into buffer `buf`.
+  auto issue_points = [&](int tsk, unsigned buf) {
+    int type, b, i, k;
+    dag_decode(g, tsk, type, b, i, k);
+    double* dst = pts + buf * DAG_PTS_DOUBLES;
+    const double* ph_w = g.ph_wave + (size_t)b * 2 * n_pad;
+    unsigned long long* bar = &pt_bar[buf];
+    mbar_expect_tx(bar, (6 * TILE + 8) * sizeof(double));
+    bulk_g2s(dst, g.t + i * TILE, TILE * sizeof(double), bar);
+    bulk_g2s(dst + TILE, ph_w + i * TILE, TILE * sizeof(double), bar);
+    bulk_g2s(dst + 2 * TILE, ph_w + n_pad + i * TILE, TILE * sizeof(double), bar);
+    bulk_g2s(dst + 3 * TILE, g.t + k * TILE, TILE * sizeof(double), bar);
+    bulk_g2s(dst + 4 * TILE, ph_w + k * TILE, TILE * sizeof(double), bar);
+    bulk_g2s(dst + 5 * TILE, ph_w + n_pad + k * TILE, TILE * sizeof(double), bar);
+    bulk_g2s(dst + 6 * TILE, g.cpar_wave + (size_t)b * 8, 8 * sizeof(double), bar);
+  };
+
+  int next_tsk = 0x7fffffff;
+  if (tid == 0) {
+    if (ld_acquire_gpu(abort_flag) == 0) next_tsk = atomicAdd(g.counter, 1);
+    if (next_tsk < g.total_tasks) issue_points(next_tsk, 0);
+  }
 
   for (;;) {
     // ---- next task ---------------------------------------------------------------------------
     if (tid == 0) {
-      int type = DAG_TASK_EXIT, b = 0, i = 0, k = 0;
-      const int tsk = atomicAdd(g.counter, 1);
-      if (tsk < g.total_tasks && ld_acquire_gpu(abort_flag) == 0) {
-        dag_decode(g, tsk, type, b, i, k);
-        // update operands: rows i and k finished through column k - 1 (also orders the residual block r_i / r_k)
-        const int* rd = g.rowdone + (size_t)b * g.nt;
-        if (k > 0 && !(dag_wait(rd + i, k, abort_flag) && dag_wait(rd + k, k, abort_flag))) type = DAG_TASK_EXIT;
-        __threadfence();
-        fence_proxy_async();
+      int type = DAG_TASK_EXIT, b = 0, i = 0, k = 0, diag_ready = 0;
+      const int tsk = next_tsk;
+      next_tsk = atomicAdd(g.counter, 1);   // the task after this one: its round trip overlaps with this task
+      if (tsk < g.total_tasks) {
+        if (ld_acquire_gpu(abort_flag) == 0) {
+          dag_decode(g, tsk, type, b, i, k);
+          // update operands: rows i and k finished through column k - 1 (also orders the residual block r_i / r_k)
+          const int* rd = g.rowdone + (size_t)b * g.nt;
+          const int v1 = ld_acquire_gpu(rd + i), v2 = ld_acquire_gpu(rd + k);   // both in flight; the common case is "ready"
+          if ((v1 < k || v2 < k) && !(dag_wait(rd + i, k, abort_flag) && dag_wait(rd + k, k, abort_flag))) type = DAG_TASK_EXIT;
+          diag_ready = (type == DAG_TASK_OFF && v2 >= k + 1) ? 1 : 0;
+          fence_proxy_async();
+        }
+        // this task's points were requested during the previous one: never leave with a bulk copy in flight
+        if (type == DAG_TASK_EXIT) mbar_wait(&pt_bar[n_local & 1], (n_local >> 1) & 1);
       }
       s_task[0] = type;
       s_task[1] = b;
       s_task[2] = i;
       s_task[3] = k;
+      s_task[4] = diag_ready;
     }
     __syncthreads();
     const int type = s_task[0], b = s_task[1], ti = s_task[2], tk = s_task[3];
     if (type == DAG_TASK_EXIT) break;
+    tm.mark(0);
+    tm.count(type == DAG_TASK_DIAG ? 13 : 14);
 
     double* Aw = g.Abase + (size_t)b * g.walker_stride;
     const double* rowA = Aw + tile_index(ti, 0) * TILE_ELEMS;   // tiles (ti, 0..): contiguous
     const double* rowB = Aw + tile_index(tk, 0) * TILE_ELEMS;
     double* Ct = Aw + tile_index(ti, tk) * TILE_ELEMS;
     int* rd = g.rowdone + (size_t)b * g.nt;
+    const double* pr = pts + (n_local & 1) * DAG_PTS_DOUBLES;   // points of the tile rows; + 3 TILE: of the tile columns
+    const double* pc = pr + 3 * TILE;
+    bool b_started = false;   // thread 0: the first inv(L) slices of the solve phase are already in flight
 
-    // t of the tile rows / columns for the generation
-    if (tid < TILE) {
-      const int gi = ti * TILE + tid;
-      tis[tid] = gi < g.N ? g.t[gi] : 0.0;
-    } else {
-      const int gj = tk * TILE + (tid - TILE);
-      tjs[tid - TILE] = gj < g.N ? g.t[gj] : 0.0;
+    // first operand slices of the update, and -- when the diagonal tile is already done -- of the solve
+    if (tid == 0) {
+      const int nsl = tk * SLICES_PER_TILE;
+      for (int q = 0; q < 2 && q < nsl; ++q) {
+        const unsigned qq = qg + q, sn = qq % NST, u = qq / NST;
+        if (u > 0) mbar_wait(&empty_bar[sn], (u - 1) & 1);
+        double* dst = stages + sn * GEMM_STAGE_DOUBLES;
+        mbar_expect_tx(&full_bar[sn], 2 * SLICE_ELEMS * sizeof(double));
+        bulk_g2s(dst, rowA + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
+        bulk_g2s(dst + SLICE_ELEMS, rowB + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
+      }
+      if (s_task[4]) {
+        const double* Bsrc = rowB + (size_t)tk * TILE_ELEMS;
+        for (int q = 0; q < 2; ++q) {
+          const unsigned qq = qb + q, sn = qq % DAG_BSTAGES, u = qq / DAG_BSTAGES;
+          if (u > 0) mbar_wait(&emptyB[sn], (u - 1) & 1);
+          mbar_expect_tx(&fullB[sn], SLICE_ELEMS * sizeof(double));
+          bulk_g2s(bring + sn * SLICE_ELEMS, Bsrc + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &fullB[sn]);
+        }
+        b_started = true;
+      }
     }
+    mbar_wait(&pt_bar[n_local & 1], (n_local >> 1) & 1);   // this task's points (issued during the previous task)
 
     double acc[4][4][4];
-    const int nphase = (type == DAG_TASK_OFF) ? 2 : 1;
-    for (int phase = 0; phase < nphase; ++phase) {
-      // phase 0: update (K = 128 tk); phase 1: triangular solve against inv(L_kk) (K = 128, lower-triangular B)
-      const int wn = (phase == 1 && wm) ? 3 - (warp & 3) : (warp & 3);
-      const int q_last = (phase == 1) ? 2 * wn + 1 : 0x7fffffff;
-      const int nslices = (phase == 1) ? SLICES_PER_TILE : tk * SLICES_PER_TILE;
-      const double* Asrc = (phase == 1) ? Ct : rowA;
-      const double* Bsrc = (phase == 1) ? rowB + (size_t)tk * TILE_ELEMS : rowB;
-
-      if (phase == 1 && tid == 0) {
-        // the diagonal tile of column tk (inv(L_kk), z_k); C was written through the generic proxy above
-        if (!dag_wait(rd + tk, tk + 1, abort_flag)) s_task[0] = DAG_TASK_EXIT;
-        __threadfence();
-        fence_proxy_async();
+    const int wn0 = warp & 3;                              // update: 2 x 4 warp grid
+    const int wn1 = wm ? 3 - (warp & 3) : (warp & 3);      // solve: the two warps of an SM sub-partition get wn and 3 - wn
+    {
+      // ---- generation: acc = -K(ti, tk) ----
+      const int wn = wn0;
+      CovParams cp;
+      cp.kind = g.kind;
+      cp.a2 = pr[6 * TILE]; cp.c1 = pr[6 * TILE + 1]; cp.c2 = pr[6 * TILE + 2]; cp.c3 = pr[6 * TILE + 3];
+      cp.jit2 = pr[6 * TILE + 4]; cp.cph = 0.0;
+      const bool interior = ti > tk && (ti + 1) * TILE <= g.N;
+      if (interior && (cp.kind == 3 || cp.kind == 4)) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int np2 = 0; np2 < 2; ++np2)
+            gen_interior8_inline<3>(cp, pr, wm * 64 + mi * 16 + gq, pc, wn * 32 + np2 * 16 + 2 * tig, acc[mi][2 * np2],
+                                    acc[mi][2 * np2 + 1]);
+      } else if (interior) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int np2 = 0; np2 < 2; ++np2) {
+            const int R = wm * 64 + mi * 16 + gq;
+            const int C = wn * 32 + np2 * 16 + 2 * tig;
+            const Cov8 f = gen_interior8(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, pr, TILE, R, pc, TILE, C);
+            acc[mi][2 * np2][0] = -f.v0; acc[mi][2 * np2][1] = -f.v1; acc[mi][2 * np2][2] = -f.v2; acc[mi][2 * np2][3] = -f.v3;
+            acc[mi][2 * np2 + 1][0] = -f.v4; acc[mi][2 * np2 + 1][1] = -f.v5; acc[mi][2 * np2 + 1][2] = -f.v6;
+            acc[mi][2 * np2 + 1][3] = -f.v7;
+          }
+      } else {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+          for (int np2 = 0; np2 < 2; ++np2) {
+            const int R = wm * 64 + mi * 16 + gq;
+            const int C = wn * 32 + np2 * 16 + 2 * tig;
+            double frag[8];
+            gen_fragment8(cp, g.N, ti * TILE + R, tk * TILE + C, pr, TILE, R, pc, TILE, C, g.yerr, frag);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              acc[mi][2 * np2][v] = -frag[v];
+              acc[mi][2 * np2 + 1][v] = -frag[4 + v];
+            }
+          }
       }
-      if (phase == 1) {
-        __syncthreads();
-        if (s_task[0] == DAG_TASK_EXIT) break;
+      // the next task's points: its index has long arrived, the other buffer was last read a task ago
+      if (tid == 0 && next_tsk < g.total_tasks) issue_points(next_tsk, (n_local + 1) & 1);
+      tm.mark(1);
+    }
+    // ---- update: acc += sum_p L(ti,p) L(tk,p)^T ----
+    if (tk > 0) {
+      dag_mainloop<false>(acc, tk * SLICES_PER_TILE, qg, stages, nullptr, full_bar, empty_bar, rowA, rowB, ((wm * 8) << 5) + lane,
+                          ((wn0 * 4) << 5) + lane, 0x7fffffff, tid, lane);
+      qg += tk * SLICES_PER_TILE;
+    }
+    tm.mark(2);
+
+    bool aborted = false;
+    if (type == DAG_TASK_OFF) {
+      // ---- solve phase set-up: C = -acc into R0 (operand order), inv(L_kk) slices into R1 ----
+      const double* Bsrc = rowB + (size_t)tk * TILE_ELEMS;
+      __syncthreads();   // every warp has left the update ring: C aliases it
+#pragma unroll
+      for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+          for (int v1 = 0; v1 < 2; ++v1) {
+            const int R = wm * 64 + mi * 16 + gq + 8 * v1;
+            const int C = wn0 * 32 + ni * 8 + 2 * tig;
+            double2 o;
+            o.x = -acc[mi][ni][2 * v1 + 0];
+            o.y = -acc[mi][ni][2 * v1 + 1];
+            *reinterpret_cast<double2*>(stages + tile_off(R, C)) = o;
+          }
+      tm.mark(3);
+      if (tid == 0) {
+        if (!dag_wait(rd + tk, tk + 1, abort_flag)) s_task[0] = DAG_TASK_EXIT;
+        else if (!b_started) {
+          fence_proxy_async();
+          for (int q = 0; q < 2; ++q) {
+            const unsigned qq = qb + q, sn = qq % DAG_BSTAGES, u = qq / DAG_BSTAGES;
+            if (u > 0) mbar_wait(&emptyB[sn], (u - 1) & 1);
+            mbar_expect_tx(&fullB[sn], SLICE_ELEMS * sizeof(double));
+            bulk_g2s(bring + sn * SLICE_ELEMS, Bsrc + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &fullB[sn]);
+          }
+        }
+      }
+      __syncthreads();   // C tile complete; diagonal tile known to be done (z_k visible)
+      tm.mark(4);
+      if (s_task[0] == DAG_TASK_EXIT) {
+        // abort: the first inv(L) slices may be in flight -- let them land before this CTA can leave
+        if (tid == 0 && b_started) {
+          mbar_wait(&fullB[qb % DAG_BSTAGES], (qb / DAG_BSTAGES) & 1);
+          mbar_wait(&fullB[(qb + 1) % DAG_BSTAGES], ((qb + 1) / DAG_BSTAGES) & 1);
+        }
+        aborted = true;
+      } else {
         // values other CTAs produced are read past L1 (ld.global.cg): an SM's L1 may hold a stale line of them
         if (tid < TILE) zs[tid] = __ldcg(g.zcols + ((size_t)b * g.nt + tk) * TILE + tid);
-      }
-      if (tid == 0) {
-        for (int q = 0; q < 2 && q < nslices; ++q) {
-          const unsigned qq = qg + q, sn = qq % NST, u = qq / NST;
-          if (u > 0) mbar_wait(&empty_bar[sn], (u - 1) & 1);
-          double* dst = stages + sn * GEMM_STAGE_DOUBLES;
-          mbar_expect_tx(&full_bar[sn], 2 * SLICE_ELEMS * sizeof(double));
-          bulk_g2s(dst, Asrc + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
-          bulk_g2s(dst + SLICE_ELEMS, Bsrc + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
-        }
-      }
-
-      if (phase == 0) {
-        consumer_sync();  // tis / tjs
-        const CovParams cp = make_cov_params(g.kernel_id, g.variant, g.hp_wave + (size_t)b * g.nh);
-        const bool interior = ti > tk && (ti + 1) * TILE <= g.N;
-        if (interior) {
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int np2 = 0; np2 < 2; ++np2) {
-              const int R = wm * 64 + mi * 16 + gq;
-              const int C = wn * 32 + np2 * 16 + 2 * tig;
-              const Cov8 f = gen_interior8(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, tis[R], tis[R + 8], tjs[C], tjs[C + 1],
-                                           tjs[C + 8], tjs[C + 9]);
-              acc[mi][2 * np2][0] = -f.v0; acc[mi][2 * np2][1] = -f.v1; acc[mi][2 * np2][2] = -f.v2; acc[mi][2 * np2][3] = -f.v3;
-              acc[mi][2 * np2 + 1][0] = -f.v4; acc[mi][2 * np2 + 1][1] = -f.v5; acc[mi][2 * np2 + 1][2] = -f.v6;
-              acc[mi][2 * np2 + 1][3] = -f.v7;
-            }
-        } else {
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int np2 = 0; np2 < 2; ++np2) {
-              const int R = wm * 64 + mi * 16 + gq;
-              const int C = wn * 32 + np2 * 16 + 2 * tig;
-              double frag[8];
-              gen_fragment8(cp, g.N, ti * TILE + R, tk * TILE + C, tis[R], tis[R + 8], tjs[C], tjs[C + 1], tjs[C + 8],
-                            tjs[C + 9], g.yerr, frag);
-#pragma unroll
-              for (int v = 0; v < 4; ++v) {
-                acc[mi][2 * np2][v] = -frag[v];
-                acc[mi][2 * np2 + 1][v] = -frag[4 + v];
-              }
-            }
-        }
-      } else {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
             for (int v = 0; v < 4; ++v) acc[mi][ni][v] = 0.0;
+        dag_mainloop<true>(acc, SLICES_PER_TILE, qb, stages, bring, fullB, emptyB, nullptr, Bsrc, ((wm * 8) << 5) + lane,
+                           ((wn1 * 4) << 5) + lane, 2 * wn1 + 1, tid, lane);
+        qb += SLICES_PER_TILE;
       }
+      tm.mark(5);
+    }
 
-      // ---- main loop (as gemm_tile_kernel; the ring and its barrier phases persist across tasks) ----
-      if (nslices > 0) {
-        const int a_lane = ((wm * 8) << 5) + lane;
-        const int b_lane = ((wn * 4) << 5) + lane;
-        double af[2][8], bf[2][4];
-        {
-          const unsigned st0 = qg % NST;
-          mbar_wait(&full_bar[st0], (qg / NST) & 1);
-          const double* As = stages + st0 * GEMM_STAGE_DOUBLES + a_lane;
-          const double* Bs = stages + st0 * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
-#pragma unroll
-          for (int v = 0; v < 8; ++v) af[0][v] = As[v << 5];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) bf[0][v] = Bs[v << 5];
-        }
-        for (int q = 0; q < nslices; ++q) {
-          const unsigned qa = qg + q, st = qa % NST;
-          {
-            const int qn = q + 2;
-            if (tid == 0 && qn < nslices) {
-              const unsigned qq = qg + qn, sn = qq % NST, u = qq / NST;
-              if (u > 0) mbar_wait(&empty_bar[sn], (u - 1) & 1);
-              double* dst = stages + sn * GEMM_STAGE_DOUBLES;
-              mbar_expect_tx(&full_bar[sn], 2 * SLICE_ELEMS * sizeof(double));
-              bulk_g2s(dst, Asrc + (size_t)qn * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
-              bulk_g2s(dst + SLICE_ELEMS, Bsrc + (size_t)qn * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
-            }
-            __syncwarp();
-          }
-          const double* As = stages + st * GEMM_STAGE_DOUBLES + a_lane;
-          const double* Bs = stages + st * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const int cur = kk & 1, nxt = cur ^ 1;
-            if (kk < 3) {
-#pragma unroll
-              for (int v = 0; v < 8; ++v) af[nxt][v] = As[(((kk + 1) * 16 + v) << 5)];
-#pragma unroll
-              for (int v = 0; v < 4; ++v) bf[nxt][v] = Bs[(((kk + 1) * 16 + v) << 5)];
-            } else if (q + 1 < nslices) {
-              const unsigned qb = qa + 1, sn = qb % NST;
-              mbar_wait(&full_bar[sn], (qb / NST) & 1);
-              const double* An = stages + sn * GEMM_STAGE_DOUBLES + a_lane;
-              const double* Bn = stages + sn * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
-#pragma unroll
-              for (int v = 0; v < 8; ++v) af[nxt][v] = An[v << 5];
-#pragma unroll
-              for (int v = 0; v < 4; ++v) bf[nxt][v] = Bn[v << 5];
-            }
-            if (q <= q_last) {   // warp-uniform
-#pragma unroll
-              for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
-            }
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty_bar[st]);
-        }
-        qg += nslices;
-      }
-
+    {
+      const int wn = (type == DAG_TASK_OFF) ? wn1 : wn0;
+      if (aborted) {
+        // nothing to store
+      } else
       // ---- epilogues ---------------------------------------------------------------------------
-      if (type == DAG_TASK_OFF && phase == 0) {
-        // C = -acc to the workspace (operand order): it is the A operand of the solve phase
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-            for (int v1 = 0; v1 < 2; ++v1) {
-              const int R = wm * 64 + mi * 16 + gq + 8 * v1;
-              const int C = wn * 32 + ni * 8 + 2 * tig;
-              double2 o;
-              o.x = -acc[mi][ni][2 * v1 + 0];
-              o.y = -acc[mi][ni][2 * v1 + 1];
-              *reinterpret_cast<double2*>(Ct + tile_off(R, C)) = o;
-            }
-        fence_proxy_async();   // generic writes before this CTA's bulk copies read them back (barrier follows in phase 1)
-      } else if (type == DAG_TASK_OFF) {
+      if (type == DAG_TASK_OFF) {
         // X = acc is L(i,k): store it and fold r_i -= X z_k
-        __syncthreads();   // zs
+        __syncthreads();   // zs; every warp has read its last A fragments from the C tile
         double rowsum[4][2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -374,16 +513,20 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
 #pragma unroll
             for (int v1 = 0; v1 < 2; ++v1) part[wn * TILE + wm * 64 + mi * 16 + gq + 8 * v1] = rowsum[mi][v1];
         }
+        fence_proxy_async();   // X (generic stores) is read by other CTAs' bulk copies; R0 (generic) is the next ring
         __syncthreads();
         if (tid < TILE) {
           const double s = ((part[tid] + part[TILE + tid]) + part[2 * TILE + tid]) + part[3 * TILE + tid];
           double* ri = g.resid + (size_t)b * g.ldr + (size_t)ti * TILE;
           ri[tid] = __ldcg(ri + tid) - s;
         }
-        fence_proxy_async();
-        __threadfence();
         __syncthreads();
-        if (tid == 0) st_release_gpu(rd + ti, tk + 1);
+        // one fence after the barrier covers the whole CTA's stores (fence cumulativity), then the release
+        if (tid == 0) {
+          __threadfence();
+          st_release_gpu(rd + ti, tk + 1);
+        }
+        tm.mark(6);
       } else {
         // ---- diagonal tile: S = -acc (column-major, ld = PB_LD), residual row, sweep ----
         __syncthreads();   // every warp has left the ring: S aliases it
@@ -403,7 +546,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           for (int r = TILE + 1; r < PB_LD; ++r) S[r + (size_t)tid * PB_LD] = 0.0;
         }
         __syncthreads();
-        cta_block_sweep<true, DAG_THREADS / 32>(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, Dm, wv);
+        tm.mark(7);
+        cta_block_sweep<true, DAG_THREADS / 32>(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, Dm, wv, &tm);
 
         double ld_part = 0.0, q_part = 0.0;
         int first_bad = 0x7fffffff, nan_seen = 0;
@@ -432,6 +576,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         }
         if (tid < TILE) isd_s[tid] = isd;
         __syncthreads();
+        tm.mark(11);
         for (int e2 = tid; e2 < TILE_ELEMS / 2; e2 += DAG_THREADS) {
           const int e = 2 * e2;
           const int kg = e >> 9, m8 = (e >> 5) & 15, gg = (e >> 2) & 7, k3 = e & 3;
@@ -442,12 +587,21 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           o.y = (C + 1 < R) ? S[C + 1 + (size_t)R * PB_LD] * s : (C + 1 == R ? s : 0.0);
           reinterpret_cast<double2*>(Ct)[e2] = o;
         }
-        fence_proxy_async();   // S (generic) before the ring is refilled; inv(L_kk) before other CTAs' bulk copies
-        __threadfence();
+        fence_proxy_async();   // S, PA ... (generic) before the rings are refilled; inv(L_kk) before other CTAs' bulk copies
         __syncthreads();
-        if (tid == 0) st_release_gpu(rd + tk, tk + 1);
+        if (tid == 0) {
+          __threadfence();
+          st_release_gpu(rd + tk, tk + 1);
+        }
+        tm.mark(12);
       }
     }
-    __syncthreads();   // s_task / tis / tjs / zs / part are rewritten by the next task
+    ++n_local;
+    __syncthreads();   // s_task / zs / part are rewritten by the next task
+    tm.mark(15);
   }
+#ifdef DAG_TIMING
+  if (tid == 0)
+    for (int i = 0; i < 16; ++i) atomicAdd(&g_dag_timing[i], (unsigned long long)tm.a[i]);
+#endif
 }

@@ -62,7 +62,7 @@ __host__ __device__ inline size_t mid_buf_doubles(int R) {
 }
 __host__ inline size_t mid_smem_bytes(int N) {
   const int R = mid_npad(N), nw = mid_warps(N);
-  return (mid_buf_doubles(R) + 4 * (size_t)R + (size_t)nw * 32 + 32 * MID_INV_LD + 32 + 32 + 16 + 32 * 17 + MRV_MAX_MODPAR +
+  return (mid_buf_doubles(R) + 6 * (size_t)R + (size_t)nw * 32 + 32 * MID_INV_LD + 32 + 32 + 16 + 32 * 17 + MRV_MAX_MODPAR +
           MRV_MAX_HP + 32 + 16 + 2 * MID_STAGES) * sizeof(double);
 }
 
@@ -268,8 +268,8 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
   constexpr int FW = NWM;                   // the dedicated factor warp
   const int N = D.N, R = mid_npad(N), nblk = R / MID_NB;
   double* buf = smem;                       // ring of operand slices  |  panel in operand order
-  double* ts = buf + mid_buf_doubles(R);    // R   t (zero padded)
-  double* r = ts + R;                       // R   residual (zero padded)
+  double* ts = buf + mid_buf_doubles(R);    // 3 R  t (zero padded), phase cosine, phase sine of every point
+  double* r = ts + 3 * R;                   // R   residual (zero padded)
   double* dvec = r + R;                     // R   pivots
   double* zvec = dvec + R;                  // R   z = L^-1 r
   double* rpart = zvec + R;                 // NWM x 32  per-warp partials of the residual update
@@ -340,6 +340,13 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
     __syncthreads();
 
     const CovParams cp = make_cov_params(D.kernel_id, D.variant, hpv);
+    for (int i = tid; i < R; i += NT) {
+      double c = 1.0, s = 0.0;
+      if (i < N) cov_point_phase(cp, ts[i] - D.t_ref, c, s);
+      ts[R + i] = c;
+      ts[2 * R + i] = s;
+    }
+    __syncthreads();
     int fb = 0x7fffffff, fb_nan = 0;   // first non-positive pivot (tracked by the factor warp)
 
     // -K for column half h (columns 16 h .. 16 h + 15) of the m16 row fragments f = warp + NWM s of panel jj
@@ -355,11 +362,11 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
           if (f < Fj) {
             const int gi0 = rw0 + 16 * f + gq, gj0 = rw0 + 8 * ni + 2 * tig;
             if (f >= 2 && rw0 + 16 * f + 15 < N) {   // warp-uniform: below the diagonal block, no padding
-              const Cov4 c4 = gen_interior4(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1]);
+              const Cov4 c4 = gen_interior4(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, ts, R, gi0, ts, R, gj0);
               acc[s][ni][0] = -c4.v0; acc[s][ni][1] = -c4.v1; acc[s][ni][2] = -c4.v2; acc[s][ni][3] = -c4.v3;
             } else {
               double frag[4];
-              gen_fragment4(cp, N, gi0, gj0, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1], yerr, frag);
+              gen_fragment4(cp, N, gi0, gj0, ts, R, gi0, ts, R, gj0, yerr, frag);
 #pragma unroll
               for (int v = 0; v < 4; ++v) acc[s][ni][v] = -frag[v];
             }
@@ -481,10 +488,10 @@ mid_logl_kernel(ProblemDesc D, const double* __restrict__ t, const double* __res
             const int gi0 = 16 * f + gq, gj0 = 8 * ni + 2 * tig;
             double frag[4];
             if (f >= 2 && 16 * f + 15 < N) {
-              const Cov4 c4 = gen_interior4(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1]);
+              const Cov4 c4 = gen_interior4(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, ts, R, gi0, ts, R, gj0);
               frag[0] = c4.v0; frag[1] = c4.v1; frag[2] = c4.v2; frag[3] = c4.v3;
             } else {
-              gen_fragment4(cp, N, gi0, gj0, ts[gi0], ts[gi0 + 8], ts[gj0], ts[gj0 + 1], yerr, frag);
+              gen_fragment4(cp, N, gi0, gj0, ts, R, gi0, ts, R, gj0, yerr, frag);
             }
 #pragma unroll
             for (int v1 = 0; v1 < 2; ++v1) {

@@ -21,7 +21,7 @@
 
 __host__ __device__ inline int small_ld(int N) { return (N + 1) | 1; }
 __host__ inline size_t small_smem_bytes(int N) {
-  return ((size_t)small_ld(N) * N + 2 * (size_t)N + MRV_MAX_MODPAR + MRV_MAX_HP + 40) * sizeof(double);
+  return ((size_t)small_ld(N) * N + 4 * (size_t)N + MRV_MAX_MODPAR + MRV_MAX_HP + 40) * sizeof(double);
 }
 
 __global__ void __launch_bounds__(MRV_SMALL_THREADS)
@@ -33,8 +33,8 @@ fused_small_logl_kernel(ProblemDesc D, const double* __restrict__ t, const doubl
   extern __shared__ double smem[];
   const int N = D.N, ld = small_ld(N);
   double* S = smem;                         // ld x N, column major; row N = residual row
-  double* ts = S + (size_t)ld * N;          // N
-  double* r = ts + N;                       // N
+  double* ts = S + (size_t)ld * N;          // 3 N: t, phase cosine, phase sine of every point (cov_pair_n)
+  double* r = ts + 3 * N;                   // N
   double* phys = r + N;                     // MRV_MAX_MODPAR
   double* hpv = phys + MRV_MAX_MODPAR;      // MRV_MAX_HP
   double* red = hpv + MRV_MAX_HP;           // 32
@@ -67,11 +67,16 @@ fused_small_logl_kernel(ProblemDesc D, const double* __restrict__ t, const doubl
 
   // 2. K (lower triangle) + residual row
   const CovParams cp = make_cov_params(D.kernel_id, D.variant, hpv);
+  for (int i = tid; i < N; i += nt) cov_point_phase(cp, ts[i] - D.t_ref, ts[N + i], ts[2 * N + i]);
+  __syncthreads();
   for (int c = warp; c < N; c += nwarps) {
     double* col = S + (size_t)c * ld;
-    const double tc = ts[c];
+    const double tc[1] = {ts[c]}, cc[1] = {ts[N + c]}, sc[1] = {ts[2 * N + c]};
     for (int i = c + lane; i < N; i += 32) {
-      const double v = (i == c) ? cov_diag(cp, yerr[i]) : cov_eval(cp, ts[i], tc);
+      const double ti1[1] = {ts[i]}, ci1[1] = {ts[N + i]}, si1[1] = {ts[2 * N + i]};
+      double ev[1];
+      cov_pair_n<1>(cp, ti1, ci1, si1, tc, cc, sc, ev);
+      const double v = (i == c) ? cov_diag(cp, yerr[i]) : ev[0];
       bad |= !isfinite(v);
       col[i] = v;
     }
@@ -136,7 +141,7 @@ __host__ __device__ inline int sblk_ld(int N) {
 }
 __host__ inline size_t small_blk_smem_bytes(int N) {
   const int nc = sblk_cols(N), ld = sblk_ld(N);
-  return (sweep_packed_doubles(ld, nc) + PB_NB * (size_t)(ld + 12) + PB_NB * (size_t)(nc + 4) + PB_NB * PB_D_LD + PB_NB + 2 * (size_t)N +
+  return (sweep_packed_doubles(ld, nc) + PB_NB * (size_t)(ld + 12) + PB_NB * (size_t)(nc + 4) + PB_NB * PB_D_LD + PB_NB + 4 * (size_t)N +
           MRV_MAX_MODPAR + MRV_MAX_HP + 40) * sizeof(double);
 }
 
@@ -156,8 +161,8 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   double* PBm = PA + PB_NB * pa_ld;
   double* Dblk = PBm + PB_NB * pb_ld;
   double* wv = Dblk + PB_NB * PB_D_LD;
-  double* ts = wv + PB_NB;                   // N
-  double* r = ts + N;                        // N
+  double* ts = wv + PB_NB;                   // 3 N: t, phase cosine, phase sine of every point (cov_pair_n)
+  double* r = ts + 3 * N;                    // N
   double* phys = r + N;                      // MRV_MAX_MODPAR
   double* hpv = phys + MRV_MAX_MODPAR;       // MRV_MAX_HP
   double* red = hpv + MRV_MAX_HP;            // 32
@@ -202,6 +207,8 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   //     (c, N-1-c), whose lower-triangle lengths add up to N+1, and every lane evaluates two
   //     independent entries per trip (ILP across the fp64 exp/sin dependency chains).
   const CovParams cp = make_cov_params(D.kernel_id, D.variant, hpv);
+  for (int i = tid; i < N; i += nt) cov_point_phase(cp, ts[i] - D.t_ref, ts[N + i], ts[2 * N + i]);
+  __syncthreads();
   // zero-lag value + jitter once per walker: K_ii = (k(0) + jit^2) + yerr_i^2, the order of cov_diag().  Inside
   // the `(i == c) ? cov_diag(...) : ev` selects the compiler evaluated k(0) -- a full exp / sin -- per element.
   const double kdiag0 = cov_from_dist(cp, 0.0, 0.0) + cp.jit2;
@@ -216,11 +223,11 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
       const int c0 = (v0 < lenA) ? cA : cB, i0 = (v0 < lenA) ? cA + v0 : cB + (v0 - lenA);
       const int c1 = (!ok1 || v1 < lenA) ? cA : cB;
       const int i1 = !ok1 ? cA : ((v1 < lenA) ? cA + v1 : cB + (v1 - lenA));
-      // both evaluations through one switch so their exp / sin chains interleave (ILP 2)
-      const double dt0 = ts[i0] - ts[c0], dt1 = ts[i1] - ts[c1];
-      const double dd[2] = {fabs(dt0), fabs(dt1)}, dd2[2] = {dt0 * dt0, dt1 * dt1};
+      // both evaluations through one switch so their exp chains interleave (ILP 2)
+      const double pti[2] = {ts[i0], ts[i1]}, pci[2] = {ts[N + i0], ts[N + i1]}, psi[2] = {ts[2 * N + i0], ts[2 * N + i1]};
+      const double ptj[2] = {ts[c0], ts[c1]}, pcj[2] = {ts[N + c0], ts[N + c1]}, psj[2] = {ts[2 * N + c0], ts[2 * N + c1]};
       double ev[2];
-      cov_from_dist_n<2>(cp, dd, dd2, ev);
+      cov_pair_n<2>(cp, pti, pci, psi, ptj, pcj, psj, ev);
       double e0 = ev[0], e1 = ev[1];
       if (i0 == c0) {
         const double ye = yerr[i0];
