@@ -561,7 +561,7 @@ static bool use_dag(const mrv_problem* p) {
   return p->nt <= DAG_AUTO_MAX_TILES;
 }
 
-static int run_wave_dag(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so) {
+static int run_wave_dag(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so, int wave_index) {
   const ProblemDesc& D = p->desc;
   const int nt = p->nt;
   DagArgs g;
@@ -585,15 +585,14 @@ static int run_wave_dag(mrv_problem* p, const double* d_hp, int64_t w0, int64_t 
   g.resid = p->resid.as<double>() + (size_t)w0 * p->n_pad;
   g.ldr = p->n_pad;
   g.zcols = p->zcols.as<double>();
-  g.rowdone = p->rowdone.as<int>();
-  g.counter = p->counter.as<int>();
+  g.rowdone = p->rowdone.as<int>() + (size_t)w0 * nt;          // cleared for all walkers by phase_table_kernel
+  g.abort_flag = p->counter.as<int>();                         // [0] abort flag of the batch, [1 + wave] task counters
+  g.counter = p->counter.as<int>() + 1 + wave_index;
   g.acc_logdet = p->logdet.as<double>() + w0;
   g.acc_quad = p->quad.as<double>() + w0;
   g.status = p->fstatus.as<int>() + w0;
   g.zout = so.z ? so.z + (size_t)w0 * so.ldz : nullptr;
   g.ldz = so.ldz;
-  CU(cudaMemsetAsync(p->rowdone.p, 0, (size_t)B * nt * sizeof(int), st));
-  CU(cudaMemsetAsync(p->counter.p, 0, sizeof(int), st));     // task counter; [1] = abort flag, cleared once per batch
   const unsigned grid = (unsigned)std::min<long long>(total, p->num_sms);
   const double fl = ((double)D.N * D.N * D.N / 3.0 + 2.0 * D.N * D.N) * (double)B;
   const double T3 = (double)TILE * TILE * TILE;
@@ -721,25 +720,24 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   if ((rc = p->quad.ensure((size_t)W * sizeof(double)))) return rc;
   if ((rc = p->fstatus.ensure((size_t)W * sizeof(int)))) return rc;
   if ((rc = p->zbuf.ensure((size_t)B * TILE * sizeof(double)))) return rc;
-  if ((rc = p->counter.ensure(64))) return rc;
+  const int64_t n_waves = (W + B - 1) / B;
+  if ((rc = p->counter.ensure((size_t)(n_waves + 2) * sizeof(int)))) return rc;
   if ((rc = p->factor.ensure((size_t)B * walker_bytes))) return rc;
   const bool dag = use_dag(p);
   if (dag) {
     if ((rc = p->zcols.ensure((size_t)B * nt * TILE * sizeof(double)))) return rc;
-    if ((rc = p->rowdone.ensure((size_t)B * nt * sizeof(int)))) return rc;
-    CU(cudaMemsetAsync(p->counter.p, 0, 4 * sizeof(int), st));
+    if ((rc = p->rowdone.ensure((size_t)W * nt * sizeof(int)))) return rc;
   }
 
   if ((rc = p->phase.ensure((size_t)W * 2 * p->n_pad * sizeof(double)))) return rc;
   if ((rc = p->cpar.ensure((size_t)W * 8 * sizeof(double)))) return rc;
   p->prof.begin(CAT_GEN, st, 0.0, 0.0);
-  phase_table_kernel<<<dim3((unsigned)std::min(8, (p->n_pad + 255) / 256), (unsigned)W), 256, 0, st>>>(
-      D.N, p->n_pad, D.t_ref, D.kernel_id, D.variant, D.nh, p->d_t, d_hp, p->phase.as<double>(), p->cpar.as<double>());
+  phase_table_kernel<<<dim3((unsigned)std::min(8, (p->n_pad + 255) / 256), (unsigned)std::min<int64_t>(W, 65535)), 256, 0, st>>>(
+      D.N, p->n_pad, (int)W, D.t_ref, D.kernel_id, D.variant, D.nh, p->d_t, d_hp, p->phase.as<double>(), p->cpar.as<double>(),
+      p->logdet.as<double>(), p->quad.as<double>(), p->fstatus.as<int>(), dag ? p->rowdone.as<int>() : nullptr, nt,
+      p->counter.as<int>(), (int)(n_waves + 2));
   p->prof.end(st);
   p->launches++;
-  CU(cudaMemsetAsync(p->logdet.p, 0, (size_t)W * sizeof(double), st));
-  CU(cudaMemsetAsync(p->quad.p, 0, (size_t)W * sizeof(double), st));
-  CU(cudaMemsetAsync(p->fstatus.p, 0, (size_t)W * sizeof(int), st));
   cudaStream_t mst = st;
   p->mean_pending = p->has_kepler && d_model_given == nullptr && p->mean_overlap_opt != 0 && !dag;
   if (p->mean_pending) {
@@ -779,7 +777,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
     const int64_t Bw = std::min<int64_t>(B, W - w0);
     const int parts = (int)std::min<int64_t>(nsub, Bw);
     if (dag) {
-      if ((rc = run_wave_dag(p, d_hp, w0, Bw, st, so))) return rc;
+      if ((rc = run_wave_dag(p, d_hp, w0, Bw, st, so, (int)(w0 / B)))) return rc;
     } else if (parts > 1) {
       CU(cudaEventRecord(p->ev_fork, st));
       int64_t off = 0;
@@ -802,7 +800,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   finalize_logl_kernel<<<(unsigned)((W + 127) / 128), 128, 0, st>>>(D, (int)W, d_hp, p->phys.as<double>(),
                                                                     p->logdet.as<double>(), p->quad.as<double>(),
                                                                     p->nonfinite.as<int>(), p->fstatus.as<int>(), d_logl,
-                                                                    d_status, so.logdet, dag ? p->counter.as<int>() + 1 : nullptr);
+                                                                    d_status, so.logdet, dag ? p->counter.as<int>() : nullptr);
   p->prof.end(st);
   p->launches++;
   CU(cudaGetLastError());

@@ -169,21 +169,38 @@ __device__ __noinline__ void gen_fragment8(const CovParams& cp, int N, int gi0, 
 // N sincospi per walker.  Padding points get (1, 0); they are never used (padding entries are the identity).
 // Also writes the walker's covariance constants (a2, c1, c2, c3, jit2, 0, 0, 0) for the dataflow kernel, which
 // fetches them with the points instead of recomputing the reciprocals in every tile task.
+// It is the first kernel of every batch of the tiled paths, so it also clears the per-walker accumulators
+// (log det, quadratic form, factorisation status), the tile-row progress counters of the dataflow kernel and its
+// task counters / abort flag -- five memset launches less per batch.
 __global__ void __launch_bounds__(256)
-phase_table_kernel(int N, int n_pad, double t_ref, int kernel_id, int variant, int nh, const double* __restrict__ t,
-                   const double* __restrict__ hp_all, double* __restrict__ ph, double* __restrict__ cpar) {
-  const int w = blockIdx.y;
-  const CovParams cp = make_cov_params(kernel_id, variant, hp_all + (size_t)w * nh);
-  if (blockIdx.x == 0 && threadIdx.x < 8) {
-    const double v[8] = {cp.a2, cp.c1, cp.c2, cp.c3, cp.jit2, 0.0, 0.0, 0.0};
-    cpar[(size_t)w * 8 + threadIdx.x] = v[threadIdx.x];
-  }
-  double* dst = ph + (size_t)w * 2 * n_pad;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
-    double c = 1.0, s = 0.0;
-    if (i < N) cov_point_phase(cp, t[i] - t_ref, c, s);
-    dst[i] = c;
-    dst[n_pad + i] = s;
+phase_table_kernel(int N, int n_pad, int W, double t_ref, int kernel_id, int variant, int nh, const double* __restrict__ t,
+                   const double* __restrict__ hp_all, double* __restrict__ ph, double* __restrict__ cpar,
+                   double* __restrict__ acc_logdet, double* __restrict__ acc_quad, int* __restrict__ fstatus,
+                   int* __restrict__ rowdone, int rowdone_per_walker, int* __restrict__ counters, int n_counters) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && counters != nullptr)
+    for (int i = threadIdx.x; i < n_counters; i += blockDim.x) counters[i] = 0;
+  for (int w = blockIdx.y; w < W; w += gridDim.y) {
+    const CovParams cp = make_cov_params(kernel_id, variant, hp_all + (size_t)w * nh);
+    if (blockIdx.x == 0) {
+      if (threadIdx.x < 8) {
+        const double v[8] = {cp.a2, cp.c1, cp.c2, cp.c3, cp.jit2, 0.0, 0.0, 0.0};
+        cpar[(size_t)w * 8 + threadIdx.x] = v[threadIdx.x];
+      }
+      if (threadIdx.x == 8) {
+        acc_logdet[w] = 0.0;
+        acc_quad[w] = 0.0;
+        fstatus[w] = 0;
+      }
+      if (rowdone != nullptr)
+        for (int i = threadIdx.x; i < rowdone_per_walker; i += blockDim.x) rowdone[(size_t)w * rowdone_per_walker + i] = 0;
+    }
+    double* dst = ph + (size_t)w * 2 * n_pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += gridDim.x * blockDim.x) {
+      double c = 1.0, s = 0.0;
+      if (i < N) cov_point_phase(cp, t[i] - t_ref, c, s);
+      dst[i] = c;
+      dst[n_pad + i] = s;
+    }
   }
 }
 
@@ -432,6 +449,8 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
         D[r * PB_D_LD + c] = v;
       }
       __syncthreads();
+      // (every thread divides by the pivot itself: letting the owner of element (j + 1, j + 1) compute the reciprocal
+      // once and publish it measured 7 % SLOWER -- the division then sits between the update and the barrier)
       for (int j = 0; j < PB_NB - 1; ++j) {
         if (in_blk && c > j && (r >= c || r <= j)) {
           const double w = 1.0 / D[j * PB_D_LD + j];
@@ -447,41 +466,58 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
         sweep_colp<PACKED>(S, ld, k0 + c)[k0 + r] = v;     // final block (lower: factor, upper: inverse part)
       }
       __syncthreads();
-      // multipliers beta[j][jp] = D[j][jp] / d_jp (j > jp), in place, for the row recurrences below
-      if (in_blk && c < r) D[r * PB_D_LD + c] = v * wv[c];
-      __syncthreads();
     }
     if (ptm) ptm->mark(8);
-    // ---- 2. panel rows ----------------------------------------------------------------------
-    if (tid < ld) {
-      const int rho = tid;
-      const bool pivot_row = rho >= k0 && rho < k0 + PB_NB;
-      const bool active = rho < n_rows && !pivot_row && (WITH_INV || rho >= k0 + PB_NB);
-      double x[PB_NB];
-      if (active) {
+    // ---- 2. panel rows on the tensor pipe ------------------------------------------------------
+    // A row's 16 panel entries x solve x U = a, U unit upper triangular with the block's multipliers; the swept pivot
+    // block holds U^-1 =: G in its upper triangle (its own rows are e_r G), so X = A G for all rows at once:
+    // X^T (16 x rows) = G^T (16 x 16) A^T (16 x rows) as m16n8k4 DMMAs, one n8 tile of 8 rows per step -- instead of
+    // one thread per row running a 120-FMA triangular recurrence (11 of the 46 us of a 128 x 128 diagonal tile).
+    {
+      const int n_n8p = n_rows8 / 8;
+      double gt0[4], gt1[4];   // G^T fragments: rows j = gq and gq + 8, columns jp = 4 kk + tig
 #pragma unroll
-        for (int j = 0; j < PB_NB; ++j) x[j] = sweep_colp<PACKED>(S, ld, k0 + j)[rho];
-        // right-looking order: the inner updates are independent (ILP), only x[jp] is on the chain
-#pragma unroll
-        for (int jp = 0; jp < PB_NB - 1; ++jp) {
-#pragma unroll
-          for (int j = jp + 1; j < PB_NB; ++j) x[j] = fma(-x[jp], D[j * PB_D_LD + jp], x[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < PB_NB; ++j) sweep_colp<PACKED>(S, ld, k0 + j)[rho] = x[j];
-      } else if (pivot_row) {
-        const int r = rho - k0;
-#pragma unroll
-        for (int j = 0; j < PB_NB; ++j) x[j] = (j == r) ? 1.0 : (j > r ? D[r * PB_D_LD + j] : 0.0);
-      } else {
-#pragma unroll
-        for (int j = 0; j < PB_NB; ++j) x[j] = 0.0;
+      for (int kk = 0; kk < 4; ++kk) {
+        const int jp = 4 * kk + tig;
+        gt0[kk] = (jp < gq) ? D[jp * PB_D_LD + gq] : (jp == gq ? 1.0 : 0.0);
+        gt1[kk] = (jp < gq + 8) ? D[jp * PB_D_LD + gq + 8] : (jp == gq + 8 ? 1.0 : 0.0);
       }
+      for (int tn = warp; tn < n_n8p; tn += NWARPS) {
+        const int rho0 = tn * 8;
+        const bool pivot_tile = rho0 >= k0 && rho0 < k0 + PB_NB;
+        const bool above = rho0 < k0;                          // inverse rows (kept only WITH_INV)
+        const bool compute = !pivot_tile && (WITH_INV || !above);
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (compute) {
 #pragma unroll
-      for (int j = 0; j < PB_NB; ++j) PA[j * pa_ld + rho] = x[j];
-      if (rho < n_cols) {
+          for (int kk = 0; kk < 4; ++kk)
+            dmma_1684_neg0(acc, gt0[kk], gt1[kk], sweep_colp<PACKED>(S, ld, k0 + 4 * kk + tig)[rho0 + gq]);
+        }
+        const int rhoA = rho0 + 2 * tig;                       // this lane's two rows: rhoA, rhoA + 1
 #pragma unroll
-        for (int j = 0; j < PB_NB; ++j) PB[j * pb_ld + rho] = (rho >= k0 + PB_NB && rho < n_cols) ? -x[j] * wv[j] : 0.0;
+        for (int h = 0; h < 2; ++h) {
+          const int j = gq + 8 * h;
+          double2 x;
+          x.x = acc[2 * h];
+          x.y = acc[2 * h + 1];
+          if (pivot_tile) {
+            const int r0 = rhoA - k0, r1 = r0 + 1;
+            x.x = (j == r0) ? 1.0 : (j > r0 ? D[r0 * PB_D_LD + j] : 0.0);
+            x.y = (j == r1) ? 1.0 : (j > r1 ? D[r1 * PB_D_LD + j] : 0.0);
+          } else if (compute) {
+            if (rhoA >= n_rows) x.x = 0.0;                     // padding rows below the residual row stay zero
+            if (rhoA + 1 >= n_rows) x.y = 0.0;
+            *reinterpret_cast<double2*>(sweep_colp<PACKED>(S, ld, k0 + j) + rhoA) = x;
+          }
+          *reinterpret_cast<double2*>(PA + j * pa_ld + rhoA) = x;
+          if (rhoA < n_cols) {
+            const double w = wv[j];
+            double2 y;
+            y.x = (rhoA >= k0 + PB_NB) ? -x.x * w : 0.0;
+            y.y = (rhoA + 1 >= k0 + PB_NB && rhoA + 1 < n_cols) ? -x.y * w : 0.0;
+            *reinterpret_cast<double2*>(PB + j * pb_ld + rhoA) = y;
+          }
+        }
       }
     }
     __syncthreads();

@@ -48,7 +48,8 @@ struct DagArgs {
   int ldr;
   double* zcols;           // [B, nt, 128]  z_k per tile column
   int* rowdone;            // [B, nt]
-  int* counter;            // [0] task counter, [1] abort flag
+  int* counter;            // this wave's task counter
+  int* abort_flag;         // one per batch (sticky across its waves)
   double* acc_logdet;      // [B]
   double* acc_quad;
   int* status;
@@ -251,7 +252,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = (warp >> 2) & 1;
   const int gq = lane >> 2, tig = lane & 3;
-  int* abort_flag = g.counter + 1;
+  int* abort_flag = g.abort_flag;
   const int n_pad = g.nt * TILE;
 
   if (tid == 0) {
