@@ -552,13 +552,13 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
   return 0;
 }
 
-// Tiled path as ONE persistent dataflow kernel per wave (dag.cuh).  Measured against the launch-per-column loop
-// above (tools/sweep_c5.py, profiles/README.md) it wins wherever the wave does not fill many rounds of CTAs per
-// launch, i.e. up to N = 4096; above that the right-looking panels of run_wave re-use operands better.
+// Tiled path as ONE persistent dataflow kernel per wave (dag.cuh).  Left-looking by tiles: every tile streams its
+// operands once per tile (16 flop per operand byte, 2.3 TB/s at the DMMA peak -- affordable up to N = 4096, where a
+// walker's factor is 67 MB); above that the right-looking panels of run_wave re-use operands better.
 static bool use_dag(const mrv_problem* p) {
   if (p->tiled_impl == 1) return false;
   if (p->tiled_impl == 2) return p->nt <= 128;
-  return p->nt <= DAG_AUTO_MAX_TILES;
+  return p->nt >= DAG_AUTO_MIN_TILES && p->nt <= DAG_AUTO_MAX_TILES;
 }
 
 static int run_wave_dag(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so, int wave_index) {

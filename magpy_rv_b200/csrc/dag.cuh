@@ -58,7 +58,11 @@ struct DagArgs {
 };
 
 #define DAG_THREADS 256
-#define DAG_AUTO_MAX_TILES 0          // automatic choice: tile columns up to which the dataflow kernel replaces run_wave
+// automatic choice (measured, tools/dag_probe.py, one B200, 128 walkers): the dataflow kernel wins from 6 tile columns
+// (N > 640: 1.01x at 768, 1.08x at 1024, 1.01x at 2048, 1.03x at 4096) and is bitwise identical; below that the
+// launch-per-column loop with its 16-warp diagonal-tile kernel is 2-4 % ahead (N = 500, 640)
+#define DAG_AUTO_MIN_TILES 6
+#define DAG_AUTO_MAX_TILES 32
 #define DAG_BSTAGES 3                 // ring of inv(L_kk) k16 slices for the solve phase
 #define DAG_SWEEP_DOUBLES (PB_LD * TILE + PB_NB * PB_PA_LD + PB_NB * PB_PB_LD + PB_NB * PB_D_LD + PB_NB + 64 + TILE)
 #define DAG_R1_OFFSET (GEMM_TMA_STAGES * GEMM_STAGE_DOUBLES)   // doubles: end of the update ring / C tile
@@ -514,7 +518,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
 #pragma unroll
             for (int v1 = 0; v1 < 2; ++v1) part[wn * TILE + wm * 64 + mi * 16 + gq + 8 * v1] = rowsum[mi][v1];
         }
-        fence_proxy_async();   // X (generic stores) is read by other CTAs' bulk copies; R0 (generic) is the next ring
+        // (no proxy fence here: a per-thread fence.proxy.async after 128 KiB of global stores waits for them to drain,
+        // ~1 us per tile.  Readers of X order their bulk copies behind it on THEIR side -- acquire of the progress
+        // counter, then fence.proxy.async --, and the reuse of R0 by the next bulk copies is ordered by the barriers.)
         __syncthreads();
         if (tid < TILE) {
           const double s = ((part[tid] + part[TILE + tid]) + part[2 * TILE + tid]) + part[3 * TILE + tid];
@@ -588,8 +594,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           o.y = (C + 1 < R) ? S[C + 1 + (size_t)R * PB_LD] * s : (C + 1 == R ? s : 0.0);
           reinterpret_cast<double2*>(Ct)[e2] = o;
         }
-        fence_proxy_async();   // S, PA ... (generic) before the rings are refilled; inv(L_kk) before other CTAs' bulk copies
-        __syncthreads();
+        __syncthreads();       // (readers of inv(L_kk) fence on their side, see the solve epilogue)
         if (tid == 0) {
           __threadfence();
           st_release_gpu(rd + tk, tk + 1);
