@@ -106,6 +106,12 @@ int mrv_logl_given_model(mrv_problem* p, const double* hp, const double* modpar,
 int mrv_solve_batch(mrv_problem* p, const double* hp, const double* rhs, int64_t W, double* z_out,
                     double* logdet_out, int32_t* status_out);
 
+/* The same for R right-hand sides and ONE hyper-parameter set hp [nh]: K is factorised once and every right-hand side
+ * is swept through the stored factor (what GPLikelihood.predict needs: L^-1 [y | Ks^T], gp_likelihood.py:429-441).
+ * rhs [R, N]; z_out [R, N], logdet_out [1] (may be NULL), status_out [1]. */
+int mrv_solve_multi(mrv_problem* p, const double* hp, const double* rhs, int64_t R, double* z_out,
+                    double* logdet_out, int32_t* status_out);
+
 /* Prediction reductions on the device: V [Np, N] (rows L^-1 Ks_p^T), z [N] (= L^-1 y), Kss [Np, Np]:
  * mean_out[p] = V_p . z;  cov_out = Kss - V V^T ([Np, Np]) when full_cov, else the Np variances
  * Kss_pp - |V_p|^2 (gp_likelihood.py:435-441, 476-481). */

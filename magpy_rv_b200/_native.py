@@ -43,6 +43,8 @@ SIGNATURES = {
                                             c_double_p, c_int32_p]),
     "mrv_solve_batch": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int64, c_double_p, c_double_p,
                                        c_int32_p]),
+    "mrv_solve_multi": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int64, c_double_p, c_double_p,
+                                       c_int32_p]),
     "mrv_predict_reduce": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, c_double_p, ctypes.c_int64,
                                           ctypes.c_int64, ctypes.c_int, c_double_p, c_double_p]),
     "mrv_model_eval": (ctypes.c_int, [ctypes.c_int, c_double_p, c_double_p, ctypes.c_int64,

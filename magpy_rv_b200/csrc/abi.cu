@@ -2,6 +2,7 @@
 // the blocked factorisation, dense helpers, FP64 tensor-pipe microbenchmark.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost ~ns unless a profiler is attached
 
 #include <algorithm>
 #include <cstdarg>
@@ -42,11 +43,14 @@ static int fail(int code, const char* fmt, ...) {
 
 #define SMALL_N_MAX 166   // largest N whose (N + 1) x N matrix + 4 N point / residual doubles fit 227 KB of shared memory
 
+static unsigned long long g_buf_gen = 0;   // bumped by every (re)allocation: captured CUDA graphs hold raw pointers
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
   int ensure(size_t need) {
     if (need <= bytes) return 0;
+    ++g_buf_gen;
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
@@ -72,6 +76,7 @@ struct PinBuf {
   size_t bytes = 0;
   int ensure(size_t need) {
     if (need <= bytes) return 0;
+    ++g_buf_gen;
     if (p) cudaFreeHost(p);
     p = nullptr;
     bytes = 0;
@@ -111,13 +116,17 @@ struct Prof {
     cudaEventCreate(&e);
     return e;
   }
+  // every kernel category is also an NVTX range on the host (gen, potrf, trsm, update_*, mean, final, fused, dag):
+  // nsys / ncu --nvtx show the phases of a batch; the reference has only a wall-clock print (mcmc.py:778,868)
   void begin(int cat, cudaStream_t st, double alg_f, double exec_f) {
+    nvtxRangePushA(kCatNames[cat]);
     if (!on) return;
     ProfRec r{cat, get(), get(), alg_f, exec_f};
     cudaEventRecord(r.e0, st);
     recs.push_back(r);
   }
   void end(cudaStream_t st) {
+    nvtxRangePop();
     if (!on) return;
     cudaEventRecord(recs.back().e1, st);
   }
@@ -187,6 +196,14 @@ struct mrv_problem {
   DevBuf hp, modpar, model, logl, status;                      // host-API staging (hp holds hp | modpar, logl holds logL | status)
   PinBuf pin_in, pin_out;
   DevBuf resid, escratch, phys, nonfinite, logdet, quad, fstatus, zbuf, factor, counter, midws, zcols, rowdone, phase, cpar;
+  // host-buffer entry point, one-CTA-per-walker paths: copy in -> kernel(s) -> copy out replayed as ONE CUDA graph
+  // launch (three stream operations per batch otherwise; the batch of a tutorial-size MCMC iteration is ~60 us of GPU work)
+  int graph_opt = 1;
+  cudaGraphExec_t graph_exec = nullptr;
+  int64_t graph_W = -1;
+  int graph_to_ecc = -1, graph_state = 0;   // state: 0 = nothing seen, 1 = this key ran eagerly once (buffers exist), 2 = captured
+  unsigned long long graph_buf_gen = 0, opt_gen = 0, graph_opt_gen = 0;
+  int64_t graph_launches = 0, graph_replays = 0;
   int64_t wave_cur = 0;
   int64_t launches = 0;
   int last_path = 0;
@@ -319,6 +336,7 @@ extern "C" void mrv_problem_destroy(mrv_problem* p) {
   p->pin_in.release();
   p->pin_out.release();
   p->prof.destroy();
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   if (p->stream) cudaStreamDestroy(p->stream);
   for (int i = 0; i < 3; ++i) {
     if (p->aux_stream[i]) cudaStreamDestroy(p->aux_stream[i]);
@@ -817,6 +835,10 @@ static int host_logl(mrv_problem* p, const double* hp, const double* modpar, con
                      double* logL_out, int32_t* status_out) {
   if (!p || !hp || !modpar || !logL_out || !status_out) return fail(-1, "null argument");
   if (W <= 0) return 0;
+  struct Range {
+    Range() { nvtxRangePushA("mrv_logl_batch"); }
+    ~Range() { nvtxRangePop(); }
+  } nvtx_range;
   CU(cudaSetDevice(p->device));
   const ProblemDesc& D = p->desc;
   int rc = 0;
@@ -833,15 +855,72 @@ static int host_logl(mrv_problem* p, const double* hp, const double* modpar, con
   double* d_mp = d_hp + n_hp;
   double* d_logl = p->logl.as<double>();
   int* d_status = reinterpret_cast<int*>(d_logl + W);
-  CU(cudaMemcpyAsync(d_hp, h_in, (n_hp + n_mp) * sizeof(double), cudaMemcpyHostToDevice, st));
+
+  // CUDA-graph replay for the single-stream paths: first call of a (W, to_ecc) key runs eagerly (allocations, function
+  // attributes), the second is captured, later ones are one cudaGraphLaunch.  Any reallocation or option change drops it.
+  const int64_t Wsel = p->ensemble_opt > 0 ? std::max<int64_t>(p->ensemble_opt, W) : W;
+  const int path_now = choose_path(p, Wsel);
+  const bool graphable = p->graph_opt && !model_y && !p->prof.on && (path_now == MRV_PATH_FUSED_SMEM || path_now == MRV_PATH_MID);
+  const bool same_key = graphable && p->graph_W == W && p->graph_to_ecc == to_ecc && p->graph_buf_gen == g_buf_gen &&
+                        p->graph_opt_gen == p->opt_gen;
+  if (same_key && p->graph_state == 2) {
+    CU(cudaGraphLaunch(p->graph_exec, st));
+    CU(cudaStreamSynchronize(st));
+    p->launches += p->graph_launches;
+    p->graph_replays++;
+    p->last_path = path_now;
+    memcpy(logL_out, p->pin_out.p, (size_t)W * sizeof(double));
+    memcpy(status_out, static_cast<char*>(p->pin_out.p) + (size_t)W * sizeof(double), (size_t)W * sizeof(int));
+    return 0;
+  }
+  const bool capture = same_key && p->graph_state == 1;
+  if (capture) CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int64_t launches0 = p->launches;
+  cudaError_t ce = cudaMemcpyAsync(d_hp, h_in, (n_hp + n_mp) * sizeof(double), cudaMemcpyHostToDevice, st);
   const double* d_model = nullptr;
-  if (model_y) {
+  if (ce == cudaSuccess && model_y) {
     if ((rc = p->model.ensure((size_t)W * D.N * sizeof(double)))) return rc;
-    CU(cudaMemcpyAsync(p->model.p, model_y, (size_t)W * D.N * sizeof(double), cudaMemcpyHostToDevice, st));
+    ce = cudaMemcpyAsync(p->model.p, model_y, (size_t)W * D.N * sizeof(double), cudaMemcpyHostToDevice, st);
     d_model = p->model.as<double>();
   }
-  if ((rc = run_logl(p, d_hp, d_mp, d_model, W, to_ecc, d_logl, d_status, st))) return rc;
-  CU(cudaMemcpyAsync(p->pin_out.p, d_logl, out_bytes, cudaMemcpyDeviceToHost, st));
+  if (ce == cudaSuccess) rc = run_logl(p, d_hp, d_mp, d_model, W, to_ecc, d_logl, d_status, st);
+  if (ce == cudaSuccess && rc == 0) ce = cudaMemcpyAsync(p->pin_out.p, d_logl, out_bytes, cudaMemcpyDeviceToHost, st);
+  if (capture) {
+    cudaGraph_t graph = nullptr;
+    cudaError_t ee = cudaStreamEndCapture(st, &graph);     // always end the capture, also on errors
+    if (p->graph_exec) {
+      cudaGraphExecDestroy(p->graph_exec);
+      p->graph_exec = nullptr;
+    }
+    p->graph_state = 0;
+    if (ce == cudaSuccess && rc == 0 && ee == cudaSuccess && graph != nullptr &&
+        cudaGraphInstantiate(&p->graph_exec, graph, 0) == cudaSuccess) {
+      p->graph_state = 2;
+      p->graph_launches = p->launches - launches0;
+      p->launches = launches0;                             // nothing ran yet
+    }
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc) return rc;
+    if (p->graph_state != 2) {
+      p->graph_opt = 0;                                    // capture is not possible here: stay eager for this handle
+      return host_logl(p, hp, modpar, model_y, W, to_ecc, logL_out, status_out);
+    }
+    CU(cudaGraphLaunch(p->graph_exec, st));
+    p->launches += p->graph_launches;
+  } else {
+    if (rc) return rc;
+    if (ce != cudaSuccess) return fail(-2, "mrv_logl_batch copy / launch failed: %s", cudaGetErrorString(ce));
+    if (graphable) {                                       // remember the key: the next identical call is captured
+      p->graph_W = W;
+      p->graph_to_ecc = to_ecc;
+      p->graph_buf_gen = g_buf_gen;
+      p->graph_opt_gen = p->opt_gen;
+      p->graph_state = 1;
+    } else {
+      p->graph_state = 0;
+    }
+  }
   CU(cudaStreamSynchronize(st));
   memcpy(logL_out, p->pin_out.p, (size_t)W * sizeof(double));
   memcpy(status_out, static_cast<char*>(p->pin_out.p) + (size_t)W * sizeof(double), (size_t)W * sizeof(int));
@@ -901,6 +980,132 @@ extern "C" int mrv_solve_batch(mrv_problem* p, const double* hp, const double* r
   if (e == cudaSuccess) e = cudaMemcpyAsync(status_out, p->status.p, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return done(fail(-2, "mrv_solve_batch copy-out: %s", cudaGetErrorString(e)));
+  return done(0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// R right-hand sides against ONE factorisation (GPLikelihood.predict: K is factored once, then L^-1 [y | Ks^T]).
+// After a tiled factorisation of one walker the workspace holds L(i,k) in tiles (i,k), i > k, and inv(L_kk) in the
+// diagonal tiles (operand order).  Forward substitution by tile columns: z_k = inv(L_kk) r_k, r_i -= L(i,k) z_k.
+// One CTA owns MRHS right-hand sides for the whole sweep (no inter-CTA dependency); thread = one tile row x half of
+// the CTA's right-hand sides; every tile is read once per CTA as coalesced 32-byte pieces (from L2 after the first CTA).
+// ------------------------------------------------------------------------------------------------
+#define MRHS 8
+__global__ void __launch_bounds__(256)
+multi_rhs_forward_kernel(int nt, const double* __restrict__ A, double* __restrict__ Z, long long ldz, int R) {
+  __shared__ double zk[TILE][MRHS];   // [column][right-hand side]
+  const int tid = threadIdx.x, row = tid & (TILE - 1), half = tid >> 7;
+  const int r0 = blockIdx.x * MRHS;
+  const int v0 = 4 * half;            // this thread's four right-hand sides: r0 + v0 .. r0 + v0 + 3
+  auto tile_times_zk = [&](const double* __restrict__ tile, double (&acc)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = 0.0;
+#pragma unroll 4
+    for (int cg = 0; cg < TILE / 4; ++cg) {
+      const double2* src = reinterpret_cast<const double2*>(tile + (((size_t)cg * 16 + (row >> 3)) << 5) + ((row & 7) << 2));
+      const double2 a01 = src[0], a23 = src[1];
+      const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double2 z01 = *reinterpret_cast<const double2*>(&zk[4 * cg + u][v0]);
+        const double2 z23 = *reinterpret_cast<const double2*>(&zk[4 * cg + u][v0 + 2]);
+        acc[0] = fma(a[u], z01.x, acc[0]);
+        acc[1] = fma(a[u], z01.y, acc[1]);
+        acc[2] = fma(a[u], z23.x, acc[2]);
+        acc[3] = fma(a[u], z23.y, acc[3]);
+      }
+    }
+  };
+  for (int k = 0; k < nt; ++k) {
+    __syncthreads();
+    // r_k of the CTA's right-hand sides -> zk (as the operand of the diagonal product)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int v = v0 + j;
+      zk[row][v] = (r0 + v < R) ? Z[(size_t)(r0 + v) * ldz + (size_t)k * TILE + row] : 0.0;
+    }
+    __syncthreads();
+    double acc[4];
+    tile_times_zk(A + tile_index(k, k) * TILE_ELEMS, acc);   // inv(L_kk) is stored with zeros above the diagonal
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int v = v0 + j;
+      zk[row][v] = acc[j];
+      if (r0 + v < R) Z[(size_t)(r0 + v) * ldz + (size_t)k * TILE + row] = acc[j];
+    }
+    __syncthreads();
+    for (int i = k + 1; i < nt; ++i) {
+      tile_times_zk(A + tile_index(i, k) * TILE_ELEMS, acc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int v = v0 + j;
+        if (r0 + v < R) Z[(size_t)(r0 + v) * ldz + (size_t)i * TILE + row] -= acc[j];
+      }
+    }
+  }
+}
+
+// z_r = L^-1 rhs_r for R right-hand sides and ONE hyper-parameter set: K is factorised once (tiled path, one
+// walker), then every right-hand side is swept through the stored factor.  The building block of
+// GPLikelihood.predict (gp_likelihood.py:429-441; the reference factorises K twice there, mrv_solve_batch
+// with a broadcast hp did it R times).
+extern "C" int mrv_solve_multi(mrv_problem* p, const double* hp, const double* rhs, int64_t R, double* z_out,
+                               double* logdet_out, int32_t* status_out) {
+  if (!p || !hp || !rhs || !z_out || !status_out) return fail(-1, "null argument");
+  if (R <= 0) return 0;
+  CU(cudaSetDevice(p->device));
+  const ProblemDesc& D = p->desc;
+  const int N = D.N;
+  int rc = 0;
+  DevBuf zwork, ldbuf, mpbuf, r0buf;
+  auto done = [&](int code) {
+    zwork.release();
+    ldbuf.release();
+    mpbuf.release();
+    r0buf.release();
+    return code;
+  };
+  const size_t ldz = (size_t)p->n_pad;
+  if ((rc = p->hp.ensure((size_t)D.nh * sizeof(double)))) return rc;
+  if ((rc = p->logl.ensure(sizeof(double)))) return rc;
+  if ((rc = p->status.ensure(sizeof(int)))) return rc;
+  if ((rc = zwork.ensure((size_t)R * ldz * sizeof(double)))) return done(rc);
+  if ((rc = ldbuf.ensure(sizeof(double)))) return done(rc);
+  if ((rc = mpbuf.ensure(std::max<size_t>(1, (size_t)D.nm) * sizeof(double)))) return done(rc);
+  if ((rc = r0buf.ensure((size_t)N * sizeof(double)))) return done(rc);
+  cudaStream_t st = p->stream;
+  cudaError_t e = cudaMemcpyAsync(p->hp.p, hp, (size_t)D.nh * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(zwork.p, 0, zwork.bytes, st);
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(zwork.p, ldz * sizeof(double), rhs, (size_t)N * sizeof(double), (size_t)N * sizeof(double), (size_t)R,
+                          cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(r0buf.p, rhs, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(mpbuf.p, 0, mpbuf.bytes, st);
+  if (e != cudaSuccess) return done(fail(-2, "mrv_solve_multi copy-in: %s", cudaGetErrorString(e)));
+  // factorise once: tiled path, one walker, no priors; the factor stays in the workspace (slot 0)
+  const int n_priors_saved = p->desc.n_priors, path_saved = p->path_opt;
+  const int64_t ens_saved = p->ensemble_opt;
+  p->desc.n_priors = 0;
+  p->path_opt = MRV_PATH_BLOCKED;
+  p->ensemble_opt = 0;
+  SolveOut so{nullptr, 0, ldbuf.as<double>(), 1};
+  rc = run_logl(p, p->hp.as<double>(), mpbuf.as<double>(), r0buf.as<double>(), 1, 0, p->logl.as<double>(), p->status.as<int>(), st, so);
+  p->desc.n_priors = n_priors_saved;
+  p->path_opt = path_saved;
+  p->ensemble_opt = ens_saved;
+  if (rc) return done(rc);
+  multi_rhs_forward_kernel<<<(unsigned)((R + MRHS - 1) / MRHS), 256, 0, st>>>(p->nt, p->factor.as<double>(), zwork.as<double>(),
+                                                                              (long long)ldz, (int)R);
+  p->launches++;
+  e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpy2DAsync(z_out, (size_t)N * sizeof(double), zwork.p, ldz * sizeof(double), (size_t)N * sizeof(double), (size_t)R,
+                          cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && logdet_out) e = cudaMemcpyAsync(logdet_out, ldbuf.p, sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(status_out, p->status.p, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return done(fail(-2, "mrv_solve_multi: %s", cudaGetErrorString(e)));
   return done(0);
 }
 
@@ -1267,6 +1472,7 @@ extern "C" int mrv_gelman_rubin(int device, const double* chains, int64_t n_step
 // ------------------------------------------------------------------------------------------------
 extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
   if (!p || !key) return fail(-1, "null argument");
+  p->opt_gen++;   // a captured graph of the host-buffer call froze the old choices
   if (!strcmp(key, "path")) {
     if (value < 0 || value > 3) return fail(-1, "path must be 0 (auto), 1 (fused smem), 2 (blocked) or 3 (streamed panel)");
     p->path_opt = (int)value;
@@ -1296,6 +1502,8 @@ extern "C" int mrv_set_option(mrv_problem* p, const char* key, int64_t value) {
     p->lookahead_opt = (int)value;
   } else if (!strcmp(key, "substreams")) {
     p->substreams_opt = (int)value;
+  } else if (!strcmp(key, "cuda_graph")) {
+    p->graph_opt = value != 0;   // 1 (default): replay the host-buffer call of the one-CTA-per-walker paths as a CUDA graph
   } else if (!strcmp(key, "tiled_impl")) {
     if (value < 0 || value > 2) return fail(-1, "tiled_impl must be 0 (automatic), 1 (launch per tile column) or 2 (persistent dataflow kernel)");
     p->tiled_impl = (int)value;
@@ -1316,6 +1524,7 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!p || !key) return -1;
   if (!strcmp(key, "path")) return p->last_path ? p->last_path : choose_path(p);
   if (!strcmp(key, "launches")) return p->launches;
+  if (!strcmp(key, "graph_replays")) return p->graph_replays;
   if (!strcmp(key, "wave_walkers")) return p->wave_cur;
   if (!strcmp(key, "tiled_impl")) return use_dag(p) ? 2 : 1;
   if (!strcmp(key, "n_pad")) return p->n_pad;

@@ -198,6 +198,21 @@ class LikelihoodProblem:
         nat.check(rc, "mrv_solve_batch")
         return z, logdet, status
 
+    def solve_multi(self, hp, rhs):
+        """(z [R, N] = L^-1 rhs_r, logdet, status) for ONE hyper-parameter set: one factorisation, R forward
+        substitutions through the stored factor -- see mrv_solve_multi."""
+        hp = nat.as_f64(hp).ravel()
+        assert hp.shape == (self.nh,)
+        rhs = nat.as_f64(rhs).reshape(-1, self.N)
+        R = rhs.shape[0]
+        z = np.empty((R, self.N), dtype=np.float64)
+        logdet = np.empty(1, dtype=np.float64)
+        status = np.empty(1, dtype=np.int32)
+        rc = nat.lib().mrv_solve_multi(self._handle, nat.dptr(hp), nat.dptr(rhs), R, nat.dptr(z), nat.dptr(logdet),
+                                       status.ctypes.data_as(nat.c_int32_p))
+        nat.check(rc, "mrv_solve_multi")
+        return z, float(logdet[0]), status
+
     def set_option(self, key, value):
         nat.check(nat.lib().mrv_set_option(self._handle, key.encode(), int(value)), "mrv_set_option(%s)" % key)
 

@@ -105,10 +105,13 @@ class GatherBuffers:
     def gather_to_host(self, dist, check=True):
         """All-gather, ONE device-to-host copy, unpack on the host: (log L [W] float64, status [W] int32)."""
         import torch
+        if self.device.type == "cuda":
+            torch.cuda.nvtx.range_push("gather")          # NVTX: the one collective of an iteration
         dist.all_gather_into_tensor(self.recv, self.send)
         if self.device.type == "cuda":
             self.host.copy_(self.recv, non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
+            torch.cuda.nvtx.range_pop()
             h = self._host_np
         else:
             h = self.recv.numpy()

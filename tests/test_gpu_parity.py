@@ -526,6 +526,63 @@ def test_solve_batch_blocked_and_fused_agree():
             prob.close()
 
 
+@pytest.mark.parametrize("N,R", [(60, 1), (128, 9), (300, 11), (1000, 19), (1300, 8)])
+def test_solve_multi_factors_once_and_matches_scipy(N, R):
+    """mrv_solve_multi: ONE factorisation of K, then R right-hand sides swept through the stored factor
+    (GPLikelihood.predict; ADVICE r1: the batched form factorised K once per right-hand side).  Against SciPy's
+    triangular solve of the oracle's covariance and against mrv_solve_batch with the hyper-parameters broadcast."""
+    from scipy.linalg import cholesky, solve_triangular
+    rng = np.random.default_rng(N + R)
+    t = np.sort(rng.uniform(0, 1.1 * N, N))
+    y = rng.normal(0, 1, N)
+    e = rng.uniform(0.5, 1.0, N)
+    hp = np.array([21.0, 0.6, 35.0, 6.0, 1.2])
+    rhs = rng.normal(0, 1, (R, N))
+    prob = engine.LikelihoodProblem(t, y, e, "JitterQuasiPer")
+    launches0 = prob.info("launches")
+    z, logdet, st = prob.solve_multi(hp, rhs)
+    n_launch = prob.info("launches") - launches0
+    assert st[0] == 0
+    K = port.compute_kernel("JitterQuasiPer", hp, t, t, t, e)
+    L = cholesky(K, lower=True)
+    want = solve_triangular(L, rhs.T, lower=True).T
+    np.testing.assert_allclose(z, want, rtol=1e-9, atol=1e-10)
+    assert abs(logdet - 2 * np.sum(np.log(np.diag(L)))) <= 1e-11 * abs(logdet)
+    zb, ldb, stb = prob.solve(hp, rhs)
+    np.testing.assert_allclose(z, zb, rtol=1e-10, atol=1e-11)
+    # one factorisation: the launch count does not grow with the number of right-hand sides
+    launches0 = prob.info("launches")
+    prob.solve_multi(hp, rhs[:1])
+    assert prob.info("launches") - launches0 == n_launch
+    prob.close()
+
+
+@pytest.mark.parametrize("name,W", [("C1", 100), ("C2", 37), ("C3", 48)])
+def test_cuda_graph_replay_of_the_host_buffer_call(name, W):
+    """mrv_logl_batch on the one-CTA-per-walker paths replays copy in -> kernel(s) -> copy out as one CUDA graph from the
+    third identical call on; values are bitwise those of the eager call, new parameters flow through the pinned staging
+    buffer, and a different ensemble size or an option change drops the graph."""
+    cfg = workloads.make_config(name, W=W)
+    prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["model_list"], cfg["prior_list"],
+                                    flags=cfg["flags"])
+    prob.set_option("cuda_graph", 0)
+    eager, st = prob.logl(cfg["hp"], cfg["modpar"])
+    hp2 = cfg["hp"] * (1.0 + 1e-3)
+    eager2, _ = prob.logl(hp2, cfg["modpar"])
+    assert np.all(st == 0) and prob.info("path") in (1, 3) and prob.info("graph_replays") == 0
+    prob.set_option("cuda_graph", 1)
+    for i in range(5):
+        got, st = prob.logl(cfg["hp"] if i % 2 == 0 else hp2, cfg["modpar"])
+        np.testing.assert_array_equal(got, eager if i % 2 == 0 else eager2)
+        assert np.all(st == 0)
+    assert prob.info("graph_replays") >= 2
+    n = prob.info("graph_replays")
+    part, _ = prob.logl(cfg["hp"][:W // 2], cfg["modpar"][:W // 2])          # another size: eager again, then a new graph
+    np.testing.assert_array_equal(part, eager[:W // 2])
+    assert prob.info("graph_replays") == n
+    prob.close()
+
+
 def test_chain_parity_with_options_gpu():
     """flags + Offset + Keplerian, Mstar, n_splits=3, a=2.5 through the CUDA path vs the reference chain."""
     from test_host_logic import run_options_chain
