@@ -573,10 +573,14 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
 // Tiled path as ONE persistent dataflow kernel per wave (dag.cuh).  Left-looking by tiles: every tile streams its
 // operands once per tile (16 flop per operand byte, 2.3 TB/s at the DMMA peak -- affordable up to N = 4096, where a
 // walker's factor is 67 MB); above that the right-looking panels of run_wave re-use operands better.
-static bool use_dag(const mrv_problem* p) {
+static bool use_dag(const mrv_problem* p, int64_t wave = 0) {
   if (p->tiled_impl == 1) return false;
   if (p->tiled_impl == 2) return p->nt <= 128;
-  return p->nt >= DAG_AUTO_MIN_TILES && p->nt <= DAG_AUTO_MAX_TILES;
+  if (p->nt < DAG_AUTO_MIN_TILES) return false;
+  if (p->nt <= DAG_AUTO_MAX_TILES) return true;
+  // up to 64 tile columns (N = 8192) the dataflow kernel is still ahead when the wave fills the GPU (128 walkers: 1.02x,
+  // 91.3 % of the DMMA peak; 32 walkers: 0.98x); per-walker results are bitwise the same either way
+  return p->nt <= 2 * DAG_AUTO_MAX_TILES && wave >= 64;
 }
 
 static int run_wave_dag(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so, int wave_index) {
@@ -741,7 +745,7 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
   const int64_t n_waves = (W + B - 1) / B;
   if ((rc = p->counter.ensure((size_t)(n_waves + 2) * sizeof(int)))) return rc;
   if ((rc = p->factor.ensure((size_t)B * walker_bytes))) return rc;
-  const bool dag = use_dag(p);
+  const bool dag = use_dag(p, B);
   if (dag) {
     if ((rc = p->zcols.ensure((size_t)B * nt * TILE * sizeof(double)))) return rc;
     if ((rc = p->rowdone.ensure((size_t)W * nt * sizeof(int)))) return rc;
@@ -1526,7 +1530,7 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
   if (!strcmp(key, "launches")) return p->launches;
   if (!strcmp(key, "graph_replays")) return p->graph_replays;
   if (!strcmp(key, "wave_walkers")) return p->wave_cur;
-  if (!strcmp(key, "tiled_impl")) return use_dag(p) ? 2 : 1;
+  if (!strcmp(key, "tiled_impl")) return use_dag(p, p->wave_cur) ? 2 : 1;
   if (!strcmp(key, "n_pad")) return p->n_pad;
   if (!strcmp(key, "panel_tiles")) return effective_panel(p);
   if (!strcmp(key, "small_n_max")) return SMALL_N_MAX;
