@@ -402,6 +402,20 @@ __host__ __device__ inline size_t sweep_packed_doubles(int ld, int n_cols) {
 
 // Phase timers of the dataflow kernel (only with -DDAG_TIMING; thread 0 of a CTA accumulates clock64 deltas in
 // registers, tools/dag_timing.py reads the per-phase totals).  Without the flag every call is empty.
+// Reciprocal of a pivot: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps in FMA, 5 dependent FP64 instructions
+// instead of the ~25 of an IEEE division with its special-case paths (every thread of the pivot block divides after every
+// barrier: in the fused small-N kernel that one line was 15 % of all stall samples, a quarter of them FP64-pipe
+// contention).  Within 1 ulp of 1 / x for normal x; the sign and NaN pass through; x = 0 gives NaN where the division
+// gave inf (either way the pivot itself, not its reciprocal, decides the status word).
+__device__ __forceinline__ double pivot_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  return fma(y, e, y);
+}
+
 struct PhaseTimer {
 #ifdef DAG_TIMING
   long long* a;   // shared memory: 16 accumulators + the last time stamp (only thread 0 touches them)
@@ -453,7 +467,7 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
       // once and publish it measured 7 % SLOWER -- the division then sits between the update and the barrier)
       for (int j = 0; j < PB_NB - 1; ++j) {
         if (in_blk && c > j && (r >= c || r <= j)) {
-          const double w = 1.0 / D[j * PB_D_LD + j];
+          const double w = pivot_rcp(D[j * PB_D_LD + j]);
           const double beta = D[c * PB_D_LD + j] * w;
           if (r == j) v = -beta;
           else v = fma(-D[r * PB_D_LD + j], beta, v);
@@ -462,7 +476,7 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
         __syncthreads();
       }
       if (in_blk) {
-        if (r == c) wv[r] = 1.0 / v;
+        if (r == c) wv[r] = pivot_rcp(v);
         sweep_colp<PACKED>(S, ld, k0 + c)[k0 + r] = v;     // final block (lower: factor, upper: inverse part)
       }
       __syncthreads();
