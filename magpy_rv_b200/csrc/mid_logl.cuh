@@ -106,9 +106,15 @@ __device__ __forceinline__ void mid_factor16(const MidShared& sh, const double* 
   double* const rhsb = sh.rhsb;
   const double* const rj = sh.rj;
 
-      // Lean rolled loops: explicit pointers with constant offsets (no per-element index
-      // arithmetic), over-reads past column 15 land in the padding columns 16..31 of Dm / in the
-      // arrays behind invL and are never stored.  Dm[c * 17 + row], c < 32.
+      // Square-root-free right-looking LDL^T in shared memory, then the inverse of the UNIT lower factor, both as lean
+      // rolled loops with ONE __syncwarp per step (explicit pointers with constant offsets; over-reads past column 15
+      // land in the padding columns 16..31 of Dm / in the arrays behind invL and are never stored):
+      //   step k:  w = 1 / d_k,  A[r][c] -= (A[r][k] w) A[c][k]   (c > k, r >= c; column k itself stays unscaled)
+      // The Cholesky form it replaces (round 1) needed the scaled column k back in shared memory before the update --
+      // rsqrt, store, __syncwarp, load -- and its inversion loop multiplied by 1 / L_kk in every step: 32 steps of
+      // ~480 clocks in the kernel (8 us per 16 x 16 block; the tensor warps waited for it at the barriers, ncu: 52 % of
+      // their stall samples).  L = Ltilde D^1/2 and inv(L) = D^-1/2 inv(Ltilde) are formed by two parallel scalings.
+      // Dm[c * 17 + row], c < 32.
       const int rr = lane & 15, g = lane >> 4;
       {
         const double* src = P + (size_t)((o + 8 * g) >> 2) * CS + 4 * (o + rr);
@@ -117,7 +123,7 @@ __device__ __forceinline__ void mid_factor16(const MidShared& sh, const double* 
         for (int u = 0; u < 8; ++u) dst[u * 17] = src[(size_t)(u >> 2) * CS + (u & 3)];
       }
       __syncwarp();
-      double* colk = Dm;
+      const double* colk = Dm;
 #pragma unroll 1
       for (int k = 0; k < 16; ++k, colk += 17) {
         const double dk = colk[k];
@@ -125,17 +131,9 @@ __device__ __forceinline__ void mid_factor16(const MidShared& sh, const double* 
           fb = row0 + o + k + 1;
           fb_nan = isnan(dk) ? 1 : 0;
         }
-        const double rs = rsqrt(dk);
-        const double lik = colk[rr] * rs;
-        if (lane == k) {
-          rdiag[k] = rs;
-          dvec[row0 + o + k] = dk;
-        }
-        __syncwarp();
-        if (lane >= k && lane < 16) colk[rr] = lik;
-        __syncwarp();
+        const double li = colk[rr] * pivot_rcp(dk);    // Ltilde[rr][k]
         const int cb = k + 1 + 8 * g;                  // first column of this half-warp's batch
-        const double* pl = colk + cb;                  // L[c][k]
+        const double* pl = colk + cb;                  // A[c][k] (unscaled)
         double* pa = Dm + cb * 17 + rr;                // A[rr][c]
         const int nst = min(16 - cb, rr - cb + 1);     // store u < nst  <=>  c < 16 && rr >= c
         double lv[8], av[8];
@@ -145,26 +143,37 @@ __device__ __forceinline__ void mid_factor16(const MidShared& sh, const double* 
           av[u] = pa[u * 17];
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) av[u] = fma(-lik, lv[u], av[u]);
+        for (int u = 0; u < 8; ++u) av[u] = fma(-li, lv[u], av[u]);
 #pragma unroll
         for (int u = 0; u < 8; ++u)
           if (u < nst) pa[u * 17] = av[u];
         __syncwarp();
       }
-      
-      // inverse of the 16 x 16 factor: column rr per lane, rows split between the half-warps
+      // pivots -> 1 / d, 1 / sqrt(d); unit factor Ltilde[i][c] = A[i][c] / d_c in place (this lane: row rr, columns 8 g ..)
+      if (lane < 16) {
+        const double d = Dm[lane * 17 + lane];
+        dvec[row0 + o + lane] = d;
+        rdiag[lane] = rsqrt(d);
+        rhsb[lane] = pivot_rcp(d);                     // (rhsb is free until the z block below)
+      }
+      __syncwarp();
+      {
+        double* pe = Dm + (8 * g) * 17 + rr;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (rr > 8 * g + u) pe[u * 17] *= rhsb[8 * g + u];
+      }
+      // inverse of the unit lower factor: column rr per lane (solve Ltilde x = e_rr), rows split between the half-warps
       double* X = invL + o * MID_INV_LD + o;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) X[(8 * g + u) * MID_INV_LD + rr] = 0.0;
+      for (int u = 0; u < 8; ++u) X[(8 * g + u) * MID_INV_LD + rr] = (8 * g + u == rr) ? 1.0 : 0.0;
       __syncwarp();
       const double* colq = Dm;
 #pragma unroll 1
-      for (int q = 0; q < 16; ++q, colq += 17) {
-        const double xq = (q >= rr) ? ((q == rr ? 1.0 : 0.0) + X[q * MID_INV_LD + rr]) * rdiag[q] : 0.0;
-        __syncwarp();
-        if (g == 0) X[q * MID_INV_LD + rr] = xq;
+      for (int q = 0; q < 15; ++q, colq += 17) {
+        const double xq = X[q * MID_INV_LD + rr];      // final: rows <= q are done
         const int ib = q + 1 + 8 * g;
-        const double* pl = colq + ib;                  // L[i][q]
+        const double* pl = colq + ib;                  // Ltilde[i][q]
         double* px = X + ib * MID_INV_LD + rr;         // X[i][rr]
         const int nst = 16 - ib;
         double lv[8], xv[8];
@@ -180,7 +189,11 @@ __device__ __forceinline__ void mid_factor16(const MidShared& sh, const double* 
           if (u < nst) px[u * MID_INV_LD] = xv[u];
         __syncwarp();
       }
-      
+      // inv(L) = D^-1/2 inv(Ltilde): scale row i by 1 / sqrt(d_i)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) X[(8 * g + u) * MID_INV_LD + rr] *= rdiag[8 * g + u];
+      __syncwarp();
+
       // z block: rhs = r_block (second half: minus L_BA z_A), z = inv(L) rhs
       if (g == 0) {
         double rhs = rj[o + rr];
