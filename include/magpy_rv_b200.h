@@ -92,6 +92,21 @@ int mrv_logl_batch(mrv_problem* p, const double* hp, const double* modpar, int64
 int mrv_logl_batch_device(mrv_problem* p, const double* d_hp, const double* d_modpar, int64_t W,
                           int to_ecc, double* d_logL_out, int32_t* d_status_out, void* stream);
 
+/* Walker sharding inside the library (one host thread, one handle per device; SURVEY.md 8(b) `mrv_shard_init`).
+ * mrv_shard_create replicates the problem on `n_dev` devices; mrv_shard_logl_batch cuts the ensemble into contiguous
+ * blocks, enqueues every block on its device and collects log L / status in walker order -- the sharded form of
+ * MCMC.compute (mcmc.py:410-461) for callers without a process group (the torch.distributed / NCCL form is
+ * magpy_rv_b200/sharding.py).  Results are bitwise those of a single device. */
+typedef struct mrv_shard mrv_shard;
+int mrv_shard_create(mrv_shard** out, int n_dev, const int* devices, const double* t, const double* y,
+                     const double* yerr, const double* flags, int64_t N, int kernel_id, int kernel_variant, int nh,
+                     const mrv_model_op* ops, int n_ops, int nm, const mrv_prior* priors, int n_priors);
+void mrv_shard_destroy(mrv_shard* sh);
+int mrv_shard_count(mrv_shard* sh);
+mrv_problem* mrv_shard_part(mrv_shard* sh, int i);   /* borrowed: options / info of one device's handle */
+int mrv_shard_logl_batch(mrv_shard* sh, const double* hp, const double* modpar, int64_t W, int to_ecc,
+                         double* logL_out, int32_t* status_out);
+
 /* Same, but the caller supplies the mean-model curve(s) model_y [W, N] instead of the op list
  * (GPLikelihood accepts an arbitrary model_y, gp_likelihood.py:64,140-141); priors read modpar
  * as given (no conversion). */

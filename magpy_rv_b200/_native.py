@@ -39,6 +39,15 @@ SIGNATURES = {
                                       c_double_p, c_int32_p]),
     "mrv_logl_batch_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
                                              ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "mrv_shard_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.POINTER(ctypes.c_int), c_double_p,
+                                        c_double_p, c_double_p, c_double_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                        ctypes.c_int, ctypes.POINTER(mrv_model_op), ctypes.c_int, ctypes.c_int,
+                                        ctypes.POINTER(mrv_prior), ctypes.c_int]),
+    "mrv_shard_destroy": (None, [ctypes.c_void_p]),
+    "mrv_shard_count": (ctypes.c_int, [ctypes.c_void_p]),
+    "mrv_shard_part": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
+    "mrv_shard_logl_batch": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int64, ctypes.c_int,
+                                            c_double_p, c_int32_p]),
     "mrv_logl_given_model": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, c_double_p, ctypes.c_int64,
                                             c_double_p, c_int32_p]),
     "mrv_solve_batch": (ctypes.c_int, [ctypes.c_void_p, c_double_p, c_double_p, ctypes.c_int64, c_double_p, c_double_p,

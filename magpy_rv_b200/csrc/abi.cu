@@ -200,7 +200,7 @@ struct mrv_problem {
   // launch (three stream operations per batch otherwise; the batch of a tutorial-size MCMC iteration is ~60 us of GPU work)
   int graph_opt = 1;
   cudaGraphExec_t graph_exec = nullptr;
-  int64_t graph_W = -1;
+  int64_t graph_W = -1, graph_ens = -1;
   int graph_to_ecc = -1, graph_state = 0;   // state: 0 = nothing seen, 1 = this key ran eagerly once (buffers exist), 2 = captured
   unsigned long long graph_buf_gen = 0, opt_gen = 0, graph_opt_gen = 0;
   int64_t graph_launches = 0, graph_replays = 0;
@@ -835,9 +835,20 @@ extern "C" int mrv_logl_batch_device(mrv_problem* p, const double* d_hp, const d
   return run_logl(p, d_hp, d_modpar, nullptr, W, to_ecc, d_logL_out, d_status_out, (cudaStream_t)stream);
 }
 
-static int host_logl(mrv_problem* p, const double* hp, const double* modpar, const double* model_y, int64_t W, int to_ecc,
-                     double* logL_out, int32_t* status_out) {
-  if (!p || !hp || !modpar || !logL_out || !status_out) return fail(-1, "null argument");
+// Host-buffer evaluation in two halves, so that one host thread can keep several devices busy (mrv_shard_logl_batch):
+// `enqueue` stages the parameters and enqueues copy in -> kernels -> copy out on the handle's stream (or replays the
+// captured graph), `finish` waits for the stream and hands the results over.
+static int host_logl_finish(mrv_problem* p, int64_t W, double* logL_out, int32_t* status_out) {
+  if (W <= 0) return 0;
+  CU(cudaSetDevice(p->device));
+  CU(cudaStreamSynchronize(p->stream));
+  memcpy(logL_out, p->pin_out.p, (size_t)W * sizeof(double));
+  memcpy(status_out, static_cast<char*>(p->pin_out.p) + (size_t)W * sizeof(double), (size_t)W * sizeof(int));
+  return 0;
+}
+
+static int host_logl_enqueue(mrv_problem* p, const double* hp, const double* modpar, const double* model_y, int64_t W, int to_ecc) {
+  if (!p || !hp || !modpar) return fail(-1, "null argument");
   if (W <= 0) return 0;
   struct Range {
     Range() { nvtxRangePushA("mrv_logl_batch"); }
@@ -866,15 +877,12 @@ static int host_logl(mrv_problem* p, const double* hp, const double* modpar, con
   const int path_now = choose_path(p, Wsel);
   const bool graphable = p->graph_opt && !model_y && !p->prof.on && (path_now == MRV_PATH_FUSED_SMEM || path_now == MRV_PATH_MID);
   const bool same_key = graphable && p->graph_W == W && p->graph_to_ecc == to_ecc && p->graph_buf_gen == g_buf_gen &&
-                        p->graph_opt_gen == p->opt_gen;
+                        p->graph_opt_gen == p->opt_gen && p->graph_ens == p->ensemble_opt;
   if (same_key && p->graph_state == 2) {
     CU(cudaGraphLaunch(p->graph_exec, st));
-    CU(cudaStreamSynchronize(st));
     p->launches += p->graph_launches;
     p->graph_replays++;
     p->last_path = path_now;
-    memcpy(logL_out, p->pin_out.p, (size_t)W * sizeof(double));
-    memcpy(status_out, static_cast<char*>(p->pin_out.p) + (size_t)W * sizeof(double), (size_t)W * sizeof(int));
     return 0;
   }
   const bool capture = same_key && p->graph_state == 1;
@@ -908,7 +916,7 @@ static int host_logl(mrv_problem* p, const double* hp, const double* modpar, con
     if (rc) return rc;
     if (p->graph_state != 2) {
       p->graph_opt = 0;                                    // capture is not possible here: stay eager for this handle
-      return host_logl(p, hp, modpar, model_y, W, to_ecc, logL_out, status_out);
+      return host_logl_enqueue(p, hp, modpar, model_y, W, to_ecc);
     }
     CU(cudaGraphLaunch(p->graph_exec, st));
     p->launches += p->graph_launches;
@@ -917,6 +925,7 @@ static int host_logl(mrv_problem* p, const double* hp, const double* modpar, con
     if (ce != cudaSuccess) return fail(-2, "mrv_logl_batch copy / launch failed: %s", cudaGetErrorString(ce));
     if (graphable) {                                       // remember the key: the next identical call is captured
       p->graph_W = W;
+      p->graph_ens = p->ensemble_opt;
       p->graph_to_ecc = to_ecc;
       p->graph_buf_gen = g_buf_gen;
       p->graph_opt_gen = p->opt_gen;
@@ -925,10 +934,14 @@ static int host_logl(mrv_problem* p, const double* hp, const double* modpar, con
       p->graph_state = 0;
     }
   }
-  CU(cudaStreamSynchronize(st));
-  memcpy(logL_out, p->pin_out.p, (size_t)W * sizeof(double));
-  memcpy(status_out, static_cast<char*>(p->pin_out.p) + (size_t)W * sizeof(double), (size_t)W * sizeof(int));
   return 0;
+}
+
+static int host_logl(mrv_problem* p, const double* hp, const double* modpar, const double* model_y, int64_t W, int to_ecc,
+                     double* logL_out, int32_t* status_out) {
+  if (!logL_out || !status_out) return fail(-1, "null argument");
+  if (int rc = host_logl_enqueue(p, hp, modpar, model_y, W, to_ecc)) return rc;
+  return host_logl_finish(p, W, logL_out, status_out);
 }
 
 extern "C" int mrv_logl_batch(mrv_problem* p, const double* hp, const double* modpar, int64_t W, int to_ecc,
@@ -940,6 +953,76 @@ extern "C" int mrv_logl_given_model(mrv_problem* p, const double* hp, const doub
                                     int64_t W, double* logL_out, int32_t* status_out) {
   if (!model_y) return fail(-1, "null model_y");
   return host_logl(p, hp, modpar, model_y, W, 0, logL_out, status_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Walker sharding inside the library (SURVEY.md 8(b) mrv_shard_init): one host thread, one problem handle per
+// device.  The ensemble is cut into contiguous blocks (sizes differ by at most one, as sharding.partition), every
+// device gets its block enqueued asynchronously, then the results are collected -- the "all-gather" of this layout is
+// the host buffer the caller already owns, so no NCCL and no torch are needed (a maintainer who patches the reference
+// as in INTEGRATION.md B shards by passing more than one device).  Per-walker results are bitwise those of one device:
+// every handle selects its kernels by the size of the WHOLE ensemble.
+// ------------------------------------------------------------------------------------------------
+struct mrv_shard {
+  std::vector<mrv_problem*> parts;
+};
+
+extern "C" int mrv_shard_create(mrv_shard** out, int n_dev, const int* devices, const double* t, const double* y,
+                                const double* yerr, const double* flags, int64_t N, int kernel_id, int kernel_variant, int nh,
+                                const mrv_model_op* ops, int n_ops, int nm, const mrv_prior* priors, int n_priors) {
+  if (!out || !devices || n_dev <= 0) return fail(-1, "mrv_shard_create: need at least one device");
+  *out = nullptr;
+  mrv_shard* sh = new (std::nothrow) mrv_shard();
+  if (!sh) return fail(-3, "out of host memory");
+  for (int i = 0; i < n_dev; ++i) {
+    mrv_problem* p = nullptr;
+    const int rc = mrv_problem_create(&p, devices[i], t, y, yerr, flags, N, kernel_id, kernel_variant, nh, ops, n_ops, nm, priors, n_priors);
+    if (rc) {
+      for (mrv_problem* q : sh->parts) mrv_problem_destroy(q);
+      delete sh;
+      return rc;
+    }
+    sh->parts.push_back(p);
+  }
+  *out = sh;
+  return 0;
+}
+
+extern "C" void mrv_shard_destroy(mrv_shard* sh) {
+  if (!sh) return;
+  for (mrv_problem* p : sh->parts) mrv_problem_destroy(p);
+  delete sh;
+}
+
+extern "C" int mrv_shard_count(mrv_shard* sh) { return sh ? (int)sh->parts.size() : 0; }
+
+extern "C" mrv_problem* mrv_shard_part(mrv_shard* sh, int i) {
+  return (sh && i >= 0 && i < (int)sh->parts.size()) ? sh->parts[(size_t)i] : nullptr;
+}
+
+extern "C" int mrv_shard_logl_batch(mrv_shard* sh, const double* hp, const double* modpar, int64_t W, int to_ecc,
+                                    double* logL_out, int32_t* status_out) {
+  if (!sh || !hp || !modpar || !logL_out || !status_out) return fail(-1, "null argument");
+  if (W <= 0) return 0;
+  const int64_t G = (int64_t)sh->parts.size();
+  const int nh = sh->parts[0]->desc.nh, nm = sh->parts[0]->desc.nm;
+  const int64_t base = W / G, rem = W % G;
+  int rc = 0;
+  int64_t start = 0;
+  for (int64_t r = 0; r < G; ++r) {          // enqueue everywhere first ...
+    const int64_t n = base + (r < rem ? 1 : 0);
+    mrv_problem* p = sh->parts[(size_t)r];
+    p->ensemble_opt = W;
+    if (n > 0 && (rc = host_logl_enqueue(p, hp + start * nh, modpar + start * nm, nullptr, n, to_ecc))) return rc;
+    start += n;
+  }
+  start = 0;
+  for (int64_t r = 0; r < G; ++r) {          // ... then collect in walker order
+    const int64_t n = base + (r < rem ? 1 : 0);
+    if (n > 0 && (rc = host_logl_finish(sh->parts[(size_t)r], n, logL_out + start, status_out + start))) return rc;
+    start += n;
+  }
+  return 0;
 }
 
 // z_b = L_b^-1 rhs_b and ln det K_b for W (hyper-parameter, right-hand side) pairs: the forward half

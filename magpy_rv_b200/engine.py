@@ -108,16 +108,22 @@ class LikelihoodProblem:
         self.priors = self._flatten_priors(prior_list)
         self.device = nat.default_device() if device is None else int(device)
         self._handle = ctypes.c_void_p()
+        self._create()
+
+    def _pod_arrays(self):
         ops_arr = _ops_array(self.ops)
         pri_arr = (nat.mrv_prior * max(1, len(self.priors)))()
         for i, (tp, src, idx, p0, p1, p2) in enumerate(self.priors):
             pri_arr[i].type, pri_arr[i].source, pri_arr[i].index = tp, src, idx
             pri_arr[i].p0, pri_arr[i].p1, pri_arr[i].p2 = p0, p1, p2
-        lib = nat.lib()
-        rc = lib.mrv_problem_create(ctypes.byref(self._handle), self.device, nat.dptr(self.t), nat.dptr(self.y),
-                                    nat.dptr(self.yerr), nat.dptr(self.flags), self.N, self.kernel_id,
-                                    self.kernel_variant, self.nh, ops_arr, len(self.ops), self.nm, pri_arr,
-                                    len(self.priors))
+        return ops_arr, pri_arr
+
+    def _create(self):
+        ops_arr, pri_arr = self._pod_arrays()
+        rc = nat.lib().mrv_problem_create(ctypes.byref(self._handle), self.device, nat.dptr(self.t), nat.dptr(self.y),
+                                          nat.dptr(self.yerr), nat.dptr(self.flags), self.N, self.kernel_id,
+                                          self.kernel_variant, self.nh, ops_arr, len(self.ops), self.nm, pri_arr,
+                                          len(self.priors))
         nat.check(rc, "mrv_problem_create")
 
     # -- flattening -----------------------------------------------------------------------------
@@ -229,6 +235,52 @@ class LikelihoodProblem:
             self.close()
         except Exception:
             pass
+
+
+class LibraryShardedProblem(LikelihoodProblem):
+    """The same problem replicated on several GPUs of the box by the library itself (``mrv_shard_*``): ONE host
+    process and thread, no process group, no torch.  ``logl`` cuts the ensemble into contiguous walker blocks,
+    keeps every device busy and returns the full vectors; per-walker values are bitwise those of one GPU.
+    (The one-process-per-GPU form with NCCL is ``sharding.ShardedEvaluator``.)"""
+
+    def __init__(self, *args, devices=(0,), **kw):
+        self.devices = [int(d) for d in devices]
+        assert len(self.devices) >= 1
+        kw["device"] = self.devices[0]
+        self._shard = ctypes.c_void_p()
+        super().__init__(*args, **kw)
+
+    def _create(self):
+        ops_arr, pri_arr = self._pod_arrays()
+        devs = (ctypes.c_int * len(self.devices))(*self.devices)
+        rc = nat.lib().mrv_shard_create(ctypes.byref(self._shard), len(self.devices), devs, nat.dptr(self.t), nat.dptr(self.y),
+                                        nat.dptr(self.yerr), nat.dptr(self.flags), self.N, self.kernel_id, self.kernel_variant,
+                                        self.nh, ops_arr, len(self.ops), self.nm, pri_arr, len(self.priors))
+        nat.check(rc, "mrv_shard_create")
+        self._handle = ctypes.c_void_p(nat.lib().mrv_shard_part(self._shard, 0))     # borrowed: info / single-device calls
+
+    def logl(self, hp, modpar, to_ecc=True, raise_on_status=False):
+        hp, modpar = self._check_shapes(hp, modpar)
+        W = hp.shape[0]
+        out = np.empty(W, dtype=np.float64)
+        status = np.empty(W, dtype=np.int32)
+        rc = nat.lib().mrv_shard_logl_batch(self._shard, nat.dptr(hp), nat.dptr(modpar), W, int(bool(to_ecc)), nat.dptr(out),
+                                            status.ctypes.data_as(nat.c_int32_p))
+        nat.check(rc, "mrv_shard_logl_batch")
+        if raise_on_status:
+            raise_for_status(status)
+        return out, status
+
+    def set_option(self, key, value):
+        for i in range(len(self.devices)):
+            part = ctypes.c_void_p(nat.lib().mrv_shard_part(self._shard, i))
+            nat.check(nat.lib().mrv_set_option(part, key.encode(), int(value)), "mrv_set_option(%s)" % key)
+
+    def close(self):
+        if getattr(self, "_shard", None) is not None and self._shard.value:
+            nat.lib().mrv_shard_destroy(self._shard)
+            self._shard = ctypes.c_void_p()
+            self._handle = ctypes.c_void_p()
 
 
 def raise_for_status(status):

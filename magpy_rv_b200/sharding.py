@@ -22,6 +22,7 @@ chains; here that raises ``RuntimeError`` on the first step it happens.
 Without an initialised process group this degrades to the single-GPU call.  torch is used only
 for the process group, device buffers and streams -- plumbing, not the product.
 """
+import os
 import zlib
 
 import numpy as np
@@ -170,9 +171,16 @@ class ShardedEvaluator:
         self._gb = None
         self._stage = None
         if local_eval is None:
-            self.problem = engine.LikelihoodProblem(t, rv, rv_err, kernel_name, model_name, prior_list,
-                                                    hparam_names=hparam_names, model_param_names=modpar_names,
-                                                    flags=flags, device=device, kernel_variant=kernel_variant)
+            devices = [int(d) for d in os.environ.get("MRV_DEVICES", "").split(",") if d.strip() != ""]
+            if len(devices) > 1 and _dist() is None:
+                # one process, several GPUs: the library shards the ensemble itself (mrv_shard_*; no process group)
+                self.problem = engine.LibraryShardedProblem(t, rv, rv_err, kernel_name, model_name, prior_list,
+                                                            hparam_names=hparam_names, model_param_names=modpar_names,
+                                                            flags=flags, kernel_variant=kernel_variant, devices=devices)
+            else:
+                self.problem = engine.LikelihoodProblem(t, rv, rv_err, kernel_name, model_name, prior_list,
+                                                        hparam_names=hparam_names, model_param_names=modpar_names,
+                                                        flags=flags, device=device, kernel_variant=kernel_variant)
 
     def _local(self, hp, modpar):
         if self._local_eval is not None:
