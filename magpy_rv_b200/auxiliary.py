@@ -69,7 +69,7 @@ def mass_calc(model_param, Mstar, earth_mass=False):
     ``[P, K, ecc, omega]`` (reference auxiliary.py:223-252).  Vectorised over walkers when the
     entries are arrays; the sampler passes the list in the reference's (quirky) order, see
     mcmc.py / SURVEY.md F9."""
-    P, K, ecc = model_param[0], model_param[1], model_param[2]
+    P, K, ecc, omega = model_param      # four entries, as the reference unpacks them (a shorter list raises ValueError)
     Mpl_sini = 4.9191 * 10**(-3) * K * np.sqrt(1 - ecc**2) * P**(1 / 3) * Mstar**(2 / 3)
     if earth_mass == False:  # noqa: E712  (reference semantics)
         return Mpl_sini

@@ -255,13 +255,18 @@ class MCMC:
         out = np.zeros(shape=(1, W, self._n_planets))
         if self._n_planets == 0:
             return out
-        if isinstance(self.Mstar, (int, float)) and self.Mstar == 0 and np.all(np.isfinite(modpar)):
-            return out      # Mstar = 0 (the default): every mass is exactly 0.0, skip the per-walker loop
         names = self.modpar_names
+        cols = []
         for i in range(self._n_planets):
             sfx = "" if "P" in names else "_" + str(i)
-            iP, iK = names.index("P" + sfx), names.index("K" + sfx)
-            iO, iE = names.index("omega" + sfx), names.index("ecc" + sfx)
+            cols.append((names.index("P" + sfx), names.index("K" + sfx), names.index("omega" + sfx), names.index("ecc" + sfx)))
+        if isinstance(self.Mstar, (int, float)) and self.Mstar == 0 and np.all(np.isfinite(modpar)) and all(
+                np.all(modpar[:, iP] >= 0) and np.all(np.abs(modpar[:, iO]) <= 1) for iP, _, iO, _ in cols):
+            # Mstar = 0 (the default): every mass is exactly 0.0 -- provided the formula is finite: the reference
+            # yields NaN, not 0, when its "eccentricity" slot exceeds 1 or P < 0 (sqrt / cube root of a negative times 0)
+            return out
+        for i in range(self._n_planets):
+            iP, iK, iO, iE = cols[i]
             # element by element on NumPy scalars, as the reference does: the array (SIMD) pow differs
             # from the scalar libm pow in the last bit
             for w in range(W):
@@ -576,9 +581,12 @@ class MCMC:
             for i in range(self._n_planets):
                 sfx = "" if "P" in names else "_" + str(i)
                 iP, iK, iO = names.index("P" + sfx), names.index("K" + sfx), names.index("omega" + sfx)
-                masses[:, :, i] = aux.mass_calc([mh[1:, :, iP], mh[1:, :, iK], mh[1:, :, iO]], self.Mstar)
+                iE = names.index("ecc" + sfx)
+                masses[:, :, i] = aux.mass_calc([mh[1:, :, iP], mh[1:, :, iK], mh[1:, :, iO], mh[1:, :, iE]], self.Mstar)
             for k in range(it):
                 self._hist_mass.append(masses[k:k + 1])
+            # the state a following split_step / compute / compare continues from: masses of the last accepted positions
+            self.mass0_list = self._masses(self.modpar0[0])
         else:
             for k in range(it):
                 self._hist_mass.append(np.zeros((1, W, 0)))
@@ -607,7 +615,13 @@ class MCMC:
 def run_MCMC(iterations, t, rv, rv_err, hparam0, kernel_name, model_param0=None, model_name=["no_model"], prior_list=[], numb_chains=None, n_splits=None, a=None, Rstar=None, Mstar=None, flags=None, plot_convergence=False, saving_folder=None, gelman_rubin_limit=1.1):
     """Run the ensemble MCMC (reference mcmc.py:676-874; same arguments, prints and return tuple:
     ``(logL_list, hparameter_list, model_parameter_list, completed_iterations)`` and additionally
-    ``mass`` as the last element when ``Mstar`` is given)."""
+    ``mass`` as the last element when ``Mstar`` is given).
+
+    ``saving_folder`` and ``gelman_rubin_limit`` are accepted for signature compatibility and have no effect, exactly as in
+    the reference whenever ``plot_convergence`` is False (they are only read inside its convergence-plot branch,
+    mcmc.py:816-860, which drops into pdb -- SURVEY.md F10); ``completed_iterations`` is therefore always
+    ``iterations``.  ``plot_convergence=True`` raises ``NotImplementedError`` (needs matplotlib; out of scope).  A correct
+    Gelman-Rubin statistic is available separately as ``MCMC.gelman_rubin_calc`` (non-parity)."""
     if model_param0 == None:  # noqa: E711
         if model_name[0].startswith("no") or model_name[0].startswith("No"):
             model_param0 = modl.mod_create(["no_model"])
