@@ -12,7 +12,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libmagpy_rv_b200.so")
+# MRV_LIB: another build of the same library (A/B probes of kernel variants, tools/build_variant.py); unset in normal use
+LIB_PATH = os.environ.get("MRV_LIB") or os.path.join(_HERE, "_lib", "libmagpy_rv_b200.so")
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)

@@ -82,6 +82,24 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
+// experiment switches (tools/build_variant.py): defaults are the measured best
+#ifndef DAG_DIAG_MAP
+#define DAG_DIAG_MAP 2        // 0: diagonal tiles updated in full; 1: (4,4,4,2 | 1,1,1,3) fragment rows per warp; 2: (3,3,3,3 | 2,2,2,2)
+#endif
+#ifndef DAG_PREFETCH
+#define DAG_PREFETCH 0        // 0: dependency loads at the start of a task (measured best); 1: acquire loads during the previous task; 2: relaxed loads + one fence
+#endif
+#ifdef DAG_KEEP_THREADFENCE
+#define DAG_PRE_RELEASE_FENCE() __threadfence()
+#else
+#define DAG_PRE_RELEASE_FENCE()   // st.release.gpu is itself cumulative over everything ordered before it (bar.sync included)
+#endif
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
 // Wait until *p >= need.  false = aborted (another CTA gave up, or this wait exceeded the limit).
@@ -154,11 +172,13 @@ __device__ __forceinline__ void dag_decode(const DagArgs& g, int tsk, int& type,
 // SOLVE: A fragments straight from the resident C tile in R0 (slice q at q * SLICE_ELEMS), inv(L_kk) slices through the
 // 3-stage ring R1; the warp owning output columns [32 wn, 32 wn + 32) stops issuing after slice q_last = 2 wn + 1
 // (inv(L) is lower triangular).  `q0` is the ring's running slice counter (stage and barrier phase persist across tasks).
-template <bool SOLVE>
+// DIAG (update of a diagonal tile): only the lower triangle is needed, so the warp owns `nmi` <= 4 m16 row fragments
+// (dag_diag_map) and neither loads nor multiplies the others.
+template <bool SOLVE, bool DIAG = false>
 __device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices, unsigned q0, const double* ringA,
                                              const double* ringB, unsigned long long* fbar, unsigned long long* ebar,
                                              const double* __restrict__ Asrc, const double* __restrict__ Bsrc, int a_lane,
-                                             int b_lane, int q_last, int tid, int lane) {
+                                             int b_lane, int q_last, int tid, int lane, int nmi = 4) {
   constexpr unsigned NSTG = SOLVE ? DAG_BSTAGES : GEMM_TMA_STAGES;
   constexpr unsigned slice_bytes = SLICE_ELEMS * sizeof(double);
   auto a_ptr = [&](int q, unsigned st) -> const double* {
@@ -174,7 +194,8 @@ __device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices
     const double* As = a_ptr(0, st0);
     const double* Bs = b_ptr(st0);
 #pragma unroll
-    for (int v = 0; v < 8; ++v) af[0][v] = As[v << 5];
+    for (int v = 0; v < 8; ++v)
+      if (!DIAG || (v >> 1) < nmi) af[0][v] = As[v << 5];
 #pragma unroll
     for (int v = 0; v < 4; ++v) bf[0][v] = Bs[v << 5];
   }
@@ -205,7 +226,8 @@ __device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices
       const int cur = kk & 1, nxt = cur ^ 1;
       if (kk < 3) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v) af[nxt][v] = As[(((kk + 1) * 16 + v) << 5)];
+        for (int v = 0; v < 8; ++v)
+          if (!DIAG || (v >> 1) < nmi) af[nxt][v] = As[(((kk + 1) * 16 + v) << 5)];
 #pragma unroll
         for (int v = 0; v < 4; ++v) bf[nxt][v] = Bs[(((kk + 1) * 16 + v) << 5)];
       } else if (q + 1 < nslices) {
@@ -214,15 +236,18 @@ __device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices
         const double* An = a_ptr(q + 1, sn);
         const double* Bn = b_ptr(sn);
 #pragma unroll
-        for (int v = 0; v < 8; ++v) af[nxt][v] = An[v << 5];
+        for (int v = 0; v < 8; ++v)
+          if (!DIAG || (v >> 1) < nmi) af[nxt][v] = An[v << 5];
 #pragma unroll
         for (int v = 0; v < 4; ++v) bf[nxt][v] = Bn[v << 5];
       }
       if (!SOLVE || q <= q_last) {   // warp-uniform
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
+          if (!DIAG || mi < nmi) {   // warp-uniform
 #pragma unroll
-          for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
+            for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
+          }
       }
     }
     __syncwarp();
@@ -298,6 +323,25 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
     bulk_g2s(dst + 6 * TILE, g.cpar_wave + (size_t)b * 8, 8 * sizeof(double), bar);
   };
 
+  // Deferred release (thread 0): the progress counter of a finished off-diagonal tile is published after the NEXT task's
+  // generation phase instead of right behind the tile's 128 KiB of stores -- the fence then finds them drained instead
+  // of waiting for them.  It is flushed early whenever this CTA is about to wait (the awaited task may itself be waiting
+  // for this counter) or to leave.  Diagonal tiles, which a whole tile column waits for, are released at once.
+  int* pend_ptr = nullptr;
+  int pend_val = 0;
+  auto flush_release = [&]() {
+    if (pend_ptr != nullptr) {
+      DAG_PRE_RELEASE_FENCE();
+      st_release_gpu(pend_ptr, pend_val);
+      pend_ptr = nullptr;
+    }
+  };
+
+  // Dependency state of the NEXT task, sampled by thread 0 while the current task computes (the counters only grow, so
+  // "ready" stays true; the acquire loads are ordered before the bulk copies of the next task by program order and the
+  // proxy fence at its start).  In the common case a task then starts without a single global-memory round trip.
+  int pre_tsk = -1, pre_v1 = 0, pre_v2 = 0, pre_abort = 0;
+
   int next_tsk = 0x7fffffff;
   if (tid == 0) {
     if (ld_acquire_gpu(abort_flag) == 0) next_tsk = atomicAdd(g.counter, 1);
@@ -311,18 +355,28 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
       const int tsk = next_tsk;
       next_tsk = atomicAdd(g.counter, 1);   // the task after this one: its round trip overlaps with this task
       if (tsk < g.total_tasks) {
-        if (ld_acquire_gpu(abort_flag) == 0) {
+        if ((pre_tsk == tsk ? pre_abort : ld_acquire_gpu(abort_flag)) == 0) {
           dag_decode(g, tsk, type, b, i, k);
           // update operands: rows i and k finished through column k - 1 (also orders the residual block r_i / r_k)
           const int* rd = g.rowdone + (size_t)b * g.nt;
-          const int v1 = ld_acquire_gpu(rd + i), v2 = ld_acquire_gpu(rd + k);   // both in flight; the common case is "ready"
-          if ((v1 < k || v2 < k) && !(dag_wait(rd + i, k, abort_flag) && dag_wait(rd + k, k, abort_flag))) type = DAG_TASK_EXIT;
+          int v1 = pre_v1, v2 = pre_v2;
+          if (pre_tsk != tsk || v1 < k || v2 < k) {
+            v1 = ld_acquire_gpu(rd + i);
+            v2 = ld_acquire_gpu(rd + k);
+          } else if (DAG_PREFETCH == 2) {
+            fence_acq_rel_gpu();           // the sampled values were relaxed loads: relaxed load + fence = acquire
+          }
+          if (v1 < k || v2 < k) {
+            flush_release();
+            if (!(dag_wait(rd + i, k, abort_flag) && dag_wait(rd + k, k, abort_flag))) type = DAG_TASK_EXIT;
+          }
           diag_ready = (type == DAG_TASK_OFF && v2 >= k + 1) ? 1 : 0;
           fence_proxy_async();
         }
         // this task's points were requested during the previous one: never leave with a bulk copy in flight
         if (type == DAG_TASK_EXIT) mbar_wait(&pt_bar[n_local & 1], (n_local >> 1) & 1);
       }
+      if (type == DAG_TASK_EXIT) flush_release();
       s_task[0] = type;
       s_task[1] = b;
       s_task[2] = i;
@@ -369,7 +423,24 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
     mbar_wait(&pt_bar[n_local & 1], (n_local >> 1) & 1);   // this task's points (issued during the previous task)
 
     double acc[4][4][4];
-    const int wn0 = warp & 3;                              // update: 2 x 4 warp grid
+    // update: 2 x 4 warp grid, warp tile = rows [rb, rb + 64) x columns [32 wn0, 32 wn0 + 32).  A DIAGONAL tile needs its
+    // lower triangle only: 20 of the 32 (m16 x n32) fragment rows; they are dealt so that every SM sub-partition (warps
+    // w and w + 4) issues 5 of them instead of 8 -- the update of a diagonal tile takes 5/8 of a full tile product.
+    //   warp            0     1     2     3     4     5     6     7
+    //   column block    0     0     1     1     2     3     3     2
+    //   m16 rows       0-3   4-7   2-5   6-7    4     6     7    5-7
+    int wn0 = warp & 3, rb = wm * 64, nmi = 4;
+    if (type == DAG_TASK_DIAG) {
+#if DAG_DIAG_MAP == 1
+      wn0 = (0x23321100u >> (4 * warp)) & 15;
+      rb = 16 * ((0x57646240u >> (4 * warp)) & 15);
+      nmi = (0x31112444u >> (4 * warp)) & 15;
+#elif DAG_DIAG_MAP == 2
+      wn0 = (0x32201100u >> (4 * warp)) & 15;
+      rb = 16 * ((0x66465230u >> (4 * warp)) & 15);
+      nmi = (0x22223333u >> (4 * warp)) & 15;
+#endif
+    }
     const int wn1 = wm ? 3 - (warp & 3) : (warp & 3);      // solve: the two warps of an SM sub-partition get wn and 3 - wn
     {
       // ---- generation: acc = -K(ti, tk) ----
@@ -384,14 +455,14 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int np2 = 0; np2 < 2; ++np2)
-            gen_interior8_inline<3>(cp, pr, wm * 64 + mi * 16 + gq, pc, wn * 32 + np2 * 16 + 2 * tig, acc[mi][2 * np2],
+            gen_interior8_inline<3>(cp, pr, rb + mi * 16 + gq, pc, wn * 32 + np2 * 16 + 2 * tig, acc[mi][2 * np2],
                                     acc[mi][2 * np2 + 1]);
       } else if (interior) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int np2 = 0; np2 < 2; ++np2) {
-            const int R = wm * 64 + mi * 16 + gq;
+            const int R = rb + mi * 16 + gq;
             const int C = wn * 32 + np2 * 16 + 2 * tig;
             const Cov8 f = gen_interior8(cp.kind, cp.a2, cp.c1, cp.c2, cp.c3, pr, TILE, R, pc, TILE, C);
             acc[mi][2 * np2][0] = -f.v0; acc[mi][2 * np2][1] = -f.v1; acc[mi][2 * np2][2] = -f.v2; acc[mi][2 * np2][3] = -f.v3;
@@ -403,7 +474,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int np2 = 0; np2 < 2; ++np2) {
-            const int R = wm * 64 + mi * 16 + gq;
+            if (mi >= nmi) continue;   // diagonal tile: fragment rows above the diagonal are not this warp's
+            const int R = rb + mi * 16 + gq;
             const int C = wn * 32 + np2 * 16 + 2 * tig;
             double frag[8];
             gen_fragment8(cp, g.N, ti * TILE + R, tk * TILE + C, pr, TILE, R, pc, TILE, C, g.yerr, frag);
@@ -415,13 +487,36 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           }
       }
       // the next task's points: its index has long arrived, the other buffer was last read a task ago
-      if (tid == 0 && next_tsk < g.total_tasks) issue_points(next_tsk, (n_local + 1) & 1);
+      if (tid == 0) {
+        flush_release();
+        if (next_tsk < g.total_tasks) {
+          issue_points(next_tsk, (n_local + 1) & 1);
+          int ntype, nb, ni, nk;
+          dag_decode(g, next_tsk, ntype, nb, ni, nk);
+          const int* nrd = g.rowdone + (size_t)nb * g.nt;
+#if DAG_PREFETCH == 1
+          pre_tsk = next_tsk;
+          pre_v1 = ld_acquire_gpu(nrd + ni);   // land while the update loop runs
+          pre_v2 = ld_acquire_gpu(nrd + nk);
+          pre_abort = ld_acquire_gpu(abort_flag);
+#elif DAG_PREFETCH == 2
+          pre_tsk = next_tsk;
+          pre_v1 = ld_relaxed_gpu(nrd + ni);   // three loads in flight, nobody waits for them here
+          pre_v2 = ld_relaxed_gpu(nrd + nk);
+          pre_abort = ld_relaxed_gpu(abort_flag);
+#endif
+        }
+      }
       tm.mark(1);
     }
     // ---- update: acc += sum_p L(ti,p) L(tk,p)^T ----
     if (tk > 0) {
-      dag_mainloop<false>(acc, tk * SLICES_PER_TILE, qg, stages, nullptr, full_bar, empty_bar, rowA, rowB, ((wm * 8) << 5) + lane,
-                          ((wn0 * 4) << 5) + lane, 0x7fffffff, tid, lane);
+      if (type == DAG_TASK_DIAG)
+        dag_mainloop<false, true>(acc, tk * SLICES_PER_TILE, qg, stages, nullptr, full_bar, empty_bar, rowA, rowB,
+                                  ((rb >> 3) << 5) + lane, ((wn0 * 4) << 5) + lane, 0x7fffffff, tid, lane, nmi);
+      else
+        dag_mainloop<false>(acc, tk * SLICES_PER_TILE, qg, stages, nullptr, full_bar, empty_bar, rowA, rowB, ((wm * 8) << 5) + lane,
+                            ((wn0 * 4) << 5) + lane, 0x7fffffff, tid, lane);
       qg += tk * SLICES_PER_TILE;
     }
     tm.mark(2);
@@ -530,12 +625,19 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         __syncthreads();
         // one fence after the barrier covers the whole CTA's stores (fence cumulativity), then the release
         if (tid == 0) {
-          __threadfence();
+#ifdef DAG_EAGER_RELEASE
+          DAG_PRE_RELEASE_FENCE();
           st_release_gpu(rd + ti, tk + 1);
+#else
+          pend_ptr = rd + ti;
+          pend_val = tk + 1;
+#endif
         }
         tm.mark(6);
       } else {
         // ---- diagonal tile: S = -acc (column-major, ld = PB_LD), residual row, sweep ----
+        // (only the fragment rows that reach the lower triangle exist; the sweep never reads what lies above it: the
+        // strict upper triangle is where it ASSIGNS the inverse, blocked.cuh)
         __syncthreads();   // every warp has left the ring: S aliases it
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -543,7 +645,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-              const int R = wm * 64 + mi * 16 + gq + 8 * (v >> 1);
+              if (mi >= nmi) continue;
+              const int R = rb + mi * 16 + gq + 8 * (v >> 1);
               const int C = wn * 32 + ni * 8 + 2 * tig + (v & 1);
               S[R + (size_t)C * PB_LD] = -acc[mi][ni][v];
             }
@@ -596,7 +699,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         }
         __syncthreads();       // (readers of inv(L_kk) fence on their side, see the solve epilogue)
         if (tid == 0) {
-          __threadfence();
+          DAG_PRE_RELEASE_FENCE();
           st_release_gpu(rd + tk, tk + 1);
         }
         tm.mark(12);
