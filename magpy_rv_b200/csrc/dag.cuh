@@ -92,6 +92,9 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 #ifndef DAG_DIAG_MAP
 #define DAG_DIAG_MAP 2        // 0: diagonal tiles updated in full; 1: (4,4,4,2 | 1,1,1,3) fragment rows per warp; 2: (3,3,3,3 | 2,2,2,2)
 #endif
+#ifndef DAG_SOLVE_STRIPS
+#define DAG_SOLVE_STRIPS 1    // solve phase in 16 x 128 warp strips (balanced triangular skip) instead of the 2 x 4 warp grid
+#endif
 #ifndef DAG_PREFETCH
 #define DAG_PREFETCH 0        // 0: dependency loads at the start of a task (measured best); 1: acquire loads during the previous task; 2: relaxed loads + one fence
 #endif
@@ -249,6 +252,59 @@ __device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices
             for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
           }
       }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ebar[st]);
+  }
+}
+
+// Solve phase X = C inv(L_kk)^T in WARP STRIPS: warp w owns the 16 rows [16 w, 16 w + 16) of all 128 columns (16 n8
+// accumulator fragments).  inv(L_kk) is lower triangular, so k16 slice q only feeds the columns >= 16 q, i.e. the
+// fragment pairs vp >= q: every warp issues the same 36 / 64 of a full tile product -- the triangle is skipped without
+// any imbalance between warps (the 2 x 4 warp grid of the update had the warps of column block 3 do all 8 slices, and a
+// single warp cannot use its sub-partition's FP64 tensor pipe alone).  A fragments come straight from the resident C
+// tile (slice q at q * SLICE_ELEMS), inv(L_kk) slices through the 3-stage ring.  One code copy per slice (Q is a compile
+// time constant), so the skip costs no predicates.
+template <int Q>
+__device__ __forceinline__ void dag_solve_slice(double (&acc)[4][4][4], const double* __restrict__ As, const double* __restrict__ Bs) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const double a0 = As[(kk * 16) << 5], a1 = As[(kk * 16 + 1) << 5];
+#pragma unroll
+    for (int v = 2 * Q; v < 16; ++v) dmma_1684(acc[v >> 2][v & 3], a0, a1, Bs[(kk * 16 + v) << 5]);
+  }
+}
+__device__ __forceinline__ void dag_solve_strips(double (&acc)[4][4][4], unsigned q0, const double* Ctile, const double* ringB,
+                                                 unsigned long long* fbar, unsigned long long* ebar,
+                                                 const double* __restrict__ Bsrc, int warp, int tid, int lane) {
+  constexpr unsigned NSTG = DAG_BSTAGES;
+  constexpr unsigned slice_bytes = SLICE_ELEMS * sizeof(double);
+  const int a_lane = ((2 * warp) << 5) + lane;
+#pragma unroll 1
+  for (int q = 0; q < SLICES_PER_TILE; ++q) {
+    const unsigned qa = q0 + q, st = qa % NSTG;
+    {
+      const int qn = q + 2;   // refill: slice q + 2 goes into the stage consumed one iteration ago
+      if (tid == 0 && qn < SLICES_PER_TILE) {
+        const unsigned qq = q0 + qn, sn = qq % NSTG, u = qq / NSTG;
+        if (u > 0) mbar_wait(&ebar[sn], (u - 1) & 1);
+        mbar_expect_tx(&fbar[sn], slice_bytes);
+        bulk_g2s(const_cast<double*>(ringB) + sn * SLICE_ELEMS, Bsrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
+      }
+      __syncwarp();
+    }
+    mbar_wait(&fbar[st], (qa / NSTG) & 1);
+    const double* As = Ctile + (size_t)q * SLICE_ELEMS + a_lane;
+    const double* Bs = ringB + st * SLICE_ELEMS + lane;
+    switch (q) {
+      case 0: dag_solve_slice<0>(acc, As, Bs); break;
+      case 1: dag_solve_slice<1>(acc, As, Bs); break;
+      case 2: dag_solve_slice<2>(acc, As, Bs); break;
+      case 3: dag_solve_slice<3>(acc, As, Bs); break;
+      case 4: dag_solve_slice<4>(acc, As, Bs); break;
+      case 5: dag_solve_slice<5>(acc, As, Bs); break;
+      case 6: dag_solve_slice<6>(acc, As, Bs); break;
+      default: dag_solve_slice<7>(acc, As, Bs); break;
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ebar[st]);
@@ -570,8 +626,12 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
             for (int v = 0; v < 4; ++v) acc[mi][ni][v] = 0.0;
+#if DAG_SOLVE_STRIPS
+        dag_solve_strips(acc, qb, stages, bring, fullB, emptyB, Bsrc, warp, tid, lane);
+#else
         dag_mainloop<true>(acc, SLICES_PER_TILE, qb, stages, bring, fullB, emptyB, nullptr, Bsrc, ((wm * 8) << 5) + lane,
                            ((wn1 * 4) << 5) + lane, 2 * wn1 + 1, tid, lane);
+#endif
         qb += SLICES_PER_TILE;
       }
       tm.mark(5);
@@ -586,6 +646,36 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
       if (type == DAG_TASK_OFF) {
         // X = acc is L(i,k): store it and fold r_i -= X z_k
         __syncthreads();   // zs; every warp has read its last A fragments from the C tile
+#if DAG_SOLVE_STRIPS
+        // strip layout: fragment v = 4 cb + ni of the warp's 16 rows.  Row sums in the order of the 2 x 4 layout (per
+        // column block cb: ni ascending, then the quad's lanes; then ((p0 + p1) + p2) + p3), so r_i is bitwise the same.
+#pragma unroll
+        for (int v1 = 0; v1 < 2; ++v1) {
+          const int R = warp * 16 + gq + 8 * v1;
+          double p4[4];
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb) {
+            double s = 0.0;
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) {
+              const int C = cb * 32 + ni * 8 + 2 * tig;
+              double2 x;
+              x.x = acc[cb][ni][2 * v1 + 0];
+              x.y = acc[cb][ni][2 * v1 + 1];
+              *reinterpret_cast<double2*>(Ct + tile_off(R, C)) = x;
+              s = fma(x.x, zs[C], s);
+              s = fma(x.y, zs[C + 1], s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            p4[cb] = s;
+          }
+          if (tig == 0) {
+            double* ri = g.resid + (size_t)b * g.ldr + (size_t)ti * TILE;
+            ri[R] = __ldcg(ri + R) - (((p4[0] + p4[1]) + p4[2]) + p4[3]);
+          }
+        }
+#else
         double rowsum[4][2];
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -622,6 +712,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           double* ri = g.resid + (size_t)b * g.ldr + (size_t)ti * TILE;
           ri[tid] = __ldcg(ri + tid) - s;
         }
+#endif
         __syncthreads();
         // one fence after the barrier covers the whole CTA's stores (fence cumulativity), then the release
         if (tid == 0) {
