@@ -405,14 +405,17 @@ static int choose_path(const mrv_problem* p, int64_t W = 0) {
   // one-CTA-per-walker streamed-panel kernel up to 512, the tiled wave factorisation above
   if (p->desc.N <= MRV_SMALL_BLK_N_MAX) return MRV_PATH_FUSED_SMEM;
   if (p->desc.N > MID_N_MAX) return MRV_PATH_BLOCKED;
-  // 320 < N <= 512: the two paths are within +-9 % of each other when N nearly fills its 128-wide tiles
-  // (padding < 32 points); the one-CTA-per-walker kernel then wins exactly when its rounds of num_sms CTAs are
-  // well filled (measured, one B200: 384 x 512 walkers = 3.46 rounds 315 k vs 344 k evals/s tiled, 384 x 1024 =
-  // 6.9 rounds 367 k vs 353 k; 512 x 512 191 k vs 205 k, 512 x 1024 219 k vs 210 k, 512 x 148 206 k vs 170 k)
-  const int pad128 = p->n_pad - p->desc.N;
-  if (p->desc.N > 320 && pad128 < 32 && W > p->num_sms) {
-    const int64_t rounds = (W + p->num_sms - 1) / p->num_sms;
-    if ((double)W < 0.93 * (double)(rounds * p->num_sms)) return MRV_PATH_BLOCKED;
+  // 320 < N <= 512 (round 2, tools/crossover_probe.py, profiles/r2s_crossover_probe.txt): the tiled path -- the dataflow
+  // kernel from 3 tile columns on -- pads N to a multiple of 128, the one-CTA-per-walker kernel runs in rounds of num_sms
+  // walkers.  Tiled wins when N fills its tiles: always at N = 384 / 512 (1.07-1.37x), at N / n_pad >= 0.87 when the rounds
+  // are badly filled (256 or 512 walkers: 86 %), >= 0.90 for well filled rounds (1024 walkers), >= 0.94 for exactly one
+  // full round (148 walkers, the streamed-panel kernel's best case).
+  if (p->desc.N > 320) {
+    const int64_t Wn = W > 0 ? W : p->num_sms;
+    const int64_t rounds = (Wn + p->num_sms - 1) / p->num_sms;
+    const double fill = (double)Wn / (double)(rounds * p->num_sms);
+    const double thr = fill >= 0.995 ? 0.94 : (fill >= 0.93 ? 0.90 : 0.87);
+    if ((double)p->desc.N >= thr * (double)p->n_pad) return MRV_PATH_BLOCKED;
   }
   return MRV_PATH_MID;
 }

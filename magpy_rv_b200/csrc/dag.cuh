@@ -58,10 +58,10 @@ struct DagArgs {
 };
 
 #define DAG_THREADS 256
-// automatic choice (measured, tools/dag_probe.py, one B200, 128 walkers): the dataflow kernel wins from 6 tile columns
-// (N > 640: 1.01x at 768, 1.08x at 1024, 1.01x at 2048, 1.03x at 4096) and is bitwise identical; below that the
-// launch-per-column loop with its 16-warp diagonal-tile kernel is 2-4 % ahead (N = 500, 640)
-#define DAG_AUTO_MIN_TILES 6
+// automatic choice (measured, tools/dag_probe.py, one B200): with the lower-triangle diagonal update, the strip solve and
+// the deferred release the dataflow kernel is ahead of the launch-per-column loop from 3 tile columns on (1.12-1.31x at
+// N = 384, 1.06x at C3, 1.24x at 640, 1.22x at 1024, 1.11x at 2048, 1.08x at 4096) and bitwise identical to it
+#define DAG_AUTO_MIN_TILES 3
 #define DAG_AUTO_MAX_TILES 32
 #define DAG_BSTAGES 3                 // ring of inv(L_kk) k16 slices for the solve phase
 #define DAG_SWEEP_DOUBLES (PB_LD * TILE + PB_NB * PB_PA_LD + PB_NB * PB_PB_LD + PB_NB * PB_D_LD + PB_NB + 64 + TILE)
@@ -90,7 +90,7 @@ __device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
 // experiment switches (tools/build_variant.py): defaults are the measured best
 #ifndef DAG_DIAG_MAP
-#define DAG_DIAG_MAP 2        // 0: diagonal tiles updated in full; 1: (4,4,4,2 | 1,1,1,3) fragment rows per warp; 2: (3,3,3,3 | 2,2,2,2)
+#define DAG_DIAG_MAP 3        // 0: diagonal tiles updated in full; 1: (4,4,4,2 | 1,1,1,3) fragment rows per warp; 2: (3,3,3,3 | 2,2,2,2); 3: 9 fragments per warp
 #endif
 #ifndef DAG_SOLVE_STRIPS
 #define DAG_SOLVE_STRIPS 1    // solve phase in 16 x 128 warp strips (balanced triangular skip) instead of the 2 x 4 warp grid
@@ -127,7 +127,7 @@ enum { DAG_TASK_EXIT = 0, DAG_TASK_DIAG = 1, DAG_TASK_OFF = 2 };
 //  4 wait for the diagonal tile     5 solve main loop                    6 solve epilogue + release
 //  7 diagonal: acc -> S + residual  8 sweep: pivot blocks  9 sweep: panel rows  10 sweep: trailing DMMA update
 // 11 pivots / log det / z           12 inv(L) write-back + release       13 # diagonal tasks  14 # off-diagonal tasks
-// 15 end-of-task barrier
+// 15 update main loop of DIAGONAL tasks (slot 2 then holds the off-diagonal tasks only)
 __device__ unsigned long long g_dag_timing[16];
 
 __device__ __forceinline__ void dag_decode(const DagArgs& g, int tsk, int& type, int& b, int& i, int& k) {
@@ -258,6 +258,110 @@ __device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices
   }
 }
 
+// Update of a DIAGONAL tile, lower triangle only, dealt by m16 x n8 accumulator fragments: fragment (u, v) = rows
+// [16 u, 16 u + 16) x columns [8 v, 8 v + 8) is needed for v <= 2 u + 1, 72 of the 128 fragments of the tile -- exactly 9 per
+// warp, and 18 per SM sub-partition (warps w and w + 4):
+//   warp          0        1              2        3              4        5              6        7
+//   segment A   u7 v0-8  u7 v9-15       u6 v0-8  u6 v9-13       u5 v0-8  u2 v0-5        u4 v0-8  u3 v0-7
+//   segment B            u0 v0-1                 u1 v0-3                 u5 v9-11                u4 v9
+// so a diagonal tile's update costs 9/16 of a full tile product (the 2 x 4 warp grid: 16/16; whole fragment rows dealt
+// 3,3,3,3 | 2,2,2,2: 12/16 -- a lone warp cannot keep its sub-partition's FP64 tensor pipe busy, so the largest share
+// of any WARP is what counts).  Segment A lives in accumulator slots 0..8 (acc[s >> 2][s & 3]), segment B in acc[3][0..3].
+// Each warp runs its own code copy (compile-time segment shapes: no predicates around the DMMAs); summation order per
+// element is unchanged (k ascending), so the tile is bitwise what the full update gives.
+__device__ __forceinline__ void dag_diag_segments(int warp, int& uA, int& vA0, int& nA, int& uB, int& vB0, int& nB) {
+  const int sh = 4 * warp;
+  uA = (0x34256677u >> sh) & 15;
+  vA0 = (0x00009090u >> sh) & 15;
+  nA = (0x89695979u >> sh) & 15;
+  uB = (0x40501000u >> sh) & 15;
+  vB0 = (0x90900000u >> sh) & 15;
+  nB = (0x10304020u >> sh) & 15;
+}
+template <int UA, int VA0, int NA, int UB, int VB0, int NB>
+__device__ __forceinline__ void dag_diag_loop(double (&acc)[4][4][4], int nslices, unsigned q0, const double* ring,
+                                              unsigned long long* fbar, unsigned long long* ebar,
+                                              const double* __restrict__ Asrc, int tid, int lane) {
+  constexpr unsigned NSTG = GEMM_TMA_STAGES;
+  constexpr unsigned slice_bytes = SLICE_ELEMS * sizeof(double);
+  constexpr int NF = 2 + NA + (NB > 0 ? 2 + NB : 0);   // fragments of one k4 step: A rows of segment A, its B columns, same for B
+  double fr[2][NF];
+  auto load = [&](double (&f)[NF], const double* As, const double* Bs, int kk) {
+    f[0] = As[(kk * 16 + 2 * UA) << 5];
+    f[1] = As[(kk * 16 + 2 * UA + 1) << 5];
+#pragma unroll
+    for (int s2 = 0; s2 < NA; ++s2) f[2 + s2] = Bs[(kk * 16 + VA0 + s2) << 5];
+    if (NB > 0) {
+      f[2 + NA] = As[(kk * 16 + 2 * UB) << 5];
+      f[3 + NA] = As[(kk * 16 + 2 * UB + 1) << 5];
+#pragma unroll
+      for (int s2 = 0; s2 < NB; ++s2) f[4 + NA + s2] = Bs[(kk * 16 + VB0 + s2) << 5];
+    }
+  };
+  auto compute = [&](const double (&f)[NF]) {
+#pragma unroll
+    for (int s2 = 0; s2 < NA; ++s2) dmma_1684(acc[s2 >> 2][s2 & 3], f[0], f[1], f[2 + s2]);
+    if (NB > 0) {
+#pragma unroll
+      for (int s2 = 0; s2 < NB; ++s2) dmma_1684(acc[3][s2], f[2 + NA], f[3 + NA], f[4 + NA + s2]);
+    }
+  };
+  {
+    const unsigned st0 = q0 % NSTG;
+    mbar_wait(&fbar[st0], (q0 / NSTG) & 1);
+    const double* As = ring + st0 * GEMM_STAGE_DOUBLES + lane;   // the slice of tile row k is both operands
+    load(fr[0], As, As, 0);
+  }
+#pragma unroll 1
+  for (int q = 0; q < nslices; ++q) {
+    const unsigned qa = q0 + q, st = qa % NSTG;
+    {
+      const int qn = q + 2;   // refill: slice q + 2 goes into the stage consumed two iterations ago
+      if (tid == 0 && qn < nslices) {
+        const unsigned qq = q0 + qn, sn = qq % NSTG, u = qq / NSTG;
+        if (u > 0) mbar_wait(&ebar[sn], (u - 1) & 1);
+        double* dst = const_cast<double*>(ring) + sn * GEMM_STAGE_DOUBLES;
+        mbar_expect_tx(&fbar[sn], slice_bytes);
+        bulk_g2s(dst, Asrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
+      }
+      __syncwarp();
+    }
+    const double* As = ring + st * GEMM_STAGE_DOUBLES + lane;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int cur = kk & 1, nxt = cur ^ 1;
+      if (kk < 3) load(fr[nxt], As, As, kk + 1);
+      else if (q + 1 < nslices) {
+        const unsigned qn1 = qa + 1, sn = qn1 % NSTG;
+        mbar_wait(&fbar[sn], (qn1 / NSTG) & 1);
+        const double* An = ring + sn * GEMM_STAGE_DOUBLES + lane;
+        load(fr[nxt], An, An, 0);
+      }
+      compute(fr[cur]);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ebar[st]);
+  }
+}
+__device__ __forceinline__ void dag_diag_update(double (&acc)[4][4][4], int nslices, unsigned q0, const double* ring,
+                                                unsigned long long* fbar, unsigned long long* ebar,
+                                                const double* __restrict__ Asrc, const double* __restrict__ Bsrc, int warp, int tid,
+                                                int lane) {
+#ifdef DAG_DIAG_SAMECODE   // timing experiment only (wrong results): every warp runs warp 0's code copy
+  if (warp >= 0) { dag_diag_loop<7, 0, 9, 0, 0, 0>(acc, nslices, q0, ring, fbar, ebar, Asrc, tid, lane); return; }
+#endif
+  switch (warp) {   // one code copy per warp; only warp 0's contains a live producer branch
+    case 0: dag_diag_loop<7, 0, 9, 0, 0, 0>(acc, nslices, q0, ring, fbar, ebar, Asrc, tid, lane); break;
+    case 1: dag_diag_loop<7, 9, 7, 0, 0, 2>(acc, nslices, q0, ring, fbar, ebar, Asrc, 1, lane); break;
+    case 2: dag_diag_loop<6, 0, 9, 0, 0, 0>(acc, nslices, q0, ring, fbar, ebar, Asrc, 1, lane); break;
+    case 3: dag_diag_loop<6, 9, 5, 1, 0, 4>(acc, nslices, q0, ring, fbar, ebar, Asrc, 1, lane); break;
+    case 4: dag_diag_loop<5, 0, 9, 0, 0, 0>(acc, nslices, q0, ring, fbar, ebar, Asrc, 1, lane); break;
+    case 5: dag_diag_loop<2, 0, 6, 5, 9, 3>(acc, nslices, q0, ring, fbar, ebar, Asrc, 1, lane); break;
+    case 6: dag_diag_loop<4, 0, 9, 0, 0, 0>(acc, nslices, q0, ring, fbar, ebar, Asrc, 1, lane); break;
+    default: dag_diag_loop<3, 0, 8, 4, 9, 1>(acc, nslices, q0, ring, fbar, ebar, Asrc, 1, lane); break;
+  }
+}
+
 // Solve phase X = C inv(L_kk)^T in WARP STRIPS: warp w owns the 16 rows [16 w, 16 w + 16) of all 128 columns (16 n8
 // accumulator fragments).  inv(L_kk) is lower triangular, so k16 slice q only feeds the columns >= 16 q, i.e. the
 // fragment pairs vp >= q: every warp issues the same 36 / 64 of a full tile product -- the triangle is skipped without
@@ -266,49 +370,63 @@ __device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices
 // tile (slice q at q * SLICE_ELEMS), inv(L_kk) slices through the 3-stage ring.  One code copy per slice (Q is a compile
 // time constant), so the skip costs no predicates.
 template <int Q>
-__device__ __forceinline__ void dag_solve_slice(double (&acc)[4][4][4], const double* __restrict__ As, const double* __restrict__ Bs) {
+__device__ __forceinline__ void dag_solve_load(double (&f)[18], const double* __restrict__ As, const double* __restrict__ Bs, int kk) {
+  f[0] = As[(kk * 16) << 5];
+  f[1] = As[(kk * 16 + 1) << 5];
+#pragma unroll
+  for (int v = 2 * Q; v < 16; ++v) f[2 + v] = Bs[(kk * 16 + v) << 5];
+}
+template <int Q>
+__device__ __forceinline__ void dag_solve_slice(double (&acc)[4][4][4], double (&fr)[2][18], unsigned q0, const double* Ctile,
+                                                const double* ringB, unsigned long long* fbar, unsigned long long* ebar,
+                                                const double* __restrict__ Bsrc, int a_lane, int tid, int lane) {
+  constexpr unsigned NSTG = DAG_BSTAGES;
+  constexpr unsigned slice_bytes = SLICE_ELEMS * sizeof(double);
+  const unsigned qa = q0 + Q, st = qa % NSTG;
+  if (Q + 2 < SLICES_PER_TILE) {   // refill: slice Q + 2 goes into the stage consumed one iteration ago
+    if (tid == 0) {
+      const unsigned qq = q0 + Q + 2, sn = qq % NSTG, u = qq / NSTG;
+      if (u > 0) mbar_wait(&ebar[sn], (u - 1) & 1);
+      mbar_expect_tx(&fbar[sn], slice_bytes);
+      bulk_g2s(const_cast<double*>(ringB) + sn * SLICE_ELEMS, Bsrc + (size_t)(Q + 2) * SLICE_ELEMS, slice_bytes, &fbar[sn]);
+    }
+    __syncwarp();
+  }
+  const double* As = Ctile + (size_t)Q * SLICE_ELEMS + a_lane;
+  const double* Bs = ringB + st * SLICE_ELEMS + lane;
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
-    const double a0 = As[(kk * 16) << 5], a1 = As[(kk * 16 + 1) << 5];
+    const int cur = (Q * 4 + kk) & 1, nxt = cur ^ 1;
+    if (kk < 3) dag_solve_load<Q>(fr[nxt], As, Bs, kk + 1);
+    else if (Q + 1 < SLICES_PER_TILE) {
+      const unsigned qn1 = qa + 1, sn = qn1 % NSTG;
+      mbar_wait(&fbar[sn], (qn1 / NSTG) & 1);
+      dag_solve_load<(Q + 1 < SLICES_PER_TILE ? Q + 1 : Q)>(fr[nxt], Ctile + (size_t)(Q + 1) * SLICE_ELEMS + a_lane, ringB + sn * SLICE_ELEMS + lane, 0);
+    }
 #pragma unroll
-    for (int v = 2 * Q; v < 16; ++v) dmma_1684(acc[v >> 2][v & 3], a0, a1, Bs[(kk * 16 + v) << 5]);
+    for (int v = 2 * Q; v < 16; ++v) dmma_1684(acc[v >> 2][v & 3], fr[cur][0], fr[cur][1], fr[cur][2 + v]);
   }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&ebar[st]);
 }
 __device__ __forceinline__ void dag_solve_strips(double (&acc)[4][4][4], unsigned q0, const double* Ctile, const double* ringB,
                                                  unsigned long long* fbar, unsigned long long* ebar,
                                                  const double* __restrict__ Bsrc, int warp, int tid, int lane) {
-  constexpr unsigned NSTG = DAG_BSTAGES;
-  constexpr unsigned slice_bytes = SLICE_ELEMS * sizeof(double);
   const int a_lane = ((2 * warp) << 5) + lane;
-#pragma unroll 1
-  for (int q = 0; q < SLICES_PER_TILE; ++q) {
-    const unsigned qa = q0 + q, st = qa % NSTG;
-    {
-      const int qn = q + 2;   // refill: slice q + 2 goes into the stage consumed one iteration ago
-      if (tid == 0 && qn < SLICES_PER_TILE) {
-        const unsigned qq = q0 + qn, sn = qq % NSTG, u = qq / NSTG;
-        if (u > 0) mbar_wait(&ebar[sn], (u - 1) & 1);
-        mbar_expect_tx(&fbar[sn], slice_bytes);
-        bulk_g2s(const_cast<double*>(ringB) + sn * SLICE_ELEMS, Bsrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
-      }
-      __syncwarp();
-    }
-    mbar_wait(&fbar[st], (qa / NSTG) & 1);
-    const double* As = Ctile + (size_t)q * SLICE_ELEMS + a_lane;
-    const double* Bs = ringB + st * SLICE_ELEMS + lane;
-    switch (q) {
-      case 0: dag_solve_slice<0>(acc, As, Bs); break;
-      case 1: dag_solve_slice<1>(acc, As, Bs); break;
-      case 2: dag_solve_slice<2>(acc, As, Bs); break;
-      case 3: dag_solve_slice<3>(acc, As, Bs); break;
-      case 4: dag_solve_slice<4>(acc, As, Bs); break;
-      case 5: dag_solve_slice<5>(acc, As, Bs); break;
-      case 6: dag_solve_slice<6>(acc, As, Bs); break;
-      default: dag_solve_slice<7>(acc, As, Bs); break;
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&ebar[st]);
+  double fr[2][18];
+  {
+    const unsigned st0 = q0 % DAG_BSTAGES;
+    mbar_wait(&fbar[st0], (q0 / DAG_BSTAGES) & 1);
+    dag_solve_load<0>(fr[0], Ctile + a_lane, ringB + st0 * SLICE_ELEMS + lane, 0);
   }
+  dag_solve_slice<0>(acc, fr, q0, Ctile, ringB, fbar, ebar, Bsrc, a_lane, tid, lane);
+  dag_solve_slice<1>(acc, fr, q0, Ctile, ringB, fbar, ebar, Bsrc, a_lane, tid, lane);
+  dag_solve_slice<2>(acc, fr, q0, Ctile, ringB, fbar, ebar, Bsrc, a_lane, tid, lane);
+  dag_solve_slice<3>(acc, fr, q0, Ctile, ringB, fbar, ebar, Bsrc, a_lane, tid, lane);
+  dag_solve_slice<4>(acc, fr, q0, Ctile, ringB, fbar, ebar, Bsrc, a_lane, tid, lane);
+  dag_solve_slice<5>(acc, fr, q0, Ctile, ringB, fbar, ebar, Bsrc, a_lane, tid, lane);
+  dag_solve_slice<6>(acc, fr, q0, Ctile, ringB, fbar, ebar, Bsrc, a_lane, tid, lane);
+  dag_solve_slice<7>(acc, fr, q0, Ctile, ringB, fbar, ebar, Bsrc, a_lane, tid, lane);
 }
 
 __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
@@ -461,6 +579,11 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         const unsigned qq = qg + q, sn = qq % NST, u = qq / NST;
         if (u > 0) mbar_wait(&empty_bar[sn], (u - 1) & 1);
         double* dst = stages + sn * GEMM_STAGE_DOUBLES;
+        if (DAG_DIAG_MAP == 3 && s_task[0] == DAG_TASK_DIAG) {   // rows i and k are the same tile row: one slice serves as A and B
+          mbar_expect_tx(&full_bar[sn], SLICE_ELEMS * sizeof(double));
+          bulk_g2s(dst, rowA + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
+          continue;
+        }
         mbar_expect_tx(&full_bar[sn], 2 * SLICE_ELEMS * sizeof(double));
         bulk_g2s(dst, rowA + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
         bulk_g2s(dst + SLICE_ELEMS, rowB + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
@@ -506,6 +629,24 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
       cp.a2 = pr[6 * TILE]; cp.c1 = pr[6 * TILE + 1]; cp.c2 = pr[6 * TILE + 2]; cp.c3 = pr[6 * TILE + 3];
       cp.jit2 = pr[6 * TILE + 4]; cp.cph = 0.0;
       const bool interior = ti > tk && (ti + 1) * TILE <= g.N;
+#if DAG_DIAG_MAP == 3
+      if (type == DAG_TASK_DIAG) {
+        int uA, vA0, nA, uB, vB0, nB;
+        dag_diag_segments(warp, uA, vA0, nA, uB, vB0, nB);
+#pragma unroll
+        for (int s2 = 0; s2 < 13; ++s2) {
+          const bool segA = s2 < 9;
+          if (segA ? (s2 >= nA) : (s2 - 9 >= nB)) continue;
+          const int R = 16 * (segA ? uA : uB) + gq;
+          const int C = 8 * (segA ? vA0 + s2 : vB0 + s2 - 9) + 2 * tig;
+          double frag[4];
+          gen_fragment4(cp, g.N, tk * TILE + R, tk * TILE + C, pr, TILE, R, pc, TILE, C, g.yerr, frag);
+          const int slot = segA ? s2 : 12 + (s2 - 9);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[slot >> 2][slot & 3][v] = -frag[v];
+        }
+      } else
+#endif
       if (interior && (cp.kind == 3 || cp.kind == 4)) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -568,14 +709,18 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
     // ---- update: acc += sum_p L(ti,p) L(tk,p)^T ----
     if (tk > 0) {
       if (type == DAG_TASK_DIAG)
+#if DAG_DIAG_MAP == 3
+        dag_diag_update(acc, tk * SLICES_PER_TILE, qg, stages, full_bar, empty_bar, rowA, rowB, warp, tid, lane);
+#else
         dag_mainloop<false, true>(acc, tk * SLICES_PER_TILE, qg, stages, nullptr, full_bar, empty_bar, rowA, rowB,
                                   ((rb >> 3) << 5) + lane, ((wn0 * 4) << 5) + lane, 0x7fffffff, tid, lane, nmi);
+#endif
       else
         dag_mainloop<false>(acc, tk * SLICES_PER_TILE, qg, stages, nullptr, full_bar, empty_bar, rowA, rowB, ((wm * 8) << 5) + lane,
                             ((wn0 * 4) << 5) + lane, 0x7fffffff, tid, lane);
       qg += tk * SLICES_PER_TILE;
     }
-    tm.mark(2);
+    tm.mark(type == DAG_TASK_DIAG ? 15 : 2);
 
     bool aborted = false;
     if (type == DAG_TASK_OFF) {
@@ -730,6 +875,22 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         // (only the fragment rows that reach the lower triangle exist; the sweep never reads what lies above it: the
         // strict upper triangle is where it ASSIGNS the inverse, blocked.cuh)
         __syncthreads();   // every warp has left the ring: S aliases it
+#if DAG_DIAG_MAP == 3
+        {
+          int uA, vA0, nA, uB, vB0, nB;
+          dag_diag_segments(warp, uA, vA0, nA, uB, vB0, nB);
+#pragma unroll
+          for (int s2 = 0; s2 < 13; ++s2) {
+            const bool segA = s2 < 9;
+            if (segA ? (s2 >= nA) : (s2 - 9 >= nB)) continue;
+            const int R0 = 16 * (segA ? uA : uB) + gq;
+            const int C0 = 8 * (segA ? vA0 + s2 : vB0 + s2 - 9) + 2 * tig;
+            const int slot = segA ? s2 : 12 + (s2 - 9);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) S[R0 + 8 * (v >> 1) + (size_t)(C0 + (v & 1)) * PB_LD] = -acc[slot >> 2][slot & 3][v];
+          }
+        }
+#else
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
@@ -741,6 +902,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
               const int C = wn * 32 + ni * 8 + 2 * tig + (v & 1);
               S[R + (size_t)C * PB_LD] = -acc[mi][ni][v];
             }
+#endif
         if (tid < TILE) {
           S[TILE + (size_t)tid * PB_LD] = __ldcg(g.resid + (size_t)b * g.ldr + (size_t)tk * TILE + tid);
 #pragma unroll
@@ -798,7 +960,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
     }
     ++n_local;
     __syncthreads();   // s_task / zs / part are rewritten by the next task
-    tm.mark(15);
+    tm.mark(0);   // end-of-task barrier: counted with the next task's fetch
   }
 #ifdef DAG_TIMING
   if (tid == 0)
