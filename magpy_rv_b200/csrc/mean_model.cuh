@@ -45,22 +45,53 @@ __device__ __forceinline__ double block_sum_1bar(double v, double* scratch /* 2 
   return (r0 + r1) + (r2 + r3);
 }
 
+// block_sum_1bar whose barrier also ANDs a per-thread predicate over the block (same single barrier).
+__device__ __forceinline__ double block_sum_1bar_and(double v, double* scratch /* 2 x 32 doubles */, int buf, int pred, int* all) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  double* s = scratch + 32 * buf;
+  if (lane == 0) s[warp] = v;
+  *all = __syncthreads_and(pred);
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+  for (int w = 0; w + 3 < nwarps; w += 4) {
+    r0 += s[w];
+    r1 += s[w + 1];
+    r2 += s[w + 2];
+    r3 += s[w + 3];
+  }
+  for (int w = nwarps & ~3; w < nwarps; ++w) r0 += s[w];
+  return (r0 + r1) + (r2 + r3);
+}
+
 // Newton loop of the eccentric anomaly with PPT points per thread held in registers (point i = tid + j * blockDim).
 // The per-thread partial of ||E - E0||_1 is accumulated in increasing j, as the strided loop of the generic path does.
+//
+// The reference stops on the L1 norm of the WHOLE vector (models.py:643); with |E| in the hundreds and 500
+// points the norm stalls at a few ulp per point above the 1e-10 threshold and the loop runs all 200 iterations although
+// every point settled after ~6.  The iterates are then EXACTLY periodic: a point whose new value equals its current
+// one is a fixed point, one whose new value equals its previous one alternates between two values (a rounding 2-cycle).
+// Once every point of the vector is one or the other (one __syncthreads_and inside the reduction's barrier), every
+// later iteration repeats the same partial sums, hence the same norm: the loop can never stop before max_itr, and the
+// vector after iteration 199 is known -- fixed points as they are, 2-cycle points by the parity of the remaining
+// count.  Bitwise the result of running the remaining iterations (NaN never compares equal, so those vectors still
+// iterate to the end; so do vectors with a longer rounding cycle).
 template <int PPT>
 __device__ __forceinline__ void kepler_newton_regs(int N, const double* __restrict__ t, double P, double ecc, double t0,
                                                    double* E, double* kep_red) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const double two_pi = 2.0 * MRV_PI;
-  double M[PPT], E0[PPT];
+  double M[PPT], E0[PPT], Ep[PPT];
 #pragma unroll
   for (int j = 0; j < PPT; ++j) {
     const int i = tid + j * nt;
     M[j] = i < N ? __ddiv_rn(__dmul_rn(two_pi, __dsub_rn(t[i], t0)), P) : 0.0;
     E0[j] = M[j];
+    Ep[j] = __longlong_as_double(0x7ff8000000000000ll);   // no previous iterate yet
   }
   for (int it = 0; it < 200; ++it) {
     double part = 0.0;
+    int periodic = 1;
+    unsigned cyc = 0;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       if (tid + j * nt < N) {
@@ -70,11 +101,26 @@ __device__ __forceinline__ void kepler_newton_regs(int N, const double* __restri
         const double fp = __dsub_rn(1.0, __dmul_rn(ecc, c));
         const double En = __dsub_rn(E0[j], __ddiv_rn(f, fp));
         part += fabs(__dsub_rn(En, E0[j]));
+        const bool fixed = En == E0[j], two = En == Ep[j];
+        periodic &= (fixed || two) ? 1 : 0;
+        if (two && !fixed) cyc |= 1u << j;
+        Ep[j] = E0[j];
         E0[j] = En;
       }
     }
-    const double l1 = block_sum_1bar(part, kep_red, it & 1);   // whole-vector ||E - E0||_1, models.py:643
+    int all_periodic;
+    const double l1 = block_sum_1bar_and(part, kep_red, it & 1, periodic, &all_periodic);   // whole-vector ||E - E0||_1, models.py:643
     if (l1 <= 1.0e-10) break;                 // NaN compares false -> keeps iterating, as NumPy does
+    if (all_periodic) {
+      // every later iteration reproduces this norm (> 1e-10): the loop runs to it = 199; 2-cycle points end on the
+      // other value when the number of remaining iterations is odd
+      if ((199 - it) & 1) {
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+          if (cyc & (1u << j)) E0[j] = Ep[j];
+      }
+      break;
+    }
   }
 #pragma unroll
   for (int j = 0; j < PPT; ++j)
