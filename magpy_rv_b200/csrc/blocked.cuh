@@ -597,6 +597,183 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same sweep with LOOK-AHEAD, for the dataflow kernel (256 threads, inverse kept, square storage).  In
+// cta_block_sweep the three phases of a block step run one after the other, and the pivot block -- 15 barrier-separated
+// scalar steps, pure latency -- leaves the FP64 pipes idle for a third of the sweep.  Here the trailing update of block
+// step kb is split: first the 16 columns of the NEXT pivot block (all warps), then warps 0-1 sweep that pivot block
+// (64 threads, four elements of a row each, a named barrier of their own) WHILE warps 2-7 update the remaining columns.
+// Every element sees the same operations in the same order as in cta_block_sweep, so the results are bitwise identical.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_sync_pivot64() { asm volatile("bar.sync 1, 64;\n" ::: "memory"); }
+
+// 16 x 16 pivot block at (k0, k0) by threads u = 0..63 (warps 0-1); the caller's __syncthreads follows.
+__device__ __forceinline__ void sweep_pivot_block64(double* S, const int ld, const int k0, double* D, double* wv, const int u) {
+  const int r = u >> 2, c0 = (u & 3) * 4;
+  double v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[e] = S[(size_t)(k0 + c0 + e) * ld + k0 + r];
+    D[r * PB_D_LD + c0 + e] = v[e];
+  }
+  bar_sync_pivot64();
+  for (int j = 0; j < PB_NB - 1; ++j) {
+    {
+      // branch-free over the thread's four elements (divergent per-element branches would run the four load -> multiply ->
+      // fma -> store chains one after the other): all loads first, selects instead of branches, predicated stores
+      const double w = pivot_rcp(D[j * PB_D_LD + j]);
+      const double drj = D[r * PB_D_LD + j];
+      double dcj[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dcj[e] = D[(c0 + e) * PB_D_LD + j];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + e;
+        const bool on = c > j && (r >= c || r <= j);
+        const double beta = dcj[e] * w;
+        const double nv = (r == j) ? -beta : fma(-drj, beta, v[e]);
+        v[e] = on ? nv : v[e];
+        if (on) D[r * PB_D_LD + c] = nv;
+      }
+    }
+    bar_sync_pivot64();
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (r == c0 + e) wv[r] = pivot_rcp(v[e]);
+    S[(size_t)(k0 + c0 + e) * ld + k0 + r] = v[e];     // final block (lower: factor, upper: inverse part)
+  }
+}
+
+// Trailing update of the m16 column tiles tm0 .. tm1 - 1 behind pivot block k0 by NW warps (this warp: index wi).
+template <int NW>
+__device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, const int n_n8, const int k0, const int tm0,
+                                                     const int tm1, const double* PA, const int pa_ld, const double* PB,
+                                                     const int pb_ld, const int wi, const int gq, const int tig) {
+  const int c_begin = k0 + PB_NB;
+  constexpr int SLOTS = (17 + NW - 1) / NW;     // n_n8 <= 17 row tiles (128 rows + the residual row)
+  int rho0s[SLOTS];
+  bool live[SLOTS], pivot[SLOTS];
+  double bfr[SLOTS][4];
+#pragma unroll
+  for (int sl = 0; sl < SLOTS; ++sl) {
+    const int tn = wi + NW * sl;
+    rho0s[sl] = tn * 8;
+    live[sl] = tn < n_n8;
+    pivot[sl] = rho0s[sl] >= k0 && rho0s[sl] < k0 + PB_NB;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) bfr[sl][kk] = live[sl] ? PA[(kk * 4 + tig) * pa_ld + rho0s[sl] + gq] : 0.0;
+  }
+  for (int tm = tm0; tm < tm1; ++tm) {
+    const int c0 = c_begin + tm * 16;
+    double a0[4], a1[4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      a0[kk] = PB[(kk * 4 + tig) * pb_ld + c0 + gq];
+      a1[kk] = PB[(kk * 4 + tig) * pb_ld + c0 + gq + 8];
+    }
+    double acc[SLOTS][4];
+    bool need[SLOTS];
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      need[sl] = live[sl] && (rho0s[sl] < c_begin || rho0s[sl] + 7 >= c0);
+      if (need[sl] && !pivot[sl]) {
+        const double2 u = *reinterpret_cast<const double2*>(S + (size_t)(c0 + gq) * ld + (rho0s[sl] + 2 * tig));
+        const double2 v = *reinterpret_cast<const double2*>(S + (size_t)(c0 + gq + 8) * ld + (rho0s[sl] + 2 * tig));
+        acc[sl][0] = u.x; acc[sl][1] = u.y; acc[sl][2] = v.x; acc[sl][3] = v.y;
+      } else {
+        acc[sl][0] = acc[sl][1] = acc[sl][2] = acc[sl][3] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int sl = 0; sl < SLOTS; ++sl)
+        if (need[sl]) dmma_1684_neg0(acc[sl], a0[kk], a1[kk], bfr[sl][kk]);   // warp-uniform predicate
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+      if (need[sl]) {
+        double2 u, v;
+        u.x = acc[sl][0]; u.y = acc[sl][1]; v.x = acc[sl][2]; v.y = acc[sl][3];
+        *reinterpret_cast<double2*>(S + (size_t)(c0 + gq) * ld + (rho0s[sl] + 2 * tig)) = u;
+        *reinterpret_cast<double2*>(S + (size_t)(c0 + gq + 8) * ld + (rho0s[sl] + 2 * tig)) = v;
+      }
+    }
+  }
+}
+
+__device__ inline void cta_block_sweep_la(double* S, const int ld, int n_cols, double* PA, const int pa_ld, double* PB,
+                                          const int pb_ld, double* D, double* wv, PhaseTimer* ptm = nullptr) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tig = lane & 3;
+  const int n_rows = n_cols + 1;                 // + residual row
+  const int n_rows8 = (n_rows + 7) & ~7;
+  const int n_n8 = n_rows8 / 8;
+  const int nblk = n_cols / PB_NB;
+  if (warp < 2) sweep_pivot_block64(S, ld, 0, D, wv, tid);
+  __syncthreads();
+  if (ptm) ptm->mark(8);
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int k0 = kb * PB_NB;
+    // ---- panel rows on the tensor pipe (all warps; as in cta_block_sweep) ----
+    {
+      double gt0[4], gt1[4];   // G^T fragments: rows j = gq and gq + 8, columns jp = 4 kk + tig
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const int jp = 4 * kk + tig;
+        gt0[kk] = (jp < gq) ? D[jp * PB_D_LD + gq] : (jp == gq ? 1.0 : 0.0);
+        gt1[kk] = (jp < gq + 8) ? D[jp * PB_D_LD + gq + 8] : (jp == gq + 8 ? 1.0 : 0.0);
+      }
+      for (int tn = warp; tn < n_n8; tn += 8) {
+        const int rho0 = tn * 8;
+        const bool pivot_tile = rho0 >= k0 && rho0 < k0 + PB_NB;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (!pivot_tile) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) dmma_1684_neg0(acc, gt0[kk], gt1[kk], S[(size_t)(k0 + 4 * kk + tig) * ld + rho0 + gq]);
+        }
+        const int rhoA = rho0 + 2 * tig;                       // this lane's two rows: rhoA, rhoA + 1
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = gq + 8 * h;
+          double2 x;
+          x.x = acc[2 * h];
+          x.y = acc[2 * h + 1];
+          if (pivot_tile) {
+            const int r0 = rhoA - k0, r1 = r0 + 1;
+            x.x = (j == r0) ? 1.0 : (j > r0 ? D[r0 * PB_D_LD + j] : 0.0);
+            x.y = (j == r1) ? 1.0 : (j > r1 ? D[r1 * PB_D_LD + j] : 0.0);
+          } else {
+            if (rhoA >= n_rows) x.x = 0.0;                     // padding rows below the residual row stay zero
+            if (rhoA + 1 >= n_rows) x.y = 0.0;
+            *reinterpret_cast<double2*>(S + (size_t)(k0 + j) * ld + rhoA) = x;
+          }
+          *reinterpret_cast<double2*>(PA + j * pa_ld + rhoA) = x;
+          if (rhoA < n_cols) {
+            const double w = wv[j];
+            double2 y;
+            y.x = (rhoA >= k0 + PB_NB) ? -x.x * w : 0.0;
+            y.y = (rhoA + 1 >= k0 + PB_NB && rhoA + 1 < n_cols) ? -x.y * w : 0.0;
+            *reinterpret_cast<double2*>(PB + j * pb_ld + rhoA) = y;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    if (ptm) ptm->mark(9);
+    const int n_m16 = (n_cols - (k0 + PB_NB)) / 16;
+    if (n_m16 == 0) break;
+    // ---- trailing update, first the columns of the next pivot block (all warps) ... ----
+    sweep_trailing_tiles<8>(S, ld, n_n8, k0, 0, 1, PA, pa_ld, PB, pb_ld, warp, gq, tig);
+    __syncthreads();
+    // ---- ... then warps 0-1 sweep that pivot block while warps 2-7 update the rest ----
+    if (warp < 2) sweep_pivot_block64(S, ld, k0 + PB_NB, D, wv, tid);
+    else sweep_trailing_tiles<6>(S, ld, n_n8, k0, 1, n_m16, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig);
+    __syncthreads();
+    if (ptm) ptm->mark(10);
+  }
+}
+
 #define POTRF_BLK_THREADS 512
 __global__ void __launch_bounds__(POTRF_BLK_THREADS)
 potrf_tile_blk_kernel(int k, int N, double* __restrict__ Abase, size_t walker_stride, double* __restrict__ resid,

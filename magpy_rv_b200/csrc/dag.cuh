@@ -95,6 +95,9 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 #ifndef DAG_SOLVE_STRIPS
 #define DAG_SOLVE_STRIPS 1    // solve phase in 16 x 128 warp strips (balanced triangular skip) instead of the 2 x 4 warp grid
 #endif
+#ifndef DAG_SWEEP_LOOKAHEAD
+#define DAG_SWEEP_LOOKAHEAD 1   // diagonal-tile sweep with the next pivot block overlapped with the trailing update (blocked.cuh)
+#endif
 #ifndef DAG_PREFETCH
 #define DAG_PREFETCH 0        // 0: dependency loads at the start of a task (measured best); 1: acquire loads during the previous task; 2: relaxed loads + one fence
 #endif
@@ -910,7 +913,11 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         }
         __syncthreads();
         tm.mark(7);
+#if DAG_SWEEP_LOOKAHEAD
+        cta_block_sweep_la(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, Dm, wv, &tm);
+#else
         cta_block_sweep<true, DAG_THREADS / 32>(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, Dm, wv, &tm);
+#endif
 
         double ld_part = 0.0, q_part = 0.0;
         int first_bad = 0x7fffffff, nan_seen = 0;
