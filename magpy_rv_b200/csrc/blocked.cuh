@@ -443,6 +443,49 @@ struct PhaseTimer {
 #endif
 };
 
+__device__ __forceinline__ void bar_sync_pivot64() { asm volatile("bar.sync 1, 64;\n" ::: "memory"); }
+
+// 16 x 16 pivot block at (k0, k0) by threads u = 0..63 (warps 0-1), four elements of a row each, synchronised by a named
+// barrier of their own; the caller's __syncthreads follows.  (One element per thread on 256 threads, as in round 1, costs
+// 1.96 us per block in the dataflow kernel, this form 1.61 us: the barrier spans two warps instead of eight.)
+template <bool PACKED>
+__device__ __forceinline__ void sweep_pivot_block64(double* S, const int ld, const int k0, double* D, double* wv, const int u) {
+  const int r = u >> 2, c0 = (u & 3) * 4;
+  double v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    v[e] = sweep_colp<PACKED>(S, ld, k0 + c0 + e)[k0 + r];
+    D[r * PB_D_LD + c0 + e] = v[e];
+  }
+  bar_sync_pivot64();
+  for (int j = 0; j < PB_NB - 1; ++j) {
+    {
+      // branch-free over the thread's four elements (divergent per-element branches would run the four load -> multiply ->
+      // fma -> store chains one after the other): all loads first, selects instead of branches, predicated stores
+      const double w = pivot_rcp(D[j * PB_D_LD + j]);
+      const double drj = D[r * PB_D_LD + j];
+      double dcj[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dcj[e] = D[(c0 + e) * PB_D_LD + j];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = c0 + e;
+        const bool on = c > j && (r >= c || r <= j);
+        const double beta = dcj[e] * w;
+        const double nv = (r == j) ? -beta : fma(-drj, beta, v[e]);
+        v[e] = on ? nv : v[e];
+        if (on) D[r * PB_D_LD + c] = nv;
+      }
+    }
+    bar_sync_pivot64();
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    if (r == c0 + e) wv[r] = pivot_rcp(v[e]);
+    sweep_colp<PACKED>(S, ld, k0 + c0 + e)[k0 + r] = v[e];     // final block (lower: factor, upper: inverse part)
+  }
+}
+
 template <bool WITH_INV, int NWARPS, bool PACKED = false>
 __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, double* PA, const int pa_ld, double* PB,
                                        const int pb_ld, double* D, double* wv, PhaseTimer* ptm = nullptr) {
@@ -453,7 +496,8 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
   const int nblk = n_cols / PB_NB;
   for (int kb = 0; kb < nblk; ++kb) {
     const int k0 = kb * PB_NB;
-    // ---- 1. pivot block -------------------------------------------------------------------
+    // ---- 1. pivot block (warps 0-1; everybody else waits at the barrier) ------------------------
+#ifdef SWEEP_PIVOT_256
     {
       const bool in_blk = tid < PB_NB * PB_NB;           // one thread per pivot-block element
       const int r = (tid >> 4) & 15, c = tid & 15;
@@ -463,8 +507,6 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
         D[r * PB_D_LD + c] = v;
       }
       __syncthreads();
-      // (every thread divides by the pivot itself: letting the owner of element (j + 1, j + 1) compute the reciprocal
-      // once and publish it measured 7 % SLOWER -- the division then sits between the update and the barrier)
       for (int j = 0; j < PB_NB - 1; ++j) {
         if (in_blk && c > j && (r >= c || r <= j)) {
           const double w = pivot_rcp(D[j * PB_D_LD + j]);
@@ -481,6 +523,10 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
       }
       __syncthreads();
     }
+#else
+    if (warp < 2) sweep_pivot_block64<PACKED>(S, ld, k0, D, wv, tid);
+    __syncthreads();
+#endif
     if (ptm) ptm->mark(8);
     // ---- 2. panel rows on the tensor pipe ------------------------------------------------------
     // A row's 16 panel entries x solve x U = a, U unit upper triangular with the block's multipliers; the swept pivot
@@ -605,46 +651,6 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
 // (64 threads, four elements of a row each, a named barrier of their own) WHILE warps 2-7 update the remaining columns.
 // Every element sees the same operations in the same order as in cta_block_sweep, so the results are bitwise identical.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bar_sync_pivot64() { asm volatile("bar.sync 1, 64;\n" ::: "memory"); }
-
-// 16 x 16 pivot block at (k0, k0) by threads u = 0..63 (warps 0-1); the caller's __syncthreads follows.
-__device__ __forceinline__ void sweep_pivot_block64(double* S, const int ld, const int k0, double* D, double* wv, const int u) {
-  const int r = u >> 2, c0 = (u & 3) * 4;
-  double v[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    v[e] = S[(size_t)(k0 + c0 + e) * ld + k0 + r];
-    D[r * PB_D_LD + c0 + e] = v[e];
-  }
-  bar_sync_pivot64();
-  for (int j = 0; j < PB_NB - 1; ++j) {
-    {
-      // branch-free over the thread's four elements (divergent per-element branches would run the four load -> multiply ->
-      // fma -> store chains one after the other): all loads first, selects instead of branches, predicated stores
-      const double w = pivot_rcp(D[j * PB_D_LD + j]);
-      const double drj = D[r * PB_D_LD + j];
-      double dcj[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) dcj[e] = D[(c0 + e) * PB_D_LD + j];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int c = c0 + e;
-        const bool on = c > j && (r >= c || r <= j);
-        const double beta = dcj[e] * w;
-        const double nv = (r == j) ? -beta : fma(-drj, beta, v[e]);
-        v[e] = on ? nv : v[e];
-        if (on) D[r * PB_D_LD + c] = nv;
-      }
-    }
-    bar_sync_pivot64();
-  }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    if (r == c0 + e) wv[r] = pivot_rcp(v[e]);
-    S[(size_t)(k0 + c0 + e) * ld + k0 + r] = v[e];     // final block (lower: factor, upper: inverse part)
-  }
-}
-
 // Trailing update of the m16 column tiles tm0 .. tm1 - 1 behind pivot block k0 by NW warps (this warp: index wi).
 template <int NW>
 __device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, const int n_n8, const int k0, const int tm0,
@@ -710,7 +716,7 @@ __device__ inline void cta_block_sweep_la(double* S, const int ld, int n_cols, d
   const int n_rows8 = (n_rows + 7) & ~7;
   const int n_n8 = n_rows8 / 8;
   const int nblk = n_cols / PB_NB;
-  if (warp < 2) sweep_pivot_block64(S, ld, 0, D, wv, tid);
+  if (warp < 2) sweep_pivot_block64<false>(S, ld, 0, D, wv, tid);
   __syncthreads();
   if (ptm) ptm->mark(8);
   for (int kb = 0; kb < nblk; ++kb) {
@@ -767,7 +773,7 @@ __device__ inline void cta_block_sweep_la(double* S, const int ld, int n_cols, d
     sweep_trailing_tiles<8>(S, ld, n_n8, k0, 0, 1, PA, pa_ld, PB, pb_ld, warp, gq, tig);
     __syncthreads();
     // ---- ... then warps 0-1 sweep that pivot block while warps 2-7 update the rest ----
-    if (warp < 2) sweep_pivot_block64(S, ld, k0 + PB_NB, D, wv, tid);
+    if (warp < 2) sweep_pivot_block64<false>(S, ld, k0 + PB_NB, D, wv, tid);
     else sweep_trailing_tiles<6>(S, ld, n_n8, k0, 1, n_m16, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig);
     __syncthreads();
     if (ptm) ptm->mark(10);
