@@ -82,12 +82,6 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
 // experiment switches (tools/build_variant.py): defaults are the measured best
 #ifndef DAG_DIAG_MAP
 #define DAG_DIAG_MAP 3        // 0: diagonal tiles updated in full; 1: (4,4,4,2 | 1,1,1,3) fragment rows per warp; 2: (3,3,3,3 | 2,2,2,2); 3: 9 fragments per warp
@@ -97,9 +91,6 @@ __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_re
 #endif
 #ifndef DAG_SWEEP_LOOKAHEAD
 #define DAG_SWEEP_LOOKAHEAD 1   // diagonal-tile sweep with the next pivot block overlapped with the trailing update (blocked.cuh)
-#endif
-#ifndef DAG_PREFETCH
-#define DAG_PREFETCH 0        // 0: dependency loads at the start of a task (measured best); 1: acquire loads during the previous task; 2: relaxed loads + one fence
 #endif
 #ifdef DAG_KEEP_THREADFENCE
 #define DAG_PRE_RELEASE_FENCE() __threadfence()
@@ -514,11 +505,6 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
     }
   };
 
-  // Dependency state of the NEXT task, sampled by thread 0 while the current task computes (the counters only grow, so
-  // "ready" stays true; the acquire loads are ordered before the bulk copies of the next task by program order and the
-  // proxy fence at its start).  In the common case a task then starts without a single global-memory round trip.
-  int pre_tsk = -1, pre_v1 = 0, pre_v2 = 0, pre_abort = 0;
-
   int next_tsk = 0x7fffffff;
   if (tid == 0) {
     if (ld_acquire_gpu(abort_flag) == 0) next_tsk = atomicAdd(g.counter, 1);
@@ -527,38 +513,45 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
 
   for (;;) {
     // ---- next task ---------------------------------------------------------------------------
-    if (tid == 0) {
+    if (warp == 0) {
+      // The three dependency words of the task (abort flag, progress of tile rows i and k) are acquired by three LANES in
+      // one instruction -- one L2 round trip instead of three back to back (an acquire load completes before the next
+      // one issues) -- and handed to lane 0 through the warp barrier of the shuffles.
+      const int tsk = __shfl_sync(0xffffffffu, next_tsk, 0);
       int type = DAG_TASK_EXIT, b = 0, i = 0, k = 0, diag_ready = 0;
-      const int tsk = next_tsk;
-      next_tsk = atomicAdd(g.counter, 1);   // the task after this one: its round trip overlaps with this task
-      if (tsk < g.total_tasks) {
-        if ((pre_tsk == tsk ? pre_abort : ld_acquire_gpu(abort_flag)) == 0) {
-          dag_decode(g, tsk, type, b, i, k);
-          // update operands: rows i and k finished through column k - 1 (also orders the residual block r_i / r_k)
-          const int* rd = g.rowdone + (size_t)b * g.nt;
-          int v1 = pre_v1, v2 = pre_v2;
-          if (pre_tsk != tsk || v1 < k || v2 < k) {
-            v1 = ld_acquire_gpu(rd + i);
-            v2 = ld_acquire_gpu(rd + k);
-          } else if (DAG_PREFETCH == 2) {
-            fence_acq_rel_gpu();           // the sampled values were relaxed loads: relaxed load + fence = acquire
-          }
-          if (v1 < k || v2 < k) {
-            flush_release();
-            if (!(dag_wait(rd + i, k, abort_flag) && dag_wait(rd + k, k, abort_flag))) type = DAG_TASK_EXIT;
-          }
-          diag_ready = (type == DAG_TASK_OFF && v2 >= k + 1) ? 1 : 0;
-          fence_proxy_async();
-        }
-        // this task's points were requested during the previous one: never leave with a bulk copy in flight
-        if (type == DAG_TASK_EXIT) mbar_wait(&pt_bar[n_local & 1], (n_local >> 1) & 1);
+      int dep = 0;
+      const bool live = tsk < g.total_tasks;
+      if (live) {
+        dag_decode(g, tsk, type, b, i, k);
+        const int* rd = g.rowdone + (size_t)b * g.nt;
+        if (lane < 3) dep = ld_acquire_gpu(lane == 0 ? abort_flag : (lane == 1 ? rd + i : rd + k));
       }
-      if (type == DAG_TASK_EXIT) flush_release();
-      s_task[0] = type;
-      s_task[1] = b;
-      s_task[2] = i;
-      s_task[3] = k;
-      s_task[4] = diag_ready;
+      __syncwarp();
+      const int aborted = __shfl_sync(0xffffffffu, dep, 0), v1 = __shfl_sync(0xffffffffu, dep, 1), v2 = __shfl_sync(0xffffffffu, dep, 2);
+      if (lane == 0) {
+        next_tsk = atomicAdd(g.counter, 1);   // the task after this one: its round trip overlaps with this task
+        if (live) {
+          if (aborted != 0) type = DAG_TASK_EXIT;
+          else {
+            // update operands: rows i and k finished through column k - 1 (also orders the residual block r_i / r_k)
+            const int* rd = g.rowdone + (size_t)b * g.nt;
+            if (v1 < k || v2 < k) {
+              flush_release();
+              if (!(dag_wait(rd + i, k, abort_flag) && dag_wait(rd + k, k, abort_flag))) type = DAG_TASK_EXIT;
+            }
+            diag_ready = (type == DAG_TASK_OFF && v2 >= k + 1) ? 1 : 0;
+            fence_proxy_async();
+          }
+          // this task's points were requested during the previous one: never leave with a bulk copy in flight
+          if (type == DAG_TASK_EXIT) mbar_wait(&pt_bar[n_local & 1], (n_local >> 1) & 1);
+        }
+        if (type == DAG_TASK_EXIT) flush_release();
+        s_task[0] = type;
+        s_task[1] = b;
+        s_task[2] = i;
+        s_task[3] = k;
+        s_task[4] = diag_ready;
+      }
     }
     __syncthreads();
     const int type = s_task[0], b = s_task[1], ti = s_task[2], tk = s_task[3];
@@ -689,23 +682,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
       // the next task's points: its index has long arrived, the other buffer was last read a task ago
       if (tid == 0) {
         flush_release();
-        if (next_tsk < g.total_tasks) {
-          issue_points(next_tsk, (n_local + 1) & 1);
-          int ntype, nb, ni, nk;
-          dag_decode(g, next_tsk, ntype, nb, ni, nk);
-          const int* nrd = g.rowdone + (size_t)nb * g.nt;
-#if DAG_PREFETCH == 1
-          pre_tsk = next_tsk;
-          pre_v1 = ld_acquire_gpu(nrd + ni);   // land while the update loop runs
-          pre_v2 = ld_acquire_gpu(nrd + nk);
-          pre_abort = ld_acquire_gpu(abort_flag);
-#elif DAG_PREFETCH == 2
-          pre_tsk = next_tsk;
-          pre_v1 = ld_relaxed_gpu(nrd + ni);   // three loads in flight, nobody waits for them here
-          pre_v2 = ld_relaxed_gpu(nrd + nk);
-          pre_abort = ld_relaxed_gpu(abort_flag);
-#endif
-        }
+        if (next_tsk < g.total_tasks) issue_points(next_tsk, (n_local + 1) & 1);
       }
       tm.mark(1);
     }
