@@ -403,7 +403,13 @@ static int choose_path(const mrv_problem* p, int64_t W = 0) {
   if (p->path_opt == MRV_PATH_MID) return MRV_PATH_MID;
   // measured crossovers (profiles/README.md): fused shared-memory kernels up to 144 points, the
   // one-CTA-per-walker streamed-panel kernel up to 512, the tiled wave factorisation above
-  if (p->desc.N <= MRV_SMALL_BLK_N_MAX) return MRV_PATH_FUSED_SMEM;
+  if (p->desc.N <= MRV_SMALL_BLK_N_MAX) {
+    // above 112 points only one fused CTA fits an SM; the streamed-panel kernel keeps two walkers per SM resident and,
+    // with its one-sweep diagonal blocks, is 1.1-1.35x ahead as soon as the ensemble needs more than one round of fused
+    // CTAs (N = 128 x 1024 walkers: 3.09 M against 2.50 M evals/s; up to 148 walkers the fused kernel's latency wins)
+    if (p->desc.N > 112 && W > p->num_sms) return MRV_PATH_MID;
+    return MRV_PATH_FUSED_SMEM;
+  }
   if (p->desc.N > MID_N_MAX) return MRV_PATH_BLOCKED;
   // 320 < N <= 512 (round 2, tools/crossover_probe.py, profiles/r2s_crossover_probe.txt): the tiled path -- the dataflow
   // kernel from 3 tile columns on -- pads N to a multiple of 128, the one-CTA-per-walker kernel runs in rounds of num_sms

@@ -106,15 +106,10 @@ __device__ __forceinline__ void mid_factor16(const MidShared& sh, const double* 
   double* const rhsb = sh.rhsb;
   const double* const rj = sh.rj;
 
-      // Square-root-free right-looking LDL^T in shared memory, then the inverse of the UNIT lower factor, both as lean
-      // rolled loops with ONE __syncwarp per step (explicit pointers with constant offsets; over-reads past column 15
-      // land in the padding columns 16..31 of Dm / in the arrays behind invL and are never stored):
-      //   step k:  w = 1 / d_k,  A[r][c] -= (A[r][k] w) A[c][k]   (c > k, r >= c; column k itself stays unscaled)
-      // The Cholesky form it replaces (round 1) needed the scaled column k back in shared memory before the update --
-      // rsqrt, store, __syncwarp, load -- and its inversion loop multiplied by 1 / L_kk in every step: 32 steps of
-      // ~480 clocks in the kernel (8 us per 16 x 16 block; the tensor warps waited for it at the barriers, ncu: 52 % of
-      // their stall samples).  L = Ltilde D^1/2 and inv(L) = D^-1/2 inv(Ltilde) are formed by two parallel scalings.
-      // Dm[c * 17 + row], c < 32.
+      // History of this routine (each step measured in the kernel): Cholesky + inversion with rsqrt per step, 32 steps of
+      // ~480 clocks (8 us per 16 x 16 block; the tensor warps waited for it at the barriers, ncu: 52 % of their stall
+      // samples); square-root-free LDL^T + inverse of the unit factor, 16 + 15 lean steps; now ONE Gauss-Jordan sweep of
+      // 15 steps (C2 +13 %, N = 160 x 1024 walkers +23 %).  Rolled loops with one __syncwarp per step; Dm[c * 17 + row].
       const int rr = lane & 15, g = lane >> 4;
       {
         const double* src = P + (size_t)((o + 8 * g) >> 2) * CS + 4 * (o + rr);
@@ -123,75 +118,60 @@ __device__ __forceinline__ void mid_factor16(const MidShared& sh, const double* 
         for (int u = 0; u < 8; ++u) dst[u * 17] = src[(size_t)(u >> 2) * CS + (u & 3)];
       }
       __syncwarp();
-      const double* colk = Dm;
+      // ONE square-root-free Gauss-Jordan sweep gives the pivots and the inverse factor together (15 steps with one
+      // __syncwarp each; the LDL^T + inversion pair it replaces needed 16 + 15): step j, with w = 1 / d_j,
+      //     beta = A[c][j] w;   A[j][c] = -beta;   A[r][c] -= A[r][j] beta   for c > j and (r >= c or r < j)
+      // -- rows r >= c carry the factor, rows r < j the (unscaled) inverse, exactly the pivot-block rule of the tiled
+      // path (blocked.cuh).  Afterwards inv(L)[n][k] = A[k][n] / sqrt(d_n) for k < n.  This lane: row rr, columns 8 g ...
+      {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = Dm[(8 * g + u) * 17 + rr];
+        const double* colj = Dm;
 #pragma unroll 1
-      for (int k = 0; k < 16; ++k, colk += 17) {
-        const double dk = colk[k];
-        if (fb == 0x7fffffff && !(dk > 0.0)) {
-          fb = row0 + o + k + 1;
-          fb_nan = isnan(dk) ? 1 : 0;
+        for (int j = 0; j < 15; ++j, colj += 17) {
+          const double dj = colj[j];
+          if (fb == 0x7fffffff && !(dj > 0.0)) {
+            fb = row0 + o + j + 1;
+            fb_nan = isnan(dj) ? 1 : 0;
+          }
+          const double w = pivot_rcp(dj);
+          const double drj = colj[rr];
+          double dcj[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dcj[u] = colj[8 * g + u];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int c = 8 * g + u;
+            const bool on = c > j && (rr >= c || rr <= j);
+            const double beta = dcj[u] * w;
+            const double nv = (rr == j) ? -beta : fma(-drj, beta, v[u]);
+            if (on) {
+              v[u] = nv;
+              Dm[c * 17 + rr] = nv;
+            }
+          }
+          __syncwarp();
         }
-        const double li = colk[rr] * pivot_rcp(dk);    // Ltilde[rr][k]
-        const int cb = k + 1 + 8 * g;                  // first column of this half-warp's batch
-        const double* pl = colk + cb;                  // A[c][k] (unscaled)
-        double* pa = Dm + cb * 17 + rr;                // A[rr][c]
-        const int nst = min(16 - cb, rr - cb + 1);     // store u < nst  <=>  c < 16 && rr >= c
-        double lv[8], av[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          lv[u] = pl[u];
-          av[u] = pa[u * 17];
+        const double d15 = Dm[15 * 17 + 15];
+        if (fb == 0x7fffffff && !(d15 > 0.0)) {
+          fb = row0 + o + 16;
+          fb_nan = isnan(d15) ? 1 : 0;
         }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) av[u] = fma(-li, lv[u], av[u]);
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (u < nst) pa[u * 17] = av[u];
-        __syncwarp();
       }
-      // pivots -> 1 / d, 1 / sqrt(d); unit factor Ltilde[i][c] = A[i][c] / d_c in place (this lane: row rr, columns 8 g ..)
       if (lane < 16) {
         const double d = Dm[lane * 17 + lane];
         dvec[row0 + o + lane] = d;
         rdiag[lane] = rsqrt(d);
-        rhsb[lane] = pivot_rcp(d);                     // (rhsb is free until the z block below)
       }
       __syncwarp();
-      {
-        double* pe = Dm + (8 * g) * 17 + rr;
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (rr > 8 * g + u) pe[u * 17] *= rhsb[8 * g + u];
-      }
-      // inverse of the unit lower factor: column rr per lane (solve Ltilde x = e_rr), rows split between the half-warps
       double* X = invL + o * MID_INV_LD + o;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) X[(8 * g + u) * MID_INV_LD + rr] = (8 * g + u == rr) ? 1.0 : 0.0;
-      __syncwarp();
-      const double* colq = Dm;
-#pragma unroll 1
-      for (int q = 0; q < 15; ++q, colq += 17) {
-        const double xq = X[q * MID_INV_LD + rr];      // final: rows <= q are done
-        const int ib = q + 1 + 8 * g;
-        const double* pl = colq + ib;                  // Ltilde[i][q]
-        double* px = X + ib * MID_INV_LD + rr;         // X[i][rr]
-        const int nst = 16 - ib;
-        double lv[8], xv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          lv[u] = pl[u];
-          xv[u] = px[u * MID_INV_LD];
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) xv[u] = fma(-lv[u], xq, xv[u]);
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (u < nst) px[u * MID_INV_LD] = xv[u];
-        __syncwarp();
+      for (int u = 0; u < 8; ++u) {
+        const int row = 8 * g + u;                     // X[row][rr] = inv(L)[row][rr]
+        const double sc = rdiag[row];
+        X[row * MID_INV_LD + rr] = (rr < row) ? Dm[row * 17 + rr] * sc : (rr == row ? sc : 0.0);
       }
-      // inv(L) = D^-1/2 inv(Ltilde): scale row i by 1 / sqrt(d_i)
-#pragma unroll
-      for (int u = 0; u < 8; ++u) X[(8 * g + u) * MID_INV_LD + rr] *= rdiag[8 * g + u];
       __syncwarp();
 
       // z block: rhs = r_block (second half: minus L_BA z_A), z = inv(L) rhs
