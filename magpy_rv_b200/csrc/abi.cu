@@ -660,7 +660,10 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
       const int fit = (int)((227 * 1024) / (smem + 1024));
       // ... but no tighter than the ensemble needs: a single round of CTAs runs fastest with the loosest cap
       const int rounds = (int)((Wsel + p->num_sms - 1) / p->num_sms);
-      const int minb = p->small_minb_opt > 0 ? p->small_minb_opt : std::max(2, std::min(4, std::min(fit, rounds)));
+      int minb = p->small_minb_opt > 0 ? p->small_minb_opt : std::max(2, std::min(4, std::min(fit, rounds)));
+      // the 4 / 3-CTA variants size their sweep for at most 64 / 80 columns (small_logl.cuh)
+      if (minb >= 4 && sblk_cols(D.N) > 64) minb = 3;
+      if (minb == 3 && sblk_cols(D.N) > 80) minb = 2;
       auto kern = minb >= 4 ? fused_small_blk_kernel<4> : (minb == 3 ? fused_small_blk_kernel<3> : fused_small_blk_kernel<2>);
       kern<<<(unsigned)W, MRV_SMALL_THREADS, smem, st>>>(D, p->d_t, p->d_y, p->d_yerr, p->d_flags, d_hp, d_modpar,
                                                          d_model_given, to_ecc, d_logl, d_status, so);

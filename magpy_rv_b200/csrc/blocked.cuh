@@ -652,12 +652,12 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
 // Every element sees the same operations in the same order as in cta_block_sweep, so the results are bitwise identical.
 // ------------------------------------------------------------------------------------------------
 // Trailing update of the m16 column tiles tm0 .. tm1 - 1 behind pivot block k0 by NW warps (this warp: index wi).
-template <int NW>
+template <int NW, int MAXT, bool WITH_INV, bool PACKED>
 __device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, const int n_n8, const int k0, const int tm0,
                                                      const int tm1, const double* PA, const int pa_ld, const double* PB,
                                                      const int pb_ld, const int wi, const int gq, const int tig) {
   const int c_begin = k0 + PB_NB;
-  constexpr int SLOTS = (17 + NW - 1) / NW;     // n_n8 <= 17 row tiles (128 rows + the residual row)
+  constexpr int SLOTS = (MAXT + NW - 1) / NW;     // n_n8 <= MAXT row tiles (rows + the residual row)
   int rho0s[SLOTS];
   bool live[SLOTS], pivot[SLOTS];
   double bfr[SLOTS][4];
@@ -665,7 +665,7 @@ __device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, co
   for (int sl = 0; sl < SLOTS; ++sl) {
     const int tn = wi + NW * sl;
     rho0s[sl] = tn * 8;
-    live[sl] = tn < n_n8;
+    live[sl] = tn < n_n8 && (WITH_INV || rho0s[sl] + 7 >= c_begin);
     pivot[sl] = rho0s[sl] >= k0 && rho0s[sl] < k0 + PB_NB;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) bfr[sl][kk] = live[sl] ? PA[(kk * 4 + tig) * pa_ld + rho0s[sl] + gq] : 0.0;
@@ -684,8 +684,8 @@ __device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, co
     for (int sl = 0; sl < SLOTS; ++sl) {
       need[sl] = live[sl] && (rho0s[sl] < c_begin || rho0s[sl] + 7 >= c0);
       if (need[sl] && !pivot[sl]) {
-        const double2 u = *reinterpret_cast<const double2*>(S + (size_t)(c0 + gq) * ld + (rho0s[sl] + 2 * tig));
-        const double2 v = *reinterpret_cast<const double2*>(S + (size_t)(c0 + gq + 8) * ld + (rho0s[sl] + 2 * tig));
+        const double2 u = *reinterpret_cast<const double2*>(sweep_colp<PACKED>(S, ld, c0 + gq) + (rho0s[sl] + 2 * tig));
+        const double2 v = *reinterpret_cast<const double2*>(sweep_colp<PACKED>(S, ld, c0 + gq + 8) + (rho0s[sl] + 2 * tig));
         acc[sl][0] = u.x; acc[sl][1] = u.y; acc[sl][2] = v.x; acc[sl][3] = v.y;
       } else {
         acc[sl][0] = acc[sl][1] = acc[sl][2] = acc[sl][3] = 0.0;
@@ -701,13 +701,14 @@ __device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, co
       if (need[sl]) {
         double2 u, v;
         u.x = acc[sl][0]; u.y = acc[sl][1]; v.x = acc[sl][2]; v.y = acc[sl][3];
-        *reinterpret_cast<double2*>(S + (size_t)(c0 + gq) * ld + (rho0s[sl] + 2 * tig)) = u;
-        *reinterpret_cast<double2*>(S + (size_t)(c0 + gq + 8) * ld + (rho0s[sl] + 2 * tig)) = v;
+        *reinterpret_cast<double2*>(sweep_colp<PACKED>(S, ld, c0 + gq) + (rho0s[sl] + 2 * tig)) = u;
+        *reinterpret_cast<double2*>(sweep_colp<PACKED>(S, ld, c0 + gq + 8) + (rho0s[sl] + 2 * tig)) = v;
       }
     }
   }
 }
 
+template <bool WITH_INV = true, bool PACKED = false, int MAXT = 17>
 __device__ inline void cta_block_sweep_la(double* S, const int ld, int n_cols, double* PA, const int pa_ld, double* PB,
                                           const int pb_ld, double* D, double* wv, PhaseTimer* ptm = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -716,7 +717,7 @@ __device__ inline void cta_block_sweep_la(double* S, const int ld, int n_cols, d
   const int n_rows8 = (n_rows + 7) & ~7;
   const int n_n8 = n_rows8 / 8;
   const int nblk = n_cols / PB_NB;
-  if (warp < 2) sweep_pivot_block64<false>(S, ld, 0, D, wv, tid);
+  if (warp < 2) sweep_pivot_block64<PACKED>(S, ld, 0, D, wv, tid);
   __syncthreads();
   if (ptm) ptm->mark(8);
   for (int kb = 0; kb < nblk; ++kb) {
@@ -733,10 +734,11 @@ __device__ inline void cta_block_sweep_la(double* S, const int ld, int n_cols, d
       for (int tn = warp; tn < n_n8; tn += 8) {
         const int rho0 = tn * 8;
         const bool pivot_tile = rho0 >= k0 && rho0 < k0 + PB_NB;
+        const bool compute = !pivot_tile && (WITH_INV || rho0 >= k0);   // rows above the pivot block: inverse rows (kept only WITH_INV)
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        if (!pivot_tile) {
+        if (compute) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) dmma_1684_neg0(acc, gt0[kk], gt1[kk], S[(size_t)(k0 + 4 * kk + tig) * ld + rho0 + gq]);
+          for (int kk = 0; kk < 4; ++kk) dmma_1684_neg0(acc, gt0[kk], gt1[kk], sweep_colp<PACKED>(S, ld, k0 + 4 * kk + tig)[rho0 + gq]);
         }
         const int rhoA = rho0 + 2 * tig;                       // this lane's two rows: rhoA, rhoA + 1
 #pragma unroll
@@ -749,10 +751,10 @@ __device__ inline void cta_block_sweep_la(double* S, const int ld, int n_cols, d
             const int r0 = rhoA - k0, r1 = r0 + 1;
             x.x = (j == r0) ? 1.0 : (j > r0 ? D[r0 * PB_D_LD + j] : 0.0);
             x.y = (j == r1) ? 1.0 : (j > r1 ? D[r1 * PB_D_LD + j] : 0.0);
-          } else {
+          } else if (compute) {
             if (rhoA >= n_rows) x.x = 0.0;                     // padding rows below the residual row stay zero
             if (rhoA + 1 >= n_rows) x.y = 0.0;
-            *reinterpret_cast<double2*>(S + (size_t)(k0 + j) * ld + rhoA) = x;
+            *reinterpret_cast<double2*>(sweep_colp<PACKED>(S, ld, k0 + j) + rhoA) = x;
           }
           *reinterpret_cast<double2*>(PA + j * pa_ld + rhoA) = x;
           if (rhoA < n_cols) {
@@ -770,11 +772,11 @@ __device__ inline void cta_block_sweep_la(double* S, const int ld, int n_cols, d
     const int n_m16 = (n_cols - (k0 + PB_NB)) / 16;
     if (n_m16 == 0) break;
     // ---- trailing update, first the columns of the next pivot block (all warps) ... ----
-    sweep_trailing_tiles<8>(S, ld, n_n8, k0, 0, 1, PA, pa_ld, PB, pb_ld, warp, gq, tig);
+    sweep_trailing_tiles<8, MAXT, WITH_INV, PACKED>(S, ld, n_n8, k0, 0, 1, PA, pa_ld, PB, pb_ld, warp, gq, tig);
     __syncthreads();
     // ---- ... then warps 0-1 sweep that pivot block while warps 2-7 update the rest ----
-    if (warp < 2) sweep_pivot_block64<false>(S, ld, k0 + PB_NB, D, wv, tid);
-    else sweep_trailing_tiles<6>(S, ld, n_n8, k0, 1, n_m16, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig);
+    if (warp < 2) sweep_pivot_block64<PACKED>(S, ld, k0 + PB_NB, D, wv, tid);
+    else sweep_trailing_tiles<6, MAXT, WITH_INV, PACKED>(S, ld, n_n8, k0, 1, n_m16, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig);
     __syncthreads();
     if (ptm) ptm->mark(10);
   }

@@ -246,7 +246,13 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
     }
   }
   __syncthreads();
+#ifdef SMALL_SWEEP_NO_LOOKAHEAD
   cta_block_sweep<false, MRV_SMALL_THREADS / 32, true>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
+#else
+  // look-ahead form (blocked.cuh).  Row tiles of 8: the MINB = 4 / 3 variants are only launched when 4 / 3 CTAs fit an SM,
+  // i.e. N <= 64 / 80 (9 / 11 row tiles incl. the residual row); N <= 144: 19
+  cta_block_sweep_la<false, true, (MINB >= 4 ? 9 : (MINB == 3 ? 11 : 19))>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
+#endif
 
   double ld_part = 0.0, q_part = 0.0;
   int first_bad = 0x7fffffff;
