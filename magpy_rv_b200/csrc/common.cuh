@@ -216,8 +216,8 @@ __device__ __forceinline__ void cov_from_dist_n(const CovParams& p, const double
 // samples of the dataflow kernel, reason "wait"; generation 9.6 us per 128 x 128 tile against ~3 us of FP64 issue time).
 // Range reduction by ln 2 (hi / lo), degree-11 polynomial (Chebyshev interpolant of exp on |r| <= ln 2 / 2, relative
 // truncation error 4.2e-18; measured against expl: <= 1.5e-16 relative over [-700, 1]), scaling by 2^t built in the
-// exponent field.  Arguments are clamped to [-700, 700]: the result below 1e-304 is not flushed to zero, and +700
-// is only reachable with negative time scales (whose covariance is not positive definite either way); NaN passes through.
+// exponent field.  Arguments below -700 are clamped (the result below 1e-304 is not flushed to zero); above +709 the result
+// is inf (only reachable with negative time scales, whose covariance is not positive definite either way); NaN passes through.
 template <int NV>
 __device__ __forceinline__ void exp_lockstep(double (&x)[NV]) {
   const double MAGIC = 6755399441055744.0;   // 1.5 * 2^52: the rounded integer sits in the low word
@@ -226,11 +226,11 @@ __device__ __forceinline__ void exp_lockstep(double (&x)[NV]) {
 #pragma unroll
   for (int e = 0; e < NV; ++e) x[e] = (x[e] < -700.0) ? -700.0 : x[e];
 #pragma unroll
-  for (int e = 0; e < NV; ++e) x[e] = (x[e] > 700.0) ? 700.0 : x[e];
-#pragma unroll
   for (int e = 0; e < NV; ++e) t[e] = fma(x[e], 1.4426950408889634074, MAGIC);
+  // large positive arguments: the power of two is capped at 2^1024 = inf in the exponent field (an integer min on the ALU
+  // pipe instead of a second FP64 compare + select per value; the reduced argument stays exact far beyond 700)
 #pragma unroll
-  for (int e = 0; e < NV; ++e) ti[e] = __double2loint(t[e]);
+  for (int e = 0; e < NV; ++e) ti[e] = min(__double2loint(t[e]), 1024);
 #pragma unroll
   for (int e = 0; e < NV; ++e) t[e] -= MAGIC;
 #pragma unroll
@@ -276,19 +276,22 @@ __device__ __forceinline__ void cov_pair_n(const CovParams& p, const double (&ti
         arg[e] = p.c1 * (dt * dt);
       }
       break;
-    case 2:
+    case 2: {
+      const double h = -0.5 * p.c1;   // c1 sin^2(pi d / per) = c1 (1 - cos) / 2 = h cos - h, one fma
 #pragma unroll
-      for (int e = 0; e < NV; ++e) arg[e] = p.c1 * fma(-0.5, fma(ci[e], cj[e], si[e] * sj[e]), 0.5);
+      for (int e = 0; e < NV; ++e) arg[e] = fma(h, fma(ci[e], cj[e], si[e] * sj[e]), -h);
       break;
+    }
     case 3:
-    case 4:
+    case 4: {
+      const double h = -0.5 * p.c3;   // c3 sin^2(pi d / per) = h cos(2 pi d / per) - h
 #pragma unroll
       for (int e = 0; e < NV; ++e) {
         const double dt = ti[e] - tj[e];
-        const double s2 = fma(-0.5, fma(ci[e], cj[e], si[e] * sj[e]), 0.5);
-        arg[e] = fma(p.c1, dt * dt, p.c3 * s2);
+        arg[e] = fma(p.c1, dt * dt, fma(h, fma(ci[e], cj[e], si[e] * sj[e]), -h));
       }
       break;
+    }
     case 5:
     case 6:
     case 7:
