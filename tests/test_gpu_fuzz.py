@@ -78,3 +78,31 @@ def test_random_configuration_matches_oracle(N):
         assert np.array_equal(np.isfinite(g), finite), (g, want)
         err = np.max(np.abs(g[finite] - want[finite]) / np.abs(want[finite])) if finite.any() else 0.0
         assert err < 1e-9, (N, c["kernel"], c["model_list"], err, g, want)
+
+
+@pytest.mark.gpu
+def test_dataflow_kernel_on_random_configurations_is_bitwise_the_launch_per_column_path():
+    """Random kernels / mean models / priors / sizes (3 ... 9 tile columns) and ensembles around the number of SMs, with a
+    non-positive-definite walker mixed in: the dataflow kernel (lower-triangle diagonal updates, strip solve, look-ahead
+    sweep, deferred release) must reproduce the launch-per-column loop bit for bit, status words included, and must do so
+    on every repetition (its task-to-SM assignment changes from run to run)."""
+    rng = np.random.default_rng(2024)
+    for k in range(10):
+        N = int(rng.integers(257, 1100))
+        c = random_case(rng, N)
+        W = int(rng.choice([2, 37, 149, 300]))
+        reps = (W + c["W"] - 1) // c["W"]
+        hp = np.tile(c["hp"], (reps, 1))[:W] * (1 + 1e-3 * rng.standard_normal((W, c["hp"].shape[1])))
+        if k % 3 == 0:
+            hp[W // 2] *= -1.0
+        mp = np.tile(c["modpar"], (reps, 1))[:W]
+        prob = engine.LikelihoodProblem(c["t"], c["y"], c["yerr"], c["kernel"], c["model_list"], c["priors"], flags=c["flags"])
+        prob.set_option("path", 2)
+        prob.set_option("tiled_impl", 1)
+        want, st_want = prob.logl(hp, mp)
+        prob.set_option("tiled_impl", 2)
+        for _ in range(2):
+            got, st = prob.logl(hp, mp)
+            np.testing.assert_array_equal(st, st_want)
+            np.testing.assert_array_equal(got, want)
+        prob.close()

@@ -335,7 +335,8 @@ def test_non_default_kernel_variants_match_goldens():
             prob.close()
 
 
-@pytest.mark.parametrize("name,N,W", [("C5", 700, 40), ("C3", 500, 300), ("C4", 1300, 9), ("C5", 2100, 5), ("C4M", 1024, 3)])
+@pytest.mark.parametrize("name,N,W", [("C5", 700, 40), ("C3", 500, 300), ("C4", 1300, 9), ("C5", 2100, 5), ("C4M", 1024, 3),
+                                      ("C5", 384, 200), ("C2", 330, 160)])
 def test_dataflow_kernel_is_bitwise_the_launch_per_column_path(name, N, W):
     """The persistent dataflow kernel (csrc/dag.cuh, tiled_impl = 2) sums every element in the order of the
     launch-per-column loop (tiled_impl = 1): log L and status must be bitwise identical, for ensembles larger and smaller

@@ -11,7 +11,7 @@ from magpy_rv_b200 import engine
 # MRV_PATHS=1,3: fused shared-memory kernel against the streamed-panel kernel (N <= 144 ... 168)
 PA, PBp = (int(x) for x in os.environ.get("MRV_PATHS", "2,3").split(","))
 Ns = [int(a) for a in sys.argv[1:]] or [256, 288, 320, 352, 384, 416, 448, 480, 512]
-Ws = [100, 148, 256, 512, 1024]
+Ws = [int(x) for x in os.environ.get("MRV_WS", "100,148,256,512,1024").split(",")]
 print("evals/s: path %d | path %d | chosen automatically   (1 fused, 2 tiled, 3 streamed panel)" % (PA, PBp))
 for N in Ns:
     row = []
