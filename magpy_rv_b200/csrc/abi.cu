@@ -1643,6 +1643,19 @@ extern "C" int64_t mrv_get_info(mrv_problem* p, const char* key) {
     }
     return (int64_t)v[i];
   }
+  if (!strncmp(key, "small_t", 7)) {   // phase timers of the fused small-N kernel (only with -DSMALL_TIMING); index 8 resets
+    long long v[8];
+    cudaSetDevice(p->device);
+    if (cudaMemcpyFromSymbol(v, g_small_timing, sizeof v) != cudaSuccess) return -1;
+    const int i = atoi(key + 7);
+    if (i < 0 || i > 8) return -1;
+    if (i == 8) {
+      memset(v, 0, sizeof v);
+      cudaMemcpyToSymbol(g_small_timing, v, sizeof v);
+      return 0;
+    }
+    return v[i];
+  }
   if (!strncmp(key, "mid_t", 5)) {   // phase timers of the streamed-panel kernel (only with -DMID_TIMING); reading resets
     long long v[32];
     cudaSetDevice(p->device);

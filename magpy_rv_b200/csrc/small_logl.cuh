@@ -145,6 +145,20 @@ __host__ inline size_t small_blk_smem_bytes(int N) {
           MRV_MAX_MODPAR + MRV_MAX_HP + 40) * sizeof(double);
 }
 
+// -DSMALL_TIMING: clock64 per phase of CTA 0, thread 0 (tools/small_timing.py): 0 prologue + mean model + residual,
+// 1 fill + phase table, 2 covariance generation, 3 sweep, 4 log det / priors / output
+__device__ long long g_small_timing[8];
+#ifdef SMALL_TIMING
+#define SMALL_MARK(i)                                             \
+  if (blockIdx.x == 0 && threadIdx.x == 0) {                      \
+    const long long now_ = clock64();                             \
+    g_small_timing[i] += now_ - tmark_;                           \
+    tmark_ = now_;                                                \
+  }
+#else
+#define SMALL_MARK(i)
+#endif
+
 // MINB = resident CTAs per SM the register cap is set for (packed factor storage: 2 CTAs fit up to N = 112,
 // 3 up to N = 80, 4 up to N = 64; the caps cost 24..60 bytes of spills)
 template <int MINB>
@@ -169,6 +183,9 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   int* ired = (int*)(red + 32);              // 32 ints
   const int w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+#ifdef SMALL_TIMING
+  long long tmark_ = clock64();
+#endif
 
   if (tid == 0) {
     for (int i = 0; i < D.nh; ++i) hpv[i] = hp_all[(size_t)w * D.nh + i];
@@ -192,6 +209,7 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   }
   __syncthreads();
 
+  SMALL_MARK(0)
   // (a) everything that is not a real lower-triangle entry: zeros, identity padding, residual row
   for (int c = warp; c < nc; c += nwarps) {
     double* col = sweep_colp<true>(S, ld, c);
@@ -212,6 +230,7 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   // zero-lag value + jitter once per walker: K_ii = (k(0) + jit^2) + yerr_i^2, the order of cov_diag().  Inside
   // the `(i == c) ? cov_diag(...) : ev` selects the compiler evaluated k(0) -- a full exp / sin -- per element.
   const double kdiag0 = cov_from_dist(cp, 0.0, 0.0) + cp.jit2;
+  SMALL_MARK(1)
   const int npairs = (N + 1) / 2;
   for (int pc = warp; pc < npairs; pc += nwarps) {
     const int cA = pc, cB = N - 1 - pc;
@@ -246,6 +265,7 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
     }
   }
   __syncthreads();
+  SMALL_MARK(2)
 #ifdef SMALL_SWEEP_NO_LOOKAHEAD
   cta_block_sweep<false, MRV_SMALL_THREADS / 32, true>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
 #else
@@ -254,6 +274,7 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   cta_block_sweep_la<false, true, (MINB >= 4 ? 9 : (MINB == 3 ? 11 : 19))>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
 #endif
 
+  SMALL_MARK(3)
   double ld_part = 0.0, q_part = 0.0;
   int first_bad = 0x7fffffff;
   for (int j = tid; j < N; j += nt) {
@@ -279,4 +300,5 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
     logl_out[w] = v;
     status_out[w] = st;
   }
+  SMALL_MARK(4)
 }
