@@ -232,35 +232,38 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   const double kdiag0 = cov_from_dist(cp, 0.0, 0.0) + cp.jit2;
   SMALL_MARK(1)
   const int npairs = (N + 1) / 2;
+  // four entries per lane and trip through the branch-free lock-step exp: with at most 16 warps per SM the library exp
+  // (one rare-path branch per call, so its evaluations cannot interleave) left the generation latency-bound
+  constexpr int GNV = MINB >= 4 ? 2 : 4;   // (the 64-register variant spills with four)
   for (int pc = warp; pc < npairs; pc += nwarps) {
     const int cA = pc, cB = N - 1 - pc;
     const int lenA = N - cA;
     const int total = (cA == cB) ? lenA : (N + 1);
-    for (int v0 = lane; v0 < total; v0 += 64) {
-      const int v1 = v0 + 32;
-      const bool ok1 = v1 < total;
-      const int c0 = (v0 < lenA) ? cA : cB, i0 = (v0 < lenA) ? cA + v0 : cB + (v0 - lenA);
-      const int c1 = (!ok1 || v1 < lenA) ? cA : cB;
-      const int i1 = !ok1 ? cA : ((v1 < lenA) ? cA + v1 : cB + (v1 - lenA));
-      // both evaluations through one switch so their exp chains interleave (ILP 2)
-      const double pti[2] = {ts[i0], ts[i1]}, pci[2] = {ts[N + i0], ts[N + i1]}, psi[2] = {ts[2 * N + i0], ts[2 * N + i1]};
-      const double ptj[2] = {ts[c0], ts[c1]}, pcj[2] = {ts[N + c0], ts[N + c1]}, psj[2] = {ts[2 * N + c0], ts[2 * N + c1]};
-      double ev[2];
-      cov_pair_n<2>(cp, pti, pci, psi, ptj, pcj, psj, ev);
-      double e0 = ev[0], e1 = ev[1];
-      if (i0 == c0) {
-        const double ye = yerr[i0];
-        e0 = kdiag0 + ye * ye;
+    for (int v0 = lane; v0 < total; v0 += 32 * GNV) {
+      int ii[GNV], cc[GNV];
+      bool ok[GNV];
+      double pti[GNV], pci[GNV], psi[GNV], ptj[GNV], pcj[GNV], psj[GNV], ev[GNV];
+#pragma unroll
+      for (int q = 0; q < GNV; ++q) {
+        const int v = v0 + 32 * q;
+        ok[q] = v < total;
+        cc[q] = (!ok[q] || v < lenA) ? cA : cB;
+        ii[q] = !ok[q] ? cA : ((v < lenA) ? cA + v : cB + (v - lenA));
+        pti[q] = ts[ii[q]]; pci[q] = ts[N + ii[q]]; psi[q] = ts[2 * N + ii[q]];
+        ptj[q] = ts[cc[q]]; pcj[q] = ts[N + cc[q]]; psj[q] = ts[2 * N + cc[q]];
       }
-      if (i1 == c1) {
-        const double ye = yerr[i1];
-        e1 = kdiag0 + ye * ye;
-      }
-      bad |= !isfinite(e0);
-      sweep_colp<true>(S, ld, c0)[i0] = e0;
-      if (ok1) {
-        bad |= !isfinite(e1);
-        sweep_colp<true>(S, ld, c1)[i1] = e1;
+      cov_pair_n<GNV, true>(cp, pti, pci, psi, ptj, pcj, psj, ev);
+#pragma unroll
+      for (int q = 0; q < GNV; ++q) {
+        double e = ev[q];
+        if (ii[q] == cc[q]) {
+          const double ye = yerr[ii[q]];
+          e = kdiag0 + ye * ye;
+        }
+        if (ok[q]) {
+          bad |= !isfinite(e);
+          sweep_colp<true>(S, ld, cc[q])[ii[q]] = e;
+        }
       }
     }
   }
