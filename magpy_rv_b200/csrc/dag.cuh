@@ -1,4 +1,4 @@
-// Persistent dataflow ("tile DAG") form of the tiled factorisation for 512 < N <= 4096, batched over a wave.
+// Persistent dataflow ("tile DAG") form of the tiled factorisation for 3 ... 32 tile columns (N <= 4096), batched over a wave.
 //
 // The launch-per-tile-column host loop of abi.cu:run_wave pays, per column, a serial chain
 //     in-panel UPDATE -> diagonal-tile kernel (latency-bound, one CTA per walker) -> TRSM
@@ -11,12 +11,13 @@
 //   O(b, i, k), i > k   acc = -K(i,k) generated from the points (first and only touch) + sum_{p<k} L(i,p) L(k,p)^T  (DMMA,
 //                       operands streamed through the bulk-copy / mbarrier ring; the k tiles of a row are contiguous in
 //                       memory); C = -acc goes to SHARED memory in operand order (it never visits HBM); once the
-//                       diagonal tile of column k is done: X = C inv(L_kk)^T (DMMA, A fragments straight from the C tile,
-//                       inv(L_kk) streamed through a second small ring, triangular skip as in TRSM), L(i,k) = X stored,
-//                       r_i -= X z_k.
-//   D(b, k)             acc = -K(k,k) + sum_{p<k} L(k,p) L(k,p)^T; the 128 x 128 block goes to shared memory and is swept
-//                       by cta_block_sweep (pivots, inv(L_kk), z_k = L_kk^-1 r_k, log det, status) exactly as
-//                       potrf_tile_blk_kernel does.
+//                       diagonal tile of column k is done: X = C inv(L_kk)^T (DMMA in 16 x 128 warp strips, A fragments
+//                       straight from the C tile, inv(L_kk) streamed through a second small ring, the zero triangle skipped
+//                       equally by every warp), L(i,k) = X stored, r_i -= X z_k; the progress counter is released one task
+//                       later, when the stores have drained.
+//   D(b, k)             acc = -K(k,k) + sum_{p<k} L(k,p) L(k,p)^T for the lower triangle only (9 accumulator fragments per
+//                       warp); the block goes to shared memory and is swept by cta_block_sweep_la (pivots, inv(L_kk),
+//                       z_k = L_kk^-1 r_k, log det, status), bitwise as potrf_tile_blk_kernel does.
 // Row i of walker b has `rowdone[b][i]` = number of finished tiles (i,0..); O(b,i,k) needs rowdone[b][i] >= k and
 // rowdone[b][k] >= k for its update and rowdone[b][k] >= k + 1 (diagonal tile done) for its solve.
 //
@@ -83,12 +84,6 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 // experiment switches (tools/build_variant.py): defaults are the measured best
-#ifndef DAG_DIAG_MAP
-#define DAG_DIAG_MAP 3        // 0: diagonal tiles updated in full; 1: (4,4,4,2 | 1,1,1,3) fragment rows per warp; 2: (3,3,3,3 | 2,2,2,2); 3: 9 fragments per warp
-#endif
-#ifndef DAG_SOLVE_STRIPS
-#define DAG_SOLVE_STRIPS 1    // solve phase in 16 x 128 warp strips (balanced triangular skip) instead of the 2 x 4 warp grid
-#endif
 #ifndef DAG_SWEEP_LOOKAHEAD
 #define DAG_SWEEP_LOOKAHEAD 1   // diagonal-tile sweep with the next pivot block overlapped with the trailing update (blocked.cuh)
 #endif
@@ -165,87 +160,67 @@ __device__ __forceinline__ void dag_decode(const DagArgs& g, int tsk, int& type,
   i = s + 3 + r % per;
 }
 
-// k16-slice main loop of a tile task.  UPDATE (SOLVE = false): A | B slice pairs through the 4-stage ring R0.
-// SOLVE: A fragments straight from the resident C tile in R0 (slice q at q * SLICE_ELEMS), inv(L_kk) slices through the
-// 3-stage ring R1; the warp owning output columns [32 wn, 32 wn + 32) stops issuing after slice q_last = 2 wn + 1
-// (inv(L) is lower triangular).  `q0` is the ring's running slice counter (stage and barrier phase persist across tasks).
-// DIAG (update of a diagonal tile): only the lower triangle is needed, so the warp owns `nmi` <= 4 m16 row fragments
-// (dag_diag_map) and neither loads nor multiplies the others.
-template <bool SOLVE, bool DIAG = false>
-__device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices, unsigned q0, const double* ringA,
-                                             const double* ringB, unsigned long long* fbar, unsigned long long* ebar,
+// k16-slice main loop of the update of an OFF-DIAGONAL tile: A | B slice pairs through the 4-stage ring, 2 x 4 warp grid
+// (warp tile 64 x 32), fragments of the next k4 step fetched while the current one issues.  `q0` is the ring's running
+// slice counter (stage and barrier phase persist across tasks).
+__device__ __forceinline__ void dag_mainloop(double (&acc)[4][4][4], int nslices, unsigned q0, const double* ring,
+                                             unsigned long long* fbar, unsigned long long* ebar,
                                              const double* __restrict__ Asrc, const double* __restrict__ Bsrc, int a_lane,
-                                             int b_lane, int q_last, int tid, int lane, int nmi = 4) {
-  constexpr unsigned NSTG = SOLVE ? DAG_BSTAGES : GEMM_TMA_STAGES;
+                                             int b_lane, int tid, int lane) {
+  constexpr unsigned NSTG = GEMM_TMA_STAGES;
   constexpr unsigned slice_bytes = SLICE_ELEMS * sizeof(double);
-  auto a_ptr = [&](int q, unsigned st) -> const double* {
-    return SOLVE ? ringA + (size_t)q * SLICE_ELEMS + a_lane : ringA + st * GEMM_STAGE_DOUBLES + a_lane;
-  };
-  auto b_ptr = [&](unsigned st) -> const double* {
-    return SOLVE ? ringB + st * SLICE_ELEMS + b_lane : ringA + st * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane;
-  };
+  auto a_ptr = [&](unsigned st) -> const double* { return ring + st * GEMM_STAGE_DOUBLES + a_lane; };
+  auto b_ptr = [&](unsigned st) -> const double* { return ring + st * GEMM_STAGE_DOUBLES + SLICE_ELEMS + b_lane; };
   double af[2][8], bf[2][4];
   {
     const unsigned st0 = q0 % NSTG;
     mbar_wait(&fbar[st0], (q0 / NSTG) & 1);
-    const double* As = a_ptr(0, st0);
+    const double* As = a_ptr(st0);
     const double* Bs = b_ptr(st0);
 #pragma unroll
-    for (int v = 0; v < 8; ++v)
-      if (!DIAG || (v >> 1) < nmi) af[0][v] = As[v << 5];
+    for (int v = 0; v < 8; ++v) af[0][v] = As[v << 5];
 #pragma unroll
     for (int v = 0; v < 4; ++v) bf[0][v] = Bs[v << 5];
   }
   for (int q = 0; q < nslices; ++q) {
     const unsigned qa = q0 + q, st = qa % NSTG;
     {
-      // refill: slice q + 2 goes into the stage consumed two (one, for the 3-stage ring) iterations ago
+      // refill: slice q + 2 goes into the stage consumed two iterations ago
       const int qn = q + 2;
       if (tid == 0 && qn < nslices) {
         const unsigned qq = q0 + qn, sn = qq % NSTG, u = qq / NSTG;
         if (u > 0) mbar_wait(&ebar[sn], (u - 1) & 1);
-        if (SOLVE) {
-          mbar_expect_tx(&fbar[sn], slice_bytes);
-          bulk_g2s(const_cast<double*>(ringB) + sn * SLICE_ELEMS, Bsrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
-        } else {
-          double* dst = const_cast<double*>(ringA) + sn * GEMM_STAGE_DOUBLES;
-          mbar_expect_tx(&fbar[sn], 2 * slice_bytes);
-          bulk_g2s(dst, Asrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
-          bulk_g2s(dst + SLICE_ELEMS, Bsrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
-        }
+        double* dst = const_cast<double*>(ring) + sn * GEMM_STAGE_DOUBLES;
+        mbar_expect_tx(&fbar[sn], 2 * slice_bytes);
+        bulk_g2s(dst, Asrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
+        bulk_g2s(dst + SLICE_ELEMS, Bsrc + (size_t)qn * SLICE_ELEMS, slice_bytes, &fbar[sn]);
       }
       __syncwarp();
     }
-    const double* As = a_ptr(q, st);
+    const double* As = a_ptr(st);
     const double* Bs = b_ptr(st);
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const int cur = kk & 1, nxt = cur ^ 1;
       if (kk < 3) {
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
-          if (!DIAG || (v >> 1) < nmi) af[nxt][v] = As[(((kk + 1) * 16 + v) << 5)];
+        for (int v = 0; v < 8; ++v) af[nxt][v] = As[(((kk + 1) * 16 + v) << 5)];
 #pragma unroll
         for (int v = 0; v < 4; ++v) bf[nxt][v] = Bs[(((kk + 1) * 16 + v) << 5)];
       } else if (q + 1 < nslices) {
         const unsigned qn1 = qa + 1, sn = qn1 % NSTG;
         mbar_wait(&fbar[sn], (qn1 / NSTG) & 1);
-        const double* An = a_ptr(q + 1, sn);
+        const double* An = a_ptr(sn);
         const double* Bn = b_ptr(sn);
 #pragma unroll
-        for (int v = 0; v < 8; ++v)
-          if (!DIAG || (v >> 1) < nmi) af[nxt][v] = An[v << 5];
+        for (int v = 0; v < 8; ++v) af[nxt][v] = An[v << 5];
 #pragma unroll
         for (int v = 0; v < 4; ++v) bf[nxt][v] = Bn[v << 5];
       }
-      if (!SOLVE || q <= q_last) {   // warp-uniform
 #pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-          if (!DIAG || mi < nmi) {   // warp-uniform
+      for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-            for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
-          }
-      }
+        for (int ni = 0; ni < 4; ++ni) dmma_1684(acc[mi][ni], af[cur][2 * mi], af[cur][2 * mi + 1], bf[cur][ni]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&ebar[st]);
@@ -341,9 +316,6 @@ __device__ __forceinline__ void dag_diag_update(double (&acc)[4][4][4], int nsli
                                                 unsigned long long* fbar, unsigned long long* ebar,
                                                 const double* __restrict__ Asrc, const double* __restrict__ Bsrc, int warp, int tid,
                                                 int lane) {
-#ifdef DAG_DIAG_SAMECODE   // timing experiment only (wrong results): every warp runs warp 0's code copy
-  if (warp >= 0) { dag_diag_loop<7, 0, 9, 0, 0, 0>(acc, nslices, q0, ring, fbar, ebar, Asrc, tid, lane); return; }
-#endif
   switch (warp) {   // one code copy per warp; only warp 0's contains a live producer branch
     case 0: dag_diag_loop<7, 0, 9, 0, 0, 0>(acc, nslices, q0, ring, fbar, ebar, Asrc, tid, lane); break;
     case 1: dag_diag_loop<7, 9, 7, 0, 0, 2>(acc, nslices, q0, ring, fbar, ebar, Asrc, 1, lane); break;
@@ -575,7 +547,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         const unsigned qq = qg + q, sn = qq % NST, u = qq / NST;
         if (u > 0) mbar_wait(&empty_bar[sn], (u - 1) & 1);
         double* dst = stages + sn * GEMM_STAGE_DOUBLES;
-        if (DAG_DIAG_MAP == 3 && s_task[0] == DAG_TASK_DIAG) {   // rows i and k are the same tile row: one slice serves as A and B
+        if (s_task[0] == DAG_TASK_DIAG) {   // rows i and k are the same tile row: one slice serves as A and B
           mbar_expect_tx(&full_bar[sn], SLICE_ELEMS * sizeof(double));
           bulk_g2s(dst, rowA + (size_t)q * SLICE_ELEMS, SLICE_ELEMS * sizeof(double), &full_bar[sn]);
           continue;
@@ -598,25 +570,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
     mbar_wait(&pt_bar[n_local & 1], (n_local >> 1) & 1);   // this task's points (issued during the previous task)
 
     double acc[4][4][4];
-    // update: 2 x 4 warp grid, warp tile = rows [rb, rb + 64) x columns [32 wn0, 32 wn0 + 32).  A DIAGONAL tile needs its
-    // lower triangle only: 20 of the 32 (m16 x n32) fragment rows; they are dealt so that every SM sub-partition (warps
-    // w and w + 4) issues 5 of them instead of 8 -- the update of a diagonal tile takes 5/8 of a full tile product.
-    //   warp            0     1     2     3     4     5     6     7
-    //   column block    0     0     1     1     2     3     3     2
-    //   m16 rows       0-3   4-7   2-5   6-7    4     6     7    5-7
-    int wn0 = warp & 3, rb = wm * 64, nmi = 4;
-    if (type == DAG_TASK_DIAG) {
-#if DAG_DIAG_MAP == 1
-      wn0 = (0x23321100u >> (4 * warp)) & 15;
-      rb = 16 * ((0x57646240u >> (4 * warp)) & 15);
-      nmi = (0x31112444u >> (4 * warp)) & 15;
-#elif DAG_DIAG_MAP == 2
-      wn0 = (0x32201100u >> (4 * warp)) & 15;
-      rb = 16 * ((0x66465230u >> (4 * warp)) & 15);
-      nmi = (0x22223333u >> (4 * warp)) & 15;
-#endif
-    }
-    const int wn1 = wm ? 3 - (warp & 3) : (warp & 3);      // solve: the two warps of an SM sub-partition get wn and 3 - wn
+    // off-diagonal tiles: 2 x 4 warp grid, warp tile = rows [rb, rb + 64) x columns [32 wn0, 32 wn0 + 32); diagonal tiles:
+    // 9 accumulator fragments per warp (dag_diag_segments); the solve re-deals the tile in 16 x 128 warp strips
+    const int wn0 = warp & 3, rb = wm * 64;
     {
       // ---- generation: acc = -K(ti, tk) ----
       const int wn = wn0;
@@ -625,7 +581,6 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
       cp.a2 = pr[6 * TILE]; cp.c1 = pr[6 * TILE + 1]; cp.c2 = pr[6 * TILE + 2]; cp.c3 = pr[6 * TILE + 3];
       cp.jit2 = pr[6 * TILE + 4]; cp.cph = 0.0;
       const bool interior = ti > tk && (ti + 1) * TILE <= g.N;
-#if DAG_DIAG_MAP == 3
       if (type == DAG_TASK_DIAG) {
         int uA, vA0, nA, uB, vB0, nB;
         dag_diag_segments(warp, uA, vA0, nA, uB, vB0, nB);
@@ -642,7 +597,6 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           for (int v = 0; v < 4; ++v) acc[slot >> 2][slot & 3][v] = -frag[v];
         }
       } else
-#endif
       if (interior && (cp.kind == 3 || cp.kind == 4)) {
 #pragma unroll
         for (int mi = 0; mi < 4; ++mi)
@@ -667,7 +621,6 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
           for (int np2 = 0; np2 < 2; ++np2) {
-            if (mi >= nmi) continue;   // diagonal tile: fragment rows above the diagonal are not this warp's
             const int R = rb + mi * 16 + gq;
             const int C = wn * 32 + np2 * 16 + 2 * tig;
             double frag[8];
@@ -689,15 +642,10 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
     // ---- update: acc += sum_p L(ti,p) L(tk,p)^T ----
     if (tk > 0) {
       if (type == DAG_TASK_DIAG)
-#if DAG_DIAG_MAP == 3
         dag_diag_update(acc, tk * SLICES_PER_TILE, qg, stages, full_bar, empty_bar, rowA, rowB, warp, tid, lane);
-#else
-        dag_mainloop<false, true>(acc, tk * SLICES_PER_TILE, qg, stages, nullptr, full_bar, empty_bar, rowA, rowB,
-                                  ((rb >> 3) << 5) + lane, ((wn0 * 4) << 5) + lane, 0x7fffffff, tid, lane, nmi);
-#endif
       else
-        dag_mainloop<false>(acc, tk * SLICES_PER_TILE, qg, stages, nullptr, full_bar, empty_bar, rowA, rowB, ((wm * 8) << 5) + lane,
-                            ((wn0 * 4) << 5) + lane, 0x7fffffff, tid, lane);
+        dag_mainloop(acc, tk * SLICES_PER_TILE, qg, stages, full_bar, empty_bar, rowA, rowB, ((wm * 8) << 5) + lane,
+                     ((wn0 * 4) << 5) + lane, tid, lane);
       qg += tk * SLICES_PER_TILE;
     }
     tm.mark(type == DAG_TASK_DIAG ? 15 : 2);
@@ -751,19 +699,13 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           for (int ni = 0; ni < 4; ++ni)
 #pragma unroll
             for (int v = 0; v < 4; ++v) acc[mi][ni][v] = 0.0;
-#if DAG_SOLVE_STRIPS
         dag_solve_strips(acc, qb, stages, bring, fullB, emptyB, Bsrc, warp, tid, lane);
-#else
-        dag_mainloop<true>(acc, SLICES_PER_TILE, qb, stages, bring, fullB, emptyB, nullptr, Bsrc, ((wm * 8) << 5) + lane,
-                           ((wn1 * 4) << 5) + lane, 2 * wn1 + 1, tid, lane);
-#endif
         qb += SLICES_PER_TILE;
       }
       tm.mark(5);
     }
 
     {
-      const int wn = (type == DAG_TASK_OFF) ? wn1 : wn0;
       if (aborted) {
         // nothing to store
       } else
@@ -771,7 +713,6 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
       if (type == DAG_TASK_OFF) {
         // X = acc is L(i,k): store it and fold r_i -= X z_k
         __syncthreads();   // zs; every warp has read its last A fragments from the C tile
-#if DAG_SOLVE_STRIPS
         // strip layout: fragment v = 4 cb + ni of the warp's 16 rows.  Row sums in the order of the 2 x 4 layout (per
         // column block cb: ni ascending, then the quad's lanes; then ((p0 + p1) + p2) + p3), so r_i is bitwise the same.
 #pragma unroll
@@ -800,44 +741,6 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
             ri[R] = __ldcg(ri + R) - (((p4[0] + p4[1]) + p4[2]) + p4[3]);
           }
         }
-#else
-        double rowsum[4][2];
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int v1 = 0; v1 < 2; ++v1) {
-            double s = 0.0;
-#pragma unroll
-            for (int ni = 0; ni < 4; ++ni) {
-              const int R = wm * 64 + mi * 16 + gq + 8 * v1;
-              const int C = wn * 32 + ni * 8 + 2 * tig;
-              double2 x;
-              x.x = acc[mi][ni][2 * v1 + 0];
-              x.y = acc[mi][ni][2 * v1 + 1];
-              *reinterpret_cast<double2*>(Ct + tile_off(R, C)) = x;
-              s = fma(x.x, zs[C], s);
-              s = fma(x.y, zs[C + 1], s);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            rowsum[mi][v1] = s;
-          }
-        if (tig == 0) {
-#pragma unroll
-          for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-            for (int v1 = 0; v1 < 2; ++v1) part[wn * TILE + wm * 64 + mi * 16 + gq + 8 * v1] = rowsum[mi][v1];
-        }
-        // (no proxy fence here: a per-thread fence.proxy.async after 128 KiB of global stores waits for them to drain,
-        // ~1 us per tile.  Readers of X order their bulk copies behind it on THEIR side -- acquire of the progress
-        // counter, then fence.proxy.async --, and the reuse of R0 by the next bulk copies is ordered by the barriers.)
-        __syncthreads();
-        if (tid < TILE) {
-          const double s = ((part[tid] + part[TILE + tid]) + part[2 * TILE + tid]) + part[3 * TILE + tid];
-          double* ri = g.resid + (size_t)b * g.ldr + (size_t)ti * TILE;
-          ri[tid] = __ldcg(ri + tid) - s;
-        }
-#endif
         __syncthreads();
         // one fence after the barrier covers the whole CTA's stores (fence cumulativity), then the release
         if (tid == 0) {
@@ -855,7 +758,6 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         // (only the fragment rows that reach the lower triangle exist; the sweep never reads what lies above it: the
         // strict upper triangle is where it ASSIGNS the inverse, blocked.cuh)
         __syncthreads();   // every warp has left the ring: S aliases it
-#if DAG_DIAG_MAP == 3
         {
           int uA, vA0, nA, uB, vB0, nB;
           dag_diag_segments(warp, uA, vA0, nA, uB, vB0, nB);
@@ -870,19 +772,6 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
             for (int v = 0; v < 4; ++v) S[R0 + 8 * (v >> 1) + (size_t)(C0 + (v & 1)) * PB_LD] = -acc[slot >> 2][slot & 3][v];
           }
         }
-#else
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-            for (int v = 0; v < 4; ++v) {
-              if (mi >= nmi) continue;
-              const int R = rb + mi * 16 + gq + 8 * (v >> 1);
-              const int C = wn * 32 + ni * 8 + 2 * tig + (v & 1);
-              S[R + (size_t)C * PB_LD] = -acc[mi][ni][v];
-            }
-#endif
         if (tid < TILE) {
           S[TILE + (size_t)tid * PB_LD] = __ldcg(g.resid + (size_t)b * g.ldr + (size_t)tk * TILE + tid);
 #pragma unroll
