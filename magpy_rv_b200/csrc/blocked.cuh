@@ -655,7 +655,8 @@ __device__ inline void cta_block_sweep(double* S, const int ld, int n_cols, doub
 template <int NW, int MAXT, bool WITH_INV, bool PACKED>
 __device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, const int n_n8, const int k0, const int tm0,
                                                      const int tm1, const double* PA, const int pa_ld, const double* PB,
-                                                     const int pb_ld, const int wi, const int gq, const int tig) {
+                                                     const int pb_ld, const int wi, const int gq, const int tig,
+                                                     const int tn_min = 0) {
   const int c_begin = k0 + PB_NB;
   constexpr int SLOTS = (MAXT + NW - 1) / NW;     // n_n8 <= MAXT row tiles (rows + the residual row)
   int rho0s[SLOTS];
@@ -665,7 +666,7 @@ __device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, co
   for (int sl = 0; sl < SLOTS; ++sl) {
     const int tn = wi + NW * sl;
     rho0s[sl] = tn * 8;
-    live[sl] = tn < n_n8 && (WITH_INV || rho0s[sl] + 7 >= c_begin);
+    live[sl] = tn < n_n8 && tn >= tn_min && (WITH_INV || rho0s[sl] + 7 >= c_begin);
     pivot[sl] = rho0s[sl] >= k0 && rho0s[sl] < k0 + PB_NB;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) bfr[sl][kk] = live[sl] ? PA[(kk * 4 + tig) * pa_ld + rho0s[sl] + gq] : 0.0;
@@ -779,6 +780,122 @@ __device__ inline void cta_block_sweep_la(double* S, const int ld, int n_cols, d
     else sweep_trailing_tiles<6, MAXT, WITH_INV, PACKED>(S, ld, n_n8, k0, 1, n_m16, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig);
     __syncthreads();
     if (ptm) ptm->mark(10);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CRITICAL-PATH form of the look-ahead sweep for the fused small-N kernel (factor rows only, 256 threads).  With a matrix
+// of ~100 columns the tensor-pipe phases of a block step are short and the chain
+//     pivot block kb -> panel rows -> next pivot block's 16 columns -> pivot block kb + 1
+// is what a step costs.  Only the 16 rows / columns of the NEXT pivot block are on that chain, so warps 0-1 keep it to
+// themselves: they finish the panel entries of those 16 rows (one 8-row tile each), update the 16 x 16 diagonal block and
+// sweep it, synchronised by their own 64-thread barrier, while warps 2-7 do everything else of step kb (panel rows of the
+// other rows, then -- once warps 0-1 have published their panel rows, named barrier 2 -- the trailing update).  The pivot
+// block buffers D / wv are double-buffered (warps 2-7 still read block kb's while block kb + 1 is swept).  Every element
+// sees the same operations in the same order as in cta_block_sweep: bitwise identical results.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bar_arrive_panel() { asm volatile("bar.arrive 2, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_panel() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
+
+// Panel entries of the 8-row tile rho0 (not a pivot tile) for pivot block k0: X = A G on the tensor pipe; writes the swept
+// columns of S and the operand panels PA / PB (as step 2 of cta_block_sweep).
+template <bool PACKED>
+__device__ __forceinline__ void sweep_panel_tile(double* S, const int ld, const int n_cols, const int n_rows, const int k0,
+                                                 const int rho0, const double (&gt0)[4], const double (&gt1)[4], double* PA,
+                                                 const int pa_ld, double* PB, const int pb_ld, const double* wv, const int gq,
+                                                 const int tig) {
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) dmma_1684_neg0(acc, gt0[kk], gt1[kk], sweep_colp<PACKED>(S, ld, k0 + 4 * kk + tig)[rho0 + gq]);
+  const int rhoA = rho0 + 2 * tig;                       // this lane's two rows: rhoA, rhoA + 1
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int j = gq + 8 * h;
+    double2 x;
+    x.x = acc[2 * h];
+    x.y = acc[2 * h + 1];
+    if (rhoA >= n_rows) x.x = 0.0;                     // padding rows below the residual row stay zero
+    if (rhoA + 1 >= n_rows) x.y = 0.0;
+    *reinterpret_cast<double2*>(sweep_colp<PACKED>(S, ld, k0 + j) + rhoA) = x;
+    *reinterpret_cast<double2*>(PA + j * pa_ld + rhoA) = x;
+    if (rhoA < n_cols) {
+      const double w = wv[j];
+      double2 y;
+      y.x = (rhoA >= k0 + PB_NB) ? -x.x * w : 0.0;
+      y.y = (rhoA + 1 >= k0 + PB_NB && rhoA + 1 < n_cols) ? -x.y * w : 0.0;
+      *reinterpret_cast<double2*>(PB + j * pb_ld + rhoA) = y;
+    }
+  }
+}
+
+template <bool PACKED, int MAXT>
+__device__ inline void cta_block_sweep_cp(double* S, const int ld, int n_cols, double* PA, const int pa_ld, double* PB,
+                                          const int pb_ld, double* D2 /* 2 x PB_NB x PB_D_LD */, double* wv2 /* 2 x PB_NB */) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, tig = lane & 3;
+  const int n_rows = n_cols + 1;                 // + residual row
+  const int n_rows8 = (n_rows + 7) & ~7;
+  const int n_n8 = n_rows8 / 8;
+  const int nblk = n_cols / PB_NB;
+  if (warp < 2) sweep_pivot_block64<PACKED>(S, ld, 0, D2, wv2, tid);
+  __syncthreads();
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int k0 = kb * PB_NB, c_begin = k0 + PB_NB;
+    const double* D = D2 + (kb & 1) * (PB_NB * PB_D_LD);
+    const double* wv = wv2 + (kb & 1) * PB_NB;
+    const bool last = c_begin >= n_cols;           // no trailing columns: only the residual row's panel entries remain
+    const int tn0 = c_begin / 8;                   // first row tile below the pivot block (factor rows only: nothing above counts)
+    double gt0[4], gt1[4];   // G^T fragments: rows j = gq and gq + 8, columns jp = 4 kk + tig
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int jp = 4 * kk + tig;
+      gt0[kk] = (jp < gq) ? D[jp * PB_D_LD + gq] : (jp == gq ? 1.0 : 0.0);
+      gt1[kk] = (jp < gq + 8) ? D[jp * PB_D_LD + gq + 8] : (jp == gq + 8 ? 1.0 : 0.0);
+    }
+    if (last) {
+      for (int tn = tn0 + warp; tn < n_n8; tn += 8) sweep_panel_tile<PACKED>(S, ld, n_cols, n_rows, k0, tn * 8, gt0, gt1, PA, pa_ld, PB, pb_ld, wv, gq, tig);
+    } else if (warp < 2) {
+      // ---- the chain: rows / columns of the next pivot block only ----
+      const int rho0 = c_begin + 8 * warp;
+      sweep_panel_tile<PACKED>(S, ld, n_cols, n_rows, k0, rho0, gt0, gt1, PA, pa_ld, PB, pb_ld, wv, gq, tig);
+      __threadfence_block();
+      bar_arrive_panel();                          // warps 2-7 may now read these panel rows
+      bar_sync_pivot64();                          // ... and so may the other warp of the pair
+      {
+        // 8 x 16 piece of the next diagonal block: S[rho][c] += sum_j PA[rho][j] PB[c][j], c in [c_begin, c_begin + 16)
+        double a0[4], a1[4], bfr[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          a0[kk] = PB[(kk * 4 + tig) * pb_ld + c_begin + gq];
+          a1[kk] = PB[(kk * 4 + tig) * pb_ld + c_begin + gq + 8];
+          bfr[kk] = PA[(kk * 4 + tig) * pa_ld + rho0 + gq];
+        }
+        double* p0 = sweep_colp<PACKED>(S, ld, c_begin + gq) + (rho0 + 2 * tig);
+        double* p1 = sweep_colp<PACKED>(S, ld, c_begin + gq + 8) + (rho0 + 2 * tig);
+        const double2 u = *reinterpret_cast<const double2*>(p0), v = *reinterpret_cast<const double2*>(p1);
+        double acc[4] = {u.x, u.y, v.x, v.y};
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) dmma_1684_neg0(acc, a0[kk], a1[kk], bfr[kk]);
+        double2 uo, vo;
+        uo.x = acc[0]; uo.y = acc[1]; vo.x = acc[2]; vo.y = acc[3];
+        *reinterpret_cast<double2*>(p0) = uo;
+        *reinterpret_cast<double2*>(p1) = vo;
+      }
+      bar_sync_pivot64();
+      sweep_pivot_block64<PACKED>(S, ld, c_begin, D2 + ((kb + 1) & 1) * (PB_NB * PB_D_LD), wv2 + ((kb + 1) & 1) * PB_NB, tid);
+    } else {
+      // ---- everything else of step kb ----
+      for (int tn = tn0 + 2 + (warp - 2); tn < n_n8; tn += 6)
+        sweep_panel_tile<PACKED>(S, ld, n_cols, n_rows, k0, tn * 8, gt0, gt1, PA, pa_ld, PB, pb_ld, wv, gq, tig);
+      __threadfence_block();
+      bar_sync_panel();                            // all panel rows of the step are in PA / PB (named barrier 2: 64 arrive, 192 wait)
+      const int n_m16 = (n_cols - c_begin) / 16;
+      // the next pivot block's columns, rows below that block (its own 16 rows are the chain's) ...
+      sweep_trailing_tiles<6, MAXT, false, PACKED>(S, ld, n_n8, k0, 0, 1, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig, tn0 + 2);
+      // ... and every column behind it
+      sweep_trailing_tiles<6, MAXT, false, PACKED>(S, ld, n_n8, k0, 1, n_m16, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig);
+    }
+    __syncthreads();
   }
 }
 

@@ -141,7 +141,7 @@ __host__ __device__ inline int sblk_ld(int N) {
 }
 __host__ inline size_t small_blk_smem_bytes(int N) {
   const int nc = sblk_cols(N), ld = sblk_ld(N);
-  return (sweep_packed_doubles(ld, nc) + PB_NB * (size_t)(ld + 12) + PB_NB * (size_t)(nc + 4) + PB_NB * PB_D_LD + PB_NB + 4 * (size_t)N +
+  return (sweep_packed_doubles(ld, nc) + PB_NB * (size_t)(ld + 12) + PB_NB * (size_t)(nc + 4) + 2 * (PB_NB * PB_D_LD + PB_NB) + 4 * (size_t)N +
           MRV_MAX_MODPAR + MRV_MAX_HP + 40) * sizeof(double);
 }
 
@@ -173,9 +173,9 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
   double* S = smem;                          // packed column blocks (sweep_colp<true>); row nc = residual row
   double* PA = S + sweep_packed_doubles(ld, nc);
   double* PBm = PA + PB_NB * pa_ld;
-  double* Dblk = PBm + PB_NB * pb_ld;
-  double* wv = Dblk + PB_NB * PB_D_LD;
-  double* ts = wv + PB_NB;                   // 3 N: t, phase cosine, phase sine of every point (cov_pair_n)
+  double* Dblk = PBm + PB_NB * pb_ld;         // 2 x (16 x 17): pivot blocks kb and kb + 1 (cta_block_sweep_cp)
+  double* wv = Dblk + 2 * PB_NB * PB_D_LD;   // 2 x 16
+  double* ts = wv + 2 * PB_NB;               // 3 N: t, phase cosine, phase sine of every point (cov_pair_n)
   double* r = ts + 3 * N;                    // N
   double* phys = r + N;                      // MRV_MAX_MODPAR
   double* hpv = phys + MRV_MAX_MODPAR;       // MRV_MAX_HP
@@ -274,7 +274,11 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
 #else
   // look-ahead form (blocked.cuh).  Row tiles of 8: the MINB = 4 / 3 variants are only launched when 4 / 3 CTAs fit an SM,
   // i.e. N <= 64 / 80 (9 / 11 row tiles incl. the residual row); N <= 144: 19
+#ifdef SMALL_SWEEP_LA
   cta_block_sweep_la<false, true, (MINB >= 4 ? 9 : (MINB == 3 ? 11 : 19))>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
+#else
+  cta_block_sweep_cp<true, (MINB >= 4 ? 9 : (MINB == 3 ? 11 : 19))>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
+#endif
 #endif
 
   SMALL_MARK(3)
