@@ -569,6 +569,19 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
     }
     mbar_wait(&pt_bar[n_local & 1], (n_local >> 1) & 1);   // this task's points (issued during the previous task)
 
+    // The residual block this task reads at its very end (r_i of an off-diagonal tile: lanes tig = 0 of warp w hold rows
+    // 16 w + gq and + 8; r_k of a diagonal tile: one row per thread) is final once the task's dependencies hold, so it is
+    // fetched now -- the L2 round trip then overlaps the whole task instead of sitting in its epilogue.
+    double rpre0 = 0.0, rpre1 = 0.0;
+    {
+      const double* rblk = g.resid + (size_t)b * g.ldr + (size_t)ti * TILE;
+      if (type == DAG_TASK_DIAG) {
+        if (tid < TILE) rpre0 = __ldcg(rblk + tid);
+      } else if (tig == 0) {
+        rpre0 = __ldcg(rblk + warp * 16 + gq);
+        rpre1 = __ldcg(rblk + warp * 16 + gq + 8);
+      }
+    }
     double acc[4][4][4];
     // off-diagonal tiles: 2 x 4 warp grid, warp tile = rows [rb, rb + 64) x columns [32 wn0, 32 wn0 + 32); diagonal tiles:
     // 9 accumulator fragments per warp (dag_diag_segments); the solve re-deals the tile in 16 x 128 warp strips
@@ -738,7 +751,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           }
           if (tig == 0) {
             double* ri = g.resid + (size_t)b * g.ldr + (size_t)ti * TILE;
-            ri[R] = __ldcg(ri + R) - (((p4[0] + p4[1]) + p4[2]) + p4[3]);
+            ri[R] = (v1 == 0 ? rpre0 : rpre1) - (((p4[0] + p4[1]) + p4[2]) + p4[3]);
           }
         }
         __syncthreads();
@@ -773,7 +786,7 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
           }
         }
         if (tid < TILE) {
-          S[TILE + (size_t)tid * PB_LD] = __ldcg(g.resid + (size_t)b * g.ldr + (size_t)tk * TILE + tid);
+          S[TILE + (size_t)tid * PB_LD] = rpre0;
 #pragma unroll
           for (int r = TILE + 1; r < PB_LD; ++r) S[r + (size_t)tid * PB_LD] = 0.0;
         }
