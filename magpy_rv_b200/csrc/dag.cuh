@@ -572,11 +572,17 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
     // The residual block this task reads at its very end (r_i of an off-diagonal tile: lanes tig = 0 of warp w hold rows
     // 16 w + gq and + 8; r_k of a diagonal tile: one row per thread) is final once the task's dependencies hold, so it is
     // fetched now -- the L2 round trip then overlaps the whole task instead of sitting in its epilogue.
-    double rpre0 = 0.0, rpre1 = 0.0;
+    double rpre0 = 0.0, rpre1 = 0.0, ld_pre = 0.0, q_pre = 0.0;
+    int st_pre = 0;
     {
       const double* rblk = g.resid + (size_t)b * g.ldr + (size_t)ti * TILE;
       if (type == DAG_TASK_DIAG) {
         if (tid < TILE) rpre0 = __ldcg(rblk + tid);
+        if (tid == 0) {   // the walker's running log det / quadratic form / status: only its diagonal tasks touch them, in order
+          ld_pre = __ldcg(g.acc_logdet + b);
+          q_pre = __ldcg(g.acc_quad + b);
+          st_pre = __ldcg(g.status + b);
+        }
       } else if (tig == 0) {
         rpre0 = __ldcg(rblk + warp * 16 + gq);
         rpre1 = __ldcg(rblk + warp * 16 + gq + 8);
@@ -819,9 +825,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         const int fb = -block_max_int(-first_bad, ired);
         const int anynan = block_max_int(nan_seen, ired);
         if (tid == 0) {
-          g.acc_logdet[b] = __ldcg(g.acc_logdet + b) + logdet;
-          g.acc_quad[b] = __ldcg(g.acc_quad + b) + quad;
-          if (__ldcg(g.status + b) == 0 && fb != 0x7fffffff) g.status[b] = anynan ? -1 : fb;
+          g.acc_logdet[b] = ld_pre + logdet;
+          g.acc_quad[b] = q_pre + quad;
+          if (st_pre == 0 && fb != 0x7fffffff) g.status[b] = anynan ? -1 : fb;
         }
         if (tid < TILE) isd_s[tid] = isd;
         __syncthreads();
