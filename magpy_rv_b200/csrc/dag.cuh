@@ -688,9 +688,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
             *reinterpret_cast<double2*>(stages + tile_off(R, C)) = o;
           }
       tm.mark(3);
-      if (tid == 0) {
+      if (tid == 0 && !b_started) {   // (b_started: the acquire at the start of the task already saw the diagonal tile done)
         if (!dag_wait(rd + tk, tk + 1, abort_flag)) s_task[0] = DAG_TASK_EXIT;
-        else if (!b_started) {
+        else {
           fence_proxy_async();
           for (int q = 0; q < 2; ++q) {
             const unsigned qq = qb + q, sn = qq % DAG_BSTAGES, u = qq / DAG_BSTAGES;
