@@ -406,6 +406,19 @@ class ClockSampler:
 
 
 PROF_CATS = ("gen", "potrf", "trsm", "update_panel", "update_mid", "update_trail", "mean", "final", "fused", "dag")
+def dag_bytes(nt, B):
+    """Algorithmic bytes one launch of the dataflow kernel moves between L2 / HBM and the SMs, for a
+    wave of B walkers: every off-diagonal tile (i, k) streams the k operand tiles of rows i and k (2 k x 128 KiB) and the
+    inverse diagonal factor (128 KiB) and is written once; every diagonal tile streams its own row once (k x 128 KiB) and
+    writes the inverse factor.  16 flop per operand byte at every N."""
+    tile = 128 * 128 * 8
+    per_walker = 0
+    for k in range(nt):
+        per_walker += (nt - 1 - k) * (2 * k + 2) * tile      # off-diagonal tiles of column k: operands + inv(L_kk) + the tile itself
+        per_walker += (k + 1) * tile                          # diagonal tile: its row once + inv(L_kk) out
+    return float(B * per_walker)
+
+
 KERNEL_NAMES = {
     "update_trail": "gemm_tile_kernel (trailing SYRK/GEMM update, DMMA)",
     "update_panel": "gemm_tile_kernel (in-panel SYRK/GEMM update, DMMA)",
@@ -481,7 +494,8 @@ def make_roofline(prob, prof, steps, ms, N, W_local, value_per_gpu, peaks, cov_c
         "launches": d["n"] // steps, "avg_launch_ms": d["ns"] / max(1, d["n"]) * 1e-6,
         "executed_tflops": (d["exec"] / (d["ns"] * 1e-9)) / 1e12,
         "launch_geometry": geom,
-        "algorithmic_bytes_per_launch": trailing_update_bytes(nt, PW, B) if dom == "update_trail" else None,
+        "algorithmic_bytes_per_launch": trailing_update_bytes(nt, PW, B) if dom == "update_trail" else (dag_bytes(nt, B) if dom == "dag" else None),
+        "l2_or_hbm_gbs": (dag_bytes(nt, B) / (d["ns"] / max(1, d["n"]) * 1e-9) / 1e9) if dom == "dag" else None,
         "traffic": cap["dram_bytes_per_launch"] if cap else None,
         "traffic_source": ("ncu --set full capture %s" % cap.get("file", "under profiles/")) if cap else
                           "no ncu capture of this launch geometry (profiles/traffic.json); algorithmic_bytes_per_launch is derived from the geometry",

@@ -580,16 +580,16 @@ static int run_wave(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, c
 }
 
 // Tiled path as ONE persistent dataflow kernel per wave (dag.cuh).  Left-looking by tiles: every tile streams its
-// operands once per tile (16 flop per operand byte, 2.3 TB/s at the DMMA peak -- affordable up to N = 4096, where a
-// walker's factor is 67 MB); above that the right-looking panels of run_wave re-use operands better.
+// operands once per tile -- 16 flop per operand byte at EVERY N, 2.3 TB/s at the DMMA peak, from L2 while a wave's factors
+// fit (N <= 4096) and from HBM above.  Round 1 assumed the right-looking panels of run_wave were needed beyond N = 4096
+// (operand re-use); measured at the end of round 2 the dataflow kernel is ahead at every size it can index (up to 128
+// tile columns): N = 8192 x 128 walkers 93.6 % of the DMMA peak against 89.5 %, N = 16384 93.8 % (waves of 32) / 95.1 %
+// (waves of 64) against 92.1 %, bitwise identical results (tools/big_dag_probe.py).
 static bool use_dag(const mrv_problem* p, int64_t wave = 0) {
+  (void)wave;
   if (p->tiled_impl == 1) return false;
-  if (p->tiled_impl == 2) return p->nt <= 128;
-  if (p->nt < DAG_AUTO_MIN_TILES) return false;
-  if (p->nt <= DAG_AUTO_MAX_TILES) return true;
-  // up to 64 tile columns (N = 8192) the dataflow kernel is still ahead when the wave fills the GPU (128 walkers: 1.02x,
-  // 91.3 % of the DMMA peak; 32 walkers: 0.98x); per-walker results are bitwise the same either way
-  return p->nt <= 2 * DAG_AUTO_MAX_TILES && wave >= 64;
+  if (p->tiled_impl == 2) return p->nt <= DAG_MAX_TILES;
+  return p->nt >= DAG_AUTO_MIN_TILES && p->nt <= DAG_MAX_TILES;
 }
 
 static int run_wave_dag(mrv_problem* p, const double* d_hp, int64_t w0, int64_t B, cudaStream_t st, const SolveOut& so, int wave_index) {
@@ -734,7 +734,8 @@ static int run_logl(mrv_problem* p, const double* d_hp, const double* d_modpar, 
       size_t free_b = 0, total_b = 0;
       CU(cudaMemGetInfo(&free_b, &total_b));
       free_b += p->factor.bytes;  // what we already hold can be reused
-      p->budget_bytes = std::max<size_t>(1, std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)40 << 30));
+      // at most half of what is free, capped at 72 GiB: 64 walkers per wave at N = 16384 (1.03 GiB of packed tiles each)
+      p->budget_bytes = std::max<size_t>(1, std::min<size_t>((size_t)(0.5 * (double)free_b), (size_t)72 << 30));
     }
     B = (int64_t)std::max<size_t>(1, p->budget_bytes / walker_bytes);
   }

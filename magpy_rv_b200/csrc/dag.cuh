@@ -63,7 +63,7 @@ struct DagArgs {
 // the deferred release the dataflow kernel is ahead of the launch-per-column loop from 3 tile columns on (1.12-1.31x at
 // N = 384, 1.06x at C3, 1.24x at 640, 1.22x at 1024, 1.11x at 2048, 1.08x at 4096) and bitwise identical to it
 #define DAG_AUTO_MIN_TILES 3
-#define DAG_AUTO_MAX_TILES 32
+#define DAG_MAX_TILES 128             // N <= 16384 (task decoding and the progress counters are sized for it)
 #define DAG_BSTAGES 3                 // ring of inv(L_kk) k16 slices for the solve phase
 #define DAG_SWEEP_DOUBLES (PB_LD * TILE + PB_NB * PB_PA_LD + PB_NB * PB_PB_LD + PB_NB * PB_D_LD + PB_NB + 64 + TILE)
 #define DAG_R1_OFFSET (GEMM_TMA_STAGES * GEMM_STAGE_DOUBLES)   // doubles: end of the update ring / C tile
@@ -73,7 +73,7 @@ struct DagArgs {
 #define DAG_AUX_DOUBLES (2 * DAG_PTS_DOUBLES + 4 * TILE + TILE)
 #define DAG_NBARS (2 * GEMM_TMA_STAGES + 2 * DAG_BSTAGES + 2)
 #define DAG_SMEM_BYTES ((size_t)(DAG_MAIN_DOUBLES + DAG_AUX_DOUBLES) * sizeof(double) + DAG_NBARS * sizeof(unsigned long long) + 16 * sizeof(int) + 17 * sizeof(long long))
-#define DAG_SPIN_LIMIT (1ll << 33)   // ~4 s of SM clocks: a dependency that takes longer means a lost task, not a slow one
+#define DAG_SPIN_LIMIT (1ll << 35)   // ~17 s of SM clocks (a wave of 64 walkers at N = 16384 runs 2.7 s): a dependency that takes longer means a lost task, not a slow one
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
