@@ -851,8 +851,10 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
       }
     }
     ++n_local;
-    __syncthreads();   // s_task / zs / part are rewritten by the next task
-    tm.mark(0);   // end-of-task barrier: counted with the next task's fetch
+    // both epilogues end in a CTA barrier with nothing but thread 0's release behind it, and nothing reads s_task / zs after
+    // that barrier: it doubles as the end-of-task barrier.  Only the aborted path comes here without one.
+    if (aborted) __syncthreads();
+    tm.mark(0);
   }
 #ifdef DAG_TIMING
   if (tid == 0)
