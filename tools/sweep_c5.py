@@ -1,13 +1,16 @@
 """The C5 scaling sweep on one GPU: evaluations per second and algorithmic TFLOP/s for N = 1024 .. 16384 at the
-per-GPU ensemble of the 8-GPU run (128 walkers), medians of 5 batches through mrv_logl_batch."""
+per-GPU ensemble of the 8-GPU run (128 walkers) -- and, with an argument, at any other ensemble size (N limited so that a
+batch stays below ~10 s) --, medians of 5 batches through mrv_logl_batch.    python tools/sweep_c5.py [walkers]"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, workloads
 from magpy_rv_b200 import engine, _native
 peak = _native.lib().mrv_fp64_mma_peak(0, 20000)
 print("DMMA peak %.2f TFLOP/s" % (peak / 1e12))
-for N in (1024, 2048, 4096, 8192, 16384):
-    W = 128
+W = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+for N in (512, 1024, 2048, 4096, 8192, 16384):
+    if workloads.flops_per_eval(N) * W / 3.0e13 > 10.0:
+        continue
     cfg = workloads.make_config("C5", W=W, N=N)
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"])
     for _ in range(2):
