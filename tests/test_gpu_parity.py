@@ -336,7 +336,7 @@ def test_non_default_kernel_variants_match_goldens():
 
 
 @pytest.mark.parametrize("name,N,W", [("C5", 700, 40), ("C3", 500, 300), ("C4", 1300, 9), ("C5", 2100, 5), ("C4M", 1024, 3),
-                                      ("C5", 384, 200), ("C2", 330, 160)])
+                                      ("C5", 384, 200), ("C2", 330, 160), ("C5", 8192, 3), ("C5", 16384, 1)])
 def test_dataflow_kernel_is_bitwise_the_launch_per_column_path(name, N, W):
     """The persistent dataflow kernel (csrc/dag.cuh, tiled_impl = 2) sums every element in the order of the
     launch-per-column loop (tiled_impl = 1): log L and status must be bitwise identical, for ensembles larger and smaller
@@ -358,9 +358,10 @@ def test_dataflow_kernel_is_bitwise_the_launch_per_column_path(name, N, W):
     assert np.all(out[1][1] == 0)
     np.testing.assert_array_equal(out[1][0], out[2][0])
     np.testing.assert_array_equal(out[1][1], out[2][1])
-    want = port.logL_batch(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["hp"][:2], cfg["model_list"], cfg["modpar"][:2],
-                           cfg["prior_list"], cfg["flags"], textbook_matern5=bool(cfg["kernel_variant"]))
-    assert relerr(out[2][0][:2], want) < RTOL
+    if N <= 4096:      # (larger sizes are pinned by the reference scalars of tests/golden/big_cases.json, see the test above)
+        want = port.logL_batch(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["hp"][:2], cfg["model_list"], cfg["modpar"][:2],
+                               cfg["prior_list"], cfg["flags"], textbook_matern5=bool(cfg["kernel_variant"]))
+        assert relerr(out[2][0][:2], want) < RTOL
 
 
 def test_streamed_panel_path_persistent_slots():
