@@ -888,7 +888,11 @@ static int host_logl_enqueue(mrv_problem* p, const double* hp, const double* mod
   // attributes), the second is captured, later ones are one cudaGraphLaunch.  Any reallocation or option change drops it.
   const int64_t Wsel = p->ensemble_opt > 0 ? std::max<int64_t>(p->ensemble_opt, W) : W;
   const int path_now = choose_path(p, Wsel);
-  const bool graphable = p->graph_opt && !model_y && !p->prof.on && (path_now == MRV_PATH_FUSED_SMEM || path_now == MRV_PATH_MID);
+  // (the tiled path qualifies when it runs as the dataflow kernel: phase table -> mean -> one kernel per wave -> finalize on
+  // one stream, workspaces sized by the first, eager call; at C3 the five launches + two copies cost 0.1 ms of a 1.08 ms call)
+  const bool graphable = p->graph_opt && !model_y && !p->prof.on &&
+                         (path_now == MRV_PATH_FUSED_SMEM || path_now == MRV_PATH_MID ||
+                          (path_now == MRV_PATH_BLOCKED && use_dag(p) && p->nt <= 32));
   const bool same_key = graphable && p->graph_W == W && p->graph_to_ecc == to_ecc && p->graph_buf_gen == g_buf_gen &&
                         p->graph_opt_gen == p->opt_gen && p->graph_ens == p->ensemble_opt;
   if (same_key && p->graph_state == 2) {

@@ -559,21 +559,24 @@ def test_solve_multi_factors_once_and_matches_scipy(N, R):
     prob.close()
 
 
-@pytest.mark.parametrize("name,W", [("C1", 100), ("C2", 37), ("C3", 48)])
+@pytest.mark.parametrize("name,W", [("C1", 100), ("C2", 37), ("C3", 48), ("C3tiled", 48), ("C5tiled", 20)])
 def test_cuda_graph_replay_of_the_host_buffer_call(name, W):
-    """mrv_logl_batch on the one-CTA-per-walker paths replays copy in -> kernel(s) -> copy out as one CUDA graph from the
-    third identical call on; values are bitwise those of the eager call, new parameters flow through the pinned staging
-    buffer, and a different ensemble size or an option change drops the graph."""
-    cfg = workloads.make_config(name, W=W)
+    """mrv_logl_batch on the one-CTA-per-walker paths -- and on the tiled path when it runs as the dataflow kernel (up to 32
+    tile columns) -- replays copy in -> kernel(s) -> copy out as one CUDA graph from the third identical call on; values are
+    bitwise those of the eager call, new parameters flow through the pinned staging buffer, and a different ensemble size or
+    an option change drops the graph."""
+    tiled = name.endswith("tiled")
+    name = name.replace("tiled", "")
+    cfg = workloads.make_config(name, W=W, N=1300) if name == "C5" else workloads.make_config(name, W=W)
     prob = engine.LikelihoodProblem(cfg["t"], cfg["y"], cfg["yerr"], cfg["kernel"], cfg["model_list"], cfg["prior_list"],
                                     flags=cfg["flags"])
     prob.set_option("cuda_graph", 0)
-    if name == "C3":
-        prob.set_option("path", 3)      # N = 500 is on the tiled path by default (round 2); the replay is a feature of paths 1 and 3
+    if name == "C3" and not tiled:
+        prob.set_option("path", 3)      # N = 500 is on the tiled path by default (round 2)
     eager, st = prob.logl(cfg["hp"], cfg["modpar"])
     hp2 = cfg["hp"] * (1.0 + 1e-3)
     eager2, _ = prob.logl(hp2, cfg["modpar"])
-    assert np.all(st == 0) and prob.info("path") in (1, 3) and prob.info("graph_replays") == 0
+    assert np.all(st == 0) and prob.info("path") in ((2,) if tiled else (1, 3)) and prob.info("graph_replays") == 0
     prob.set_option("cuda_graph", 1)
     for i in range(5):
         got, st = prob.logl(cfg["hp"] if i % 2 == 0 else hp2, cfg["modpar"])
