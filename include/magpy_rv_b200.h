@@ -215,7 +215,14 @@ int64_t mrv_stretch_split(const double* u, int64_t n_u, int64_t chain_begin, int
 
 /* Introspection / tuning (no reference counterpart). */
 enum { MRV_PATH_AUTO = 0, MRV_PATH_FUSED_SMEM = 1, MRV_PATH_BLOCKED = 2, MRV_PATH_MID = 3 };
-int mrv_set_option(mrv_problem* p, const char* key, int64_t value); /* "path", "wave_walkers", "panel_tiles" */
+/* Option keys: "path" (MRV_PATH_*; automatic by N and ensemble size), "tiled_impl" (0 automatic = persistent dataflow kernel for
+ * 3 ... 128 tile columns, 1 launch-per-column loop, 2 dataflow kernel), "wave_walkers", "ensemble_walkers" (size of the whole
+ * ensemble when this handle evaluates one shard of it: kernel selection then does not depend on the number of shards),
+ * "cuda_graph" (replay of the host-buffer call), "profile" (CUDA-event timers per kernel category, read with "prof_*" infos),
+ * and tuning knobs of the launch-per-column path / the fused kernel ("panel_tiles", "panel_inner", "update_band", "substreams",
+ * "potrf_impl", "mean_overlap", "mean_threads", "small_minb", "small_blk_min").  Results never depend on them beyond the
+ * documented 1e-9 (bitwise for everything but "path" and "potrf_impl"). */
+int mrv_set_option(mrv_problem* p, const char* key, int64_t value);
 int64_t mrv_get_info(mrv_problem* p, const char* key); /* "path", "launches", "wave_walkers", "n_pad", "workspace_bytes" */
 int mrv_device_count(void);
 const char* mrv_last_error(void);
