@@ -656,7 +656,7 @@ template <int NW, int MAXT, bool WITH_INV, bool PACKED>
 __device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, const int n_n8, const int k0, const int tm0,
                                                      const int tm1, const double* PA, const int pa_ld, const double* PB,
                                                      const int pb_ld, const int wi, const int gq, const int tig,
-                                                     const int tn_min = 0) {
+                                                     const int tn_ex = -8) {   // row tiles tn_ex, tn_ex + 1 are somebody else's
   const int c_begin = k0 + PB_NB;
   constexpr int SLOTS = (MAXT + NW - 1) / NW;     // n_n8 <= MAXT row tiles (rows + the residual row)
   int rho0s[SLOTS];
@@ -666,7 +666,7 @@ __device__ __forceinline__ void sweep_trailing_tiles(double* S, const int ld, co
   for (int sl = 0; sl < SLOTS; ++sl) {
     const int tn = wi + NW * sl;
     rho0s[sl] = tn * 8;
-    live[sl] = tn < n_n8 && tn >= tn_min && (WITH_INV || rho0s[sl] + 7 >= c_begin);
+    live[sl] = tn < n_n8 && (tn < tn_ex || tn > tn_ex + 1) && (WITH_INV || rho0s[sl] + 7 >= c_begin);
     pivot[sl] = rho0s[sl] >= k0 && rho0s[sl] < k0 + PB_NB;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) bfr[sl][kk] = live[sl] ? PA[(kk * 4 + tig) * pa_ld + rho0s[sl] + gq] : 0.0;
@@ -802,11 +802,14 @@ __device__ __forceinline__ void bar_sync_panel() { asm volatile("bar.sync 2, 256
 template <bool PACKED>
 __device__ __forceinline__ void sweep_panel_tile(double* S, const int ld, const int n_cols, const int n_rows, const int k0,
                                                  const int rho0, const double (&gt0)[4], const double (&gt1)[4], double* PA,
-                                                 const int pa_ld, double* PB, const int pb_ld, const double* wv, const int gq,
-                                                 const int tig) {
+                                                 const int pa_ld, double* PB, const int pb_ld, const double* D, const double* wv,
+                                                 const int gq, const int tig) {
+  const bool pivot_tile = rho0 >= k0 && rho0 < k0 + PB_NB;   // (only with the inverse kept: D = the swept pivot block)
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  if (!pivot_tile) {
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) dmma_1684_neg0(acc, gt0[kk], gt1[kk], sweep_colp<PACKED>(S, ld, k0 + 4 * kk + tig)[rho0 + gq]);
+    for (int kk = 0; kk < 4; ++kk) dmma_1684_neg0(acc, gt0[kk], gt1[kk], sweep_colp<PACKED>(S, ld, k0 + 4 * kk + tig)[rho0 + gq]);
+  }
   const int rhoA = rho0 + 2 * tig;                       // this lane's two rows: rhoA, rhoA + 1
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -814,9 +817,15 @@ __device__ __forceinline__ void sweep_panel_tile(double* S, const int ld, const 
     double2 x;
     x.x = acc[2 * h];
     x.y = acc[2 * h + 1];
-    if (rhoA >= n_rows) x.x = 0.0;                     // padding rows below the residual row stay zero
-    if (rhoA + 1 >= n_rows) x.y = 0.0;
-    *reinterpret_cast<double2*>(sweep_colp<PACKED>(S, ld, k0 + j) + rhoA) = x;
+    if (pivot_tile) {
+      const int r0 = rhoA - k0, r1 = r0 + 1;
+      x.x = (j == r0) ? 1.0 : (j > r0 ? D[r0 * PB_D_LD + j] : 0.0);
+      x.y = (j == r1) ? 1.0 : (j > r1 ? D[r1 * PB_D_LD + j] : 0.0);
+    } else {
+      if (rhoA >= n_rows) x.x = 0.0;                     // padding rows below the residual row stay zero
+      if (rhoA + 1 >= n_rows) x.y = 0.0;
+      *reinterpret_cast<double2*>(sweep_colp<PACKED>(S, ld, k0 + j) + rhoA) = x;
+    }
     *reinterpret_cast<double2*>(PA + j * pa_ld + rhoA) = x;
     if (rhoA < n_cols) {
       const double w = wv[j];
@@ -828,9 +837,10 @@ __device__ __forceinline__ void sweep_panel_tile(double* S, const int ld, const 
   }
 }
 
-template <bool PACKED, int MAXT>
+template <bool WITH_INV, bool PACKED, int MAXT>
 __device__ inline void cta_block_sweep_cp(double* S, const int ld, int n_cols, double* PA, const int pa_ld, double* PB,
-                                          const int pb_ld, double* D2 /* 2 x PB_NB x PB_D_LD */, double* wv2 /* 2 x PB_NB */) {
+                                          const int pb_ld, double* D2 /* 2 x PB_NB x PB_D_LD */, double* wv2 /* 2 x PB_NB */,
+                                          PhaseTimer* ptm = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gq = lane >> 2, tig = lane & 3;
   const int n_rows = n_cols + 1;                 // + residual row
@@ -839,12 +849,14 @@ __device__ inline void cta_block_sweep_cp(double* S, const int ld, int n_cols, d
   const int nblk = n_cols / PB_NB;
   if (warp < 2) sweep_pivot_block64<PACKED>(S, ld, 0, D2, wv2, tid);
   __syncthreads();
+  if (ptm) ptm->mark(8);
   for (int kb = 0; kb < nblk; ++kb) {
     const int k0 = kb * PB_NB, c_begin = k0 + PB_NB;
     const double* D = D2 + (kb & 1) * (PB_NB * PB_D_LD);
     const double* wv = wv2 + (kb & 1) * PB_NB;
     const bool last = c_begin >= n_cols;           // no trailing columns: only the residual row's panel entries remain
-    const int tn0 = c_begin / 8;                   // first row tile below the pivot block (factor rows only: nothing above counts)
+    const int tn0 = c_begin / 8;                   // first row tile below the pivot block
+    const int tn_first = WITH_INV ? 0 : tn0;       // factor rows only: nothing at or above the pivot block counts
     double gt0[4], gt1[4];   // G^T fragments: rows j = gq and gq + 8, columns jp = 4 kk + tig
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -853,11 +865,11 @@ __device__ inline void cta_block_sweep_cp(double* S, const int ld, int n_cols, d
       gt1[kk] = (jp < gq + 8) ? D[jp * PB_D_LD + gq + 8] : (jp == gq + 8 ? 1.0 : 0.0);
     }
     if (last) {
-      for (int tn = tn0 + warp; tn < n_n8; tn += 8) sweep_panel_tile<PACKED>(S, ld, n_cols, n_rows, k0, tn * 8, gt0, gt1, PA, pa_ld, PB, pb_ld, wv, gq, tig);
+      for (int tn = tn_first + warp; tn < n_n8; tn += 8) sweep_panel_tile<PACKED>(S, ld, n_cols, n_rows, k0, tn * 8, gt0, gt1, PA, pa_ld, PB, pb_ld, D, wv, gq, tig);
     } else if (warp < 2) {
       // ---- the chain: rows / columns of the next pivot block only ----
       const int rho0 = c_begin + 8 * warp;
-      sweep_panel_tile<PACKED>(S, ld, n_cols, n_rows, k0, rho0, gt0, gt1, PA, pa_ld, PB, pb_ld, wv, gq, tig);
+      sweep_panel_tile<PACKED>(S, ld, n_cols, n_rows, k0, rho0, gt0, gt1, PA, pa_ld, PB, pb_ld, D, wv, gq, tig);
       __threadfence_block();
       bar_arrive_panel();                          // warps 2-7 may now read these panel rows
       bar_sync_pivot64();                          // ... and so may the other warp of the pair
@@ -885,17 +897,20 @@ __device__ inline void cta_block_sweep_cp(double* S, const int ld, int n_cols, d
       sweep_pivot_block64<PACKED>(S, ld, c_begin, D2 + ((kb + 1) & 1) * (PB_NB * PB_D_LD), wv2 + ((kb + 1) & 1) * PB_NB, tid);
     } else {
       // ---- everything else of step kb ----
-      for (int tn = tn0 + 2 + (warp - 2); tn < n_n8; tn += 6)
-        sweep_panel_tile<PACKED>(S, ld, n_cols, n_rows, k0, tn * 8, gt0, gt1, PA, pa_ld, PB, pb_ld, wv, gq, tig);
+      for (int i = tn_first + (warp - 2); i < n_n8 - 2; i += 6) {
+        const int tn = i < tn0 ? i : i + 2;        // every row tile but the chain's two
+        sweep_panel_tile<PACKED>(S, ld, n_cols, n_rows, k0, tn * 8, gt0, gt1, PA, pa_ld, PB, pb_ld, D, wv, gq, tig);
+      }
       __threadfence_block();
       bar_sync_panel();                            // all panel rows of the step are in PA / PB (named barrier 2: 64 arrive, 192 wait)
       const int n_m16 = (n_cols - c_begin) / 16;
       // the next pivot block's columns, rows below that block (its own 16 rows are the chain's) ...
-      sweep_trailing_tiles<6, MAXT, false, PACKED>(S, ld, n_n8, k0, 0, 1, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig, tn0 + 2);
+      sweep_trailing_tiles<6, MAXT, WITH_INV, PACKED>(S, ld, n_n8, k0, 0, 1, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig, tn0);
       // ... and every column behind it
-      sweep_trailing_tiles<6, MAXT, false, PACKED>(S, ld, n_n8, k0, 1, n_m16, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig);
+      sweep_trailing_tiles<6, MAXT, WITH_INV, PACKED>(S, ld, n_n8, k0, 1, n_m16, PA, pa_ld, PB, pb_ld, warp - 2, gq, tig);
     }
     __syncthreads();
+    if (ptm) ptm->mark(10);
   }
 }
 

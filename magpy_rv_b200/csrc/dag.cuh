@@ -65,7 +65,7 @@ struct DagArgs {
 #define DAG_AUTO_MIN_TILES 3
 #define DAG_MAX_TILES 128             // N <= 16384 (task decoding and the progress counters are sized for it)
 #define DAG_BSTAGES 3                 // ring of inv(L_kk) k16 slices for the solve phase
-#define DAG_SWEEP_DOUBLES (PB_LD * TILE + PB_NB * PB_PA_LD + PB_NB * PB_PB_LD + PB_NB * PB_D_LD + PB_NB + 64 + TILE)
+#define DAG_SWEEP_DOUBLES (PB_LD * TILE + PB_NB * PB_PA_LD + PB_NB * PB_PB_LD + 2 * (PB_NB * PB_D_LD + PB_NB) + 64 + TILE)
 #define DAG_R1_OFFSET (GEMM_TMA_STAGES * GEMM_STAGE_DOUBLES)   // doubles: end of the update ring / C tile
 #define DAG_SOLVE_DOUBLES (DAG_R1_OFFSET + DAG_BSTAGES * SLICE_ELEMS)
 #define DAG_MAIN_DOUBLES (DAG_SWEEP_DOUBLES > DAG_SOLVE_DOUBLES ? DAG_SWEEP_DOUBLES : DAG_SOLVE_DOUBLES)
@@ -85,7 +85,7 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 }
 // experiment switches (tools/build_variant.py): defaults are the measured best
 #ifndef DAG_SWEEP_LOOKAHEAD
-#define DAG_SWEEP_LOOKAHEAD 1   // diagonal-tile sweep with the next pivot block overlapped with the trailing update (blocked.cuh)
+#define DAG_SWEEP_LOOKAHEAD 1   // diagonal-tile sweep: 1 = next pivot block overlapped with the trailing update; 2 = warps 0-1 own the whole pivot chain (blocked.cuh; measured +1...2.5 % up to 5 tile columns, -0.5 % at 32: not the default)
 #endif
 #ifdef DAG_KEEP_THREADFENCE
 #define DAG_PRE_RELEASE_FENCE() __threadfence()
@@ -404,8 +404,8 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
   double* PA = S + (size_t)PB_LD * TILE;
   double* PBm = PA + PB_NB * PB_PA_LD;
   double* Dm = PBm + PB_NB * PB_PB_LD;
-  double* wv = Dm + PB_NB * PB_D_LD;
-  double* red = wv + PB_NB;
+  double* wv = Dm + 2 * PB_NB * PB_D_LD;          // (pivot-block buffers double-buffered: cta_block_sweep_cp)
+  double* red = wv + 2 * PB_NB;
   int* ired = (int*)(red + 32);
   double* isd_s = red + 64;
   double* pts = smem + DAG_MAIN_DOUBLES;          // never aliased: 2 x (rows t, C, S | cols t, C, S | constants)
@@ -798,7 +798,9 @@ __global__ void __launch_bounds__(DAG_THREADS, 1) tile_dag_kernel(DagArgs g) {
         }
         __syncthreads();
         tm.mark(7);
-#if DAG_SWEEP_LOOKAHEAD
+#if DAG_SWEEP_LOOKAHEAD == 2
+        cta_block_sweep_cp<true, false, 17>(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, Dm, wv, &tm);
+#elif DAG_SWEEP_LOOKAHEAD
         cta_block_sweep_la(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, Dm, wv, &tm);
 #else
         cta_block_sweep<true, DAG_THREADS / 32>(S, PB_LD, TILE, PA, PB_PA_LD, PBm, PB_PB_LD, Dm, wv, &tm);

@@ -277,7 +277,7 @@ fused_small_blk_kernel(ProblemDesc D, const double* __restrict__ t, const double
 #ifdef SMALL_SWEEP_LA
   cta_block_sweep_la<false, true, (MINB >= 4 ? 9 : (MINB == 3 ? 11 : 19))>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
 #else
-  cta_block_sweep_cp<true, (MINB >= 4 ? 9 : (MINB == 3 ? 11 : 19))>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
+  cta_block_sweep_cp<false, true, (MINB >= 4 ? 9 : (MINB == 3 ? 11 : 19))>(S, ld, nc, PA, pa_ld, PBm, pb_ld, Dblk, wv);
 #endif
 #endif
 
