@@ -85,7 +85,7 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 }
 // experiment switches (tools/build_variant.py): defaults are the measured best
 #ifndef DAG_SWEEP_LOOKAHEAD
-#define DAG_SWEEP_LOOKAHEAD 1   // diagonal-tile sweep: 1 = next pivot block overlapped with the trailing update; 2 = warps 0-1 own the whole pivot chain (blocked.cuh; measured +1...2.5 % up to 5 tile columns, -0.5 % at 32: not the default)
+#define DAG_SWEEP_LOOKAHEAD 1   // diagonal-tile sweep: 1 = next pivot block overlapped with the trailing update; 2 = warps 0-1 own the whole pivot chain (blocked.cuh; measured +1.2...2.5 % up to 8 tile columns, -0.55 % at 32, and selecting between the two by size costs the large sizes 0.4 % through code size alone: not the default)
 #endif
 #ifdef DAG_KEEP_THREADFENCE
 #define DAG_PRE_RELEASE_FENCE() __threadfence()
